@@ -1,0 +1,453 @@
+// linalg.cuh -- batched dense FP64 kernels of the tiled (global-memory) path:
+// gemv, SYRK on the DMMA tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4),
+// blocked right-looking Cholesky (panel kernel + DMMA trailing update) and
+// blocked triangular solves.  Column-major everywhere, batch = slowest index.
+//
+// They replace the LAPACK/BLAS calls of the reference's dense back end:
+// mul! (src/densesolver.jl:42-43,49-50,66,73,83-86), cholesky! (:47,:51) and
+// ldiv! (:48,:75).
+#pragma once
+#include "common.cuh"
+
+namespace socp {
+
+// ------------------------------------------------------------------ cp.async
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;   // src-size 0 => zero fill, no global read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------
+// gemv, transposed:  out[c] = sum_r M[r,c] x[r]  (+ c1*v1[c] + c2*v2[c] [+ out[c]])
+// grid (ceil(cols/8), batch), block 256: one warp per column, lanes over rows.
+// ---------------------------------------------------------------------------
+struct GemvEpi {
+    const double* v1; double c1; int64_t s1;
+    const double* v2; double c2; int64_t s2;
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(256)
+k_gemv_t(const double* __restrict__ M, int64_t strideM, int ld, int rows, int cols,
+         const double* __restrict__ x, int64_t strideX, double* __restrict__ out, int64_t strideOut,
+         double alpha, GemvEpi epi, const int* __restrict__ active, const uint8_t* __restrict__ flag) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    if (flag && !flag[b]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;
+    if (c >= cols) return;
+    const double* col = M + (int64_t)b * strideM + (int64_t)c * ld;
+    const double* xb = x + (int64_t)b * strideX;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = lane;
+    for (; r + 96 < rows; r += 128) {
+        a0 = fma(col[r], xb[r], a0);
+        a1 = fma(col[r + 32], xb[r + 32], a1);
+        a2 = fma(col[r + 64], xb[r + 64], a2);
+        a3 = fma(col[r + 96], xb[r + 96], a3);
+    }
+    for (; r < rows; r += 32) a0 = fma(col[r], xb[r], a0);
+    double acc = alpha * warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) {
+        if (epi.v1) acc += epi.c1 * epi.v1[(int64_t)b * epi.s1 + c];
+        if (epi.v2) acc += epi.c2 * epi.v2[(int64_t)b * epi.s2 + c];
+        double* o = out + (int64_t)b * strideOut + c;
+        if (epi.accumulate) acc += *o;
+        *o = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// gemv, not transposed:  out[r] = sum_c M[r,c] x[c]  (+ epilogue as above)
+// grid (ceil(rows/32), batch), block (32, 8): lane = row, y = column phase.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gemv_n(const double* __restrict__ M, int64_t strideM, int ld, int rows, int cols,
+         const double* __restrict__ x, int64_t strideX, double* __restrict__ out, int64_t strideOut,
+         double alpha, GemvEpi epi, const int* __restrict__ active, const uint8_t* __restrict__ flag) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    if (flag && !flag[b]) return;
+    __shared__ double part[8][33];
+    const int lane = threadIdx.x, ph = threadIdx.y;
+    const int r = blockIdx.x * 32 + lane;
+    const double* Mb = M + (int64_t)b * strideM;
+    const double* xb = x + (int64_t)b * strideX;
+    double a0 = 0.0, a1 = 0.0;
+    if (r < rows) {
+        int c = ph;
+        for (; c + 8 < cols; c += 16) {
+            a0 = fma(Mb[r + (int64_t)c * ld], xb[c], a0);
+            a1 = fma(Mb[r + (int64_t)(c + 8) * ld], xb[c + 8], a1);
+        }
+        for (; c < cols; c += 8) a0 = fma(Mb[r + (int64_t)c * ld], xb[c], a0);
+    }
+    part[ph][lane] = a0 + a1;
+    __syncthreads();
+    if (ph == 0 && r < rows) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc += part[q][lane];
+        acc *= alpha;
+        if (epi.v1) acc += epi.c1 * epi.v1[(int64_t)b * epi.s1 + r];
+        if (epi.v2) acc += epi.c2 * epi.v2[(int64_t)b * epi.s2 + r];
+        double* o = out + (int64_t)b * strideOut + r;
+        if (epi.accumulate) acc += *o;
+        *o = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// SYRK on the FP64 tensor pipe.
+//   KMAJOR = true : A is K x N column-major (ld = lda), C[i,j] = sum_r A[r,i] A[r,j]
+//                   (H = Gt' Gt, reference src/densesolver.jl:42-43)
+//   KMAJOR = false: A is N x K column-major,            C[i,j] = sum_c A[i,c] A[j,c]
+//                   (trailing update of the blocked Cholesky)
+//   C = beta*C + alpha*(...) (+ addC where addFlag[b]) on the lower-triangle TILES
+//   (diagonal tiles are written in full).
+// Tile BT x BT per CTA, NW x NW warps each owning a (BT/NW)^2 sub-tile made of
+// m8n8k4 DMMAs; operands staged through shared memory with a 3-stage cp.async
+// ring.  Requirements: A 16-byte aligned, lda even; KMAJOR: K % KT == 0 with the
+// pad rows of A zero.
+// grid (ntiles*(ntiles+1)/2, batch).
+// ---------------------------------------------------------------------------
+template <int BT, int NW, int KT, bool KMAJOR>
+struct SyrkCfg {
+    static constexpr int THREADS = NW * NW * 32;
+    static constexpr int WT = BT / NW;          // warp tile edge
+    static constexpr int MT = WT / 8;           // 8x8 mma tiles per warp-tile edge
+    static constexpr int STAGES = 3;
+    // KMAJOR: tile stored [col][r], r contiguous, row stride KT+4 (== 4 mod 16 for KT=16/32)
+    // else  : tile stored [c][i],  i contiguous, row stride BT+4
+    static constexpr int TS_ROWS = KMAJOR ? BT : KT;
+    static constexpr int TS_LD = KMAJOR ? (KT + 4) : (BT + 4);
+    static constexpr int TILE_DOUBLES = TS_ROWS * TS_LD;
+    static constexpr size_t SMEM = (size_t)STAGES * 2 * TILE_DOUBLES * sizeof(double);
+};
+
+template <int BT, int NW, int KT, bool KMAJOR>
+__global__ void __launch_bounds__(NW * NW * 32)
+k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
+       double* __restrict__ C, int64_t strideC, int ldc, double alpha, double beta,
+       const double* __restrict__ addC, int64_t strideAdd, int ldadd, const uint8_t* __restrict__ addFlag,
+       const int* __restrict__ active) {
+    using Cfg = SyrkCfg<BT, NW, KT, KMAJOR>;
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    // lower-triangle tile index -> (ti, tj), ti >= tj
+    int t = blockIdx.x;
+    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int i0 = ti * BT, j0 = tj * BT;
+    const bool diag = (ti == tj);
+
+    extern __shared__ __align__(16) double smem[];
+    const double* Ab = A + (int64_t)b * strideA;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = warp / NW, wc = warp % NW;
+    const int nk = (K + KT - 1) / KT;
+
+    auto tileA = [&](int s) { return smem + (size_t)s * 2 * Cfg::TILE_DOUBLES; };
+    auto tileB = [&](int s) { return smem + (size_t)s * 2 * Cfg::TILE_DOUBLES + Cfg::TILE_DOUBLES; };
+
+    auto load_stage = [&](int s, int kb) {
+        const int r0 = kb * KT;
+        if (KMAJOR) {
+            // BT columns x KT rows, 16B chunks along r
+            constexpr int CH = KT / 2;
+            for (int q = tid; q < BT * CH; q += Cfg::THREADS) {
+                const int col = q / CH, ch = q % CH;
+                const int r = r0 + ch * 2;
+                {
+                    const int gc = i0 + col;
+                    const bool ok = (gc < N) && (r < K);
+                    cp_async16(tileA(s) + col * Cfg::TS_LD + ch * 2, Ab + (int64_t)gc * lda + r, ok);
+                }
+                if (!diag) {
+                    const int gc = j0 + col;
+                    const bool ok = (gc < N) && (r < K);
+                    cp_async16(tileB(s) + col * Cfg::TS_LD + ch * 2, Ab + (int64_t)gc * lda + r, ok);
+                }
+            }
+        } else {
+            // KT columns (c) x BT rows (i), 16B chunks along i
+            constexpr int CH = BT / 2;
+            for (int q = tid; q < KT * CH; q += Cfg::THREADS) {
+                const int c = q / CH, ch = q % CH;
+                const int gc = r0 + c;
+                {
+                    const int gi = i0 + ch * 2;
+                    const bool ok = (gc < K) && (gi < N);
+                    cp_async16(tileA(s) + c * Cfg::TS_LD + ch * 2, Ab + (int64_t)gc * lda + gi, ok);
+                }
+                if (!diag) {
+                    const int gi = j0 + ch * 2;
+                    const bool ok = (gc < K) && (gi < N);
+                    cp_async16(tileB(s) + c * Cfg::TS_LD + ch * 2, Ab + (int64_t)gc * lda + gi, ok);
+                }
+            }
+        }
+    };
+
+    double acc[Cfg::MT][Cfg::MT][2];
+#pragma unroll
+    for (int a = 0; a < Cfg::MT; ++a)
+#pragma unroll
+        for (int c = 0; c < Cfg::MT; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+
+    // prologue
+#pragma unroll
+    for (int s = 0; s < Cfg::STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kb = 0; kb < nk; ++kb) {
+        cp_async_wait<Cfg::STAGES - 2>();
+        __syncthreads();
+        {   // prefetch stage kb + STAGES-1 into the slot consumed at iteration kb-1
+            const int nxt = kb + Cfg::STAGES - 1;
+            if (nxt < nk) load_stage(nxt % Cfg::STAGES, nxt);
+            cp_async_commit();
+        }
+        const int s = kb % Cfg::STAGES;
+        const double* ta = tileA(s);
+        const double* tb = diag ? tileA(s) : tileB(s);
+        const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll
+        for (int kk = 0; kk < KT; kk += 4) {
+            double af[Cfg::MT], bf[Cfg::MT];
+#pragma unroll
+            for (int a = 0; a < Cfg::MT; ++a) {
+                const int row = wr * Cfg::WT + a * 8 + fr;
+                af[a] = KMAJOR ? ta[row * Cfg::TS_LD + kk + fk] : ta[(kk + fk) * Cfg::TS_LD + row];
+            }
+#pragma unroll
+            for (int c = 0; c < Cfg::MT; ++c) {
+                const int col = wc * Cfg::WT + c * 8 + fr;
+                bf[c] = KMAJOR ? tb[col * Cfg::TS_LD + kk + fk] : tb[(kk + fk) * Cfg::TS_LD + col];
+            }
+#pragma unroll
+            for (int a = 0; a < Cfg::MT; ++a)
+#pragma unroll
+                for (int c = 0; c < Cfg::MT; ++c) dmma884(acc[a][c][0], acc[a][c][1], af[a], bf[c]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: C fragment layout of m8n8k4: row = lane/4, cols = 2*(lane%4) + {0,1}
+    double* Cb = C + (int64_t)b * strideC;
+    const bool add = addC && (!addFlag || addFlag[b]);
+    const double* Ad = add ? addC + (int64_t)b * strideAdd : nullptr;
+#pragma unroll
+    for (int a = 0; a < Cfg::MT; ++a)
+#pragma unroll
+        for (int c = 0; c < Cfg::MT; ++c) {
+            const int gi = i0 + wr * Cfg::WT + a * 8 + (lane >> 2);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = j0 + wc * Cfg::WT + c * 8 + 2 * (lane & 3) + e;
+                if (gi < N && gj < N) {
+                    double v = alpha * acc[a][c][e];
+                    double* dst = Cb + (int64_t)gj * ldc + gi;
+                    if (beta != 0.0) v += beta * (*dst);
+                    if (add) v += Ad[(int64_t)gj * ldadd + gi];
+                    *dst = v;
+                }
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------
+// Blocked Cholesky, panel step (lower, in place, column-major, ld = ldh).
+// For panel starting at column j (width jb = min(NB, n-j)):
+//   every CTA factors the jb x jb diagonal block in shared memory (redundantly);
+//   CTA x == 0 writes it back; CTA x owns rows j+NB+128x .. +128 of the
+//   sub-panel and solves  L21 = A21 L11^-T  with one thread per row (row in
+//   registers).  fail[b] |= 1 on a pivot that is not > 0 (LAPACK dpotrf's info>0,
+//   Julia's PosDefException, reference src/densesolver.jl:47,51).
+// grid (max(1, ceil((n-j-NB)/128)), batch), block 128.
+// ---------------------------------------------------------------------------
+constexpr int CHOL_NB = 64;
+
+__global__ void __launch_bounds__(128)
+k_potrf_panel(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, int* __restrict__ fail,
+              const int* __restrict__ active) {
+    constexpr int NB = CHOL_NB;
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    __shared__ double D[NB][NB + 1];
+    __shared__ int sfail;
+    double* Hb = H + (int64_t)b * strideH;
+    const int jb = min(NB, n - j);
+    const int tid = threadIdx.x;
+    if (tid == 0) sfail = 0;
+    for (int q = tid; q < jb * jb; q += 128) {
+        const int r = q % jb, c = q / jb;
+        D[r][c] = (r >= c) ? Hb[(int64_t)(j + c) * ldh + j + r] : 0.0;
+    }
+    __syncthreads();
+    for (int c = 0; c < jb; ++c) {
+        const double piv = D[c][c];
+        if (!(piv > 0.0)) {            // uniform across the CTA
+            if (tid == 0) sfail = 1;
+            break;
+        }
+        const double rdiag = sqrt(piv);
+        __syncthreads();               // everyone has read D[c][c]
+        for (int r = c + tid; r < jb; r += 128) D[r][c] = (r == c) ? rdiag : D[r][c] / rdiag;
+        __syncthreads();
+        // trailing update of the lower triangle: (r, cc) with c < cc <= r < jb
+        const int m = jb - c - 1;
+        for (int q = tid; q < m * m; q += 128) {
+            const int rr = q % m, cq = q / m;
+            if (rr >= cq) {
+                const int r = c + 1 + rr, cc = c + 1 + cq;
+                D[r][cc] = fma(-D[r][c], D[cc][c], D[r][cc]);
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (sfail) {
+        if (tid == 0 && blockIdx.x == 0) fail[b] = 1;
+        return;
+    }
+    if (blockIdx.x == 0) {
+        for (int q = tid; q < jb * jb; q += 128) {
+            const int r = q % jb, c = q / jb;
+            if (r >= c) Hb[(int64_t)(j + c) * ldh + j + r] = D[r][c];
+        }
+    }
+    if (jb < NB) return;               // last (ragged) panel has no rows below
+    const int row = j + NB + blockIdx.x * 128 + tid;
+    if (row >= n) return;
+    double a[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) a[c] = Hb[(int64_t)(j + c) * ldh + row];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        double v = a[c];
+#pragma unroll
+        for (int q = 0; q < c; ++q) v = fma(-a[q], D[c][q], v);
+        a[c] = v / D[c][c];
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) Hb[(int64_t)(j + c) * ldh + row] = a[c];
+}
+
+// ---------------------------------------------------------------------------
+// Triangular solves with the Cholesky factor, in place on X (n x nrhs, ld = ldx):
+//   k_trsv_fwd:  X <- L^-1 X        k_trsv_bwd:  X <- L^-T X
+// One CTA (256 threads) per (rhs, problem); the right-hand side lives in shared
+// memory (n doubles, dynamic).  Blocks of 32: the diagonal block is solved by
+// warp 0 with shuffles; the off-diagonal part is a coalesced gemv.
+// grid (nrhs, batch), dynamic smem = n * 8.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_trsv_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n,
+           double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    extern __shared__ double xs[];
+    const double* Lb = L + (int64_t)b * strideL;
+    double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
+    __syncthreads();
+    for (int jb = 0; jb < n; jb += 32) {
+        const int w = min(32, n - jb);
+        if (warp == 0) {
+            // lane i owns row jb+i of the diagonal block
+            double lrow[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                lrow[c] = (lane < w && c <= lane && c < w) ? Lb[(int64_t)(jb + c) * ldl + jb + lane] : 0.0;
+            double x = (lane < w) ? xs[jb + lane] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                if (lane == c && c < w) x = x / lrow[c];
+                const double xc = __shfl_sync(FULL_MASK, x, c);
+                if (lane > c && lane < w) x = fma(-lrow[c], xc, x);
+            }
+            if (lane < w) xs[jb + lane] = x;
+        }
+        __syncthreads();
+        // rows below the block: xs[r] -= sum_c L[r, jb+c] xs[jb+c]
+        for (int r = jb + 32 + tid; r < n; r += 256) {
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < 32; c += 2) {
+                acc0 = fma(Lb[(int64_t)(jb + c) * ldl + r], xs[jb + c], acc0);
+                acc1 = fma(Lb[(int64_t)(jb + c + 1) * ldl + r], xs[jb + c + 1], acc1);
+            }
+            xs[r] -= acc0 + acc1;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_trsv_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n,
+           double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    extern __shared__ double xs[];
+    const double* Lb = L + (int64_t)b * strideL;
+    double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
+    __syncthreads();
+    const int nblk = (n + 31) / 32;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int jb = blk * 32;
+        const int w = min(32, n - jb);
+        // left-looking: xs[jb+i] -= sum_{r >= jb+32} L[r, jb+i] xs[r]; warp per column
+        for (int i = warp; i < w; i += 8) {
+            const double* col = Lb + (int64_t)(jb + i) * ldl;
+            double acc0 = 0.0, acc1 = 0.0;
+            int r = jb + 32 + lane;
+            for (; r + 32 < n; r += 64) {
+                acc0 = fma(col[r], xs[r], acc0);
+                acc1 = fma(col[r + 32], xs[r + 32], acc1);
+            }
+            for (; r < n; r += 32) acc0 = fma(col[r], xs[r], acc0);
+            const double acc = warp_sum(acc0 + acc1);
+            if (lane == 0) xs[jb + i] -= acc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // diagonal block, transposed: lane i needs L[jb+c, jb+i] for c >= i
+            double lcol[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+                lcol[c] = (lane < w && c >= lane && c < w) ? Lb[(int64_t)(jb + lane) * ldl + jb + c] : 0.0;
+            double x = (lane < w) ? xs[jb + lane] : 0.0;
+#pragma unroll
+            for (int c = 31; c >= 0; --c) {
+                if (lane == c && c < w) x = x / lcol[c];
+                const double xc = __shfl_sync(FULL_MASK, x, c);
+                if (lane < c && c < w) x = fma(-lcol[c], xc, x);
+            }
+            if (lane < w) xs[jb + lane] = x;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
+}
+
+}  // namespace socp

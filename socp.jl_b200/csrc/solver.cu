@@ -1,0 +1,876 @@
+// solver.cu -- host side of libsocp_b200: device shards, the tiled solve driver
+// (reference src/solver.jl:40-152 over the batch) and the C ABI of
+// include/socp_b200.h.  CUDA runtime only; no torch types, no CPU fallback.
+#include "../../include/socp_b200.h"
+#include "linalg.cuh"
+#include "tiled_kernels.cuh"
+#include "fused_small.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace socp;
+
+namespace {
+
+constexpr int POC_CHUNK = 128;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct CudaErr {
+    int code;
+    std::string msg;
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            char buf_[512];                                                                       \
+            snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                     cudaGetErrorString(e_));                                                     \
+            throw CudaErr{(int)e_, buf_};                                                         \
+        }                                                                                         \
+    } while (0)
+
+struct UsageErr {
+    int code;
+    std::string msg;
+};
+
+// One device's contiguous shard of the batch.
+struct Shard {
+    int device = 0;
+    int64_t first = 0;     // first problem of the shard in the caller's batch
+    int batch = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<void*> allocs;
+    Ws w{};
+    // layout (device copies)
+    int *d_kind = nullptr, *d_offs = nullptr, *d_dim = nullptr;
+    // owned copies of the problem data
+    double *d_c = nullptr, *d_A = nullptr, *d_b = nullptr, *d_G = nullptr, *d_h = nullptr;
+    uint8_t* d_sing = nullptr;
+    int* h_nactive = nullptr;   // pinned
+    int64_t launches = 0;
+    bool have_data = false, have_scaling = false, have_factor = false;
+    bool any_sing = false;
+    bool sharedA = false, sharedG = false;
+    int threads = 256;     // CTA size of the per-problem cone kernels
+    socp_timings tim{};
+    FusedPlan fused{};
+
+    template <class T>
+    T* alloc(size_t count, bool zero = true) {
+        void* p = nullptr;
+        if (count == 0) count = 1;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        allocs.push_back(p);
+        if (zero) CK(cudaMemsetAsync(p, 0, count * sizeof(T), stream));
+        return (T*)p;
+    }
+    void release() {
+        cudaSetDevice(device);
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+        if (h_nactive) cudaFreeHost(h_nactive);
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+struct socp_handle {
+    int n = 0, p = 0, k = 0;
+    std::vector<int> kind, offs, dim;          // caller's cones
+    std::vector<int> wkind, woffs, wdim;       // work cones
+    std::vector<int> first_work;               // caller cone -> first work cone
+    int deg = 0;
+    int64_t batch = 0;
+    std::vector<Shard> shards;
+    std::string err;
+    socp_timings tim{};
+};
+
+namespace {
+
+// ---------------------------------------------------------------- launch helpers
+#define LAUNCH(sh, kern, grid, block, smem, ...)                       \
+    do {                                                               \
+        kern<<<grid, block, smem, (sh).stream>>>(__VA_ARGS__);         \
+        (sh).launches++;                                               \
+    } while (0)
+
+GemvEpi epi(const double* v1 = nullptr, double c1 = 0, int64_t s1 = 0, const double* v2 = nullptr, double c2 = 0,
+            int64_t s2 = 0, int acc = 0) {
+    GemvEpi e;
+    e.v1 = v1; e.c1 = c1; e.s1 = s1;
+    e.v2 = v2; e.c2 = c2; e.s2 = s2;
+    e.accumulate = acc;
+    return e;
+}
+
+// out[cols] = alpha * M' x + epilogue
+void gemv_t(Shard& sh, const double* M, int64_t sM, int ld, int rows, int cols, const double* x, int64_t sx,
+            double* out, int64_t so, double alpha, GemvEpi e, const int* active, const uint8_t* flag = nullptr) {
+    if (cols == 0) return;
+    dim3 grid((cols + 7) / 8, sh.batch);
+    LAUNCH(sh, k_gemv_t, grid, 256, 0, M, sM, ld, rows, cols, x, sx, out, so, alpha, e, active, flag);
+}
+void gemv_n(Shard& sh, const double* M, int64_t sM, int ld, int rows, int cols, const double* x, int64_t sx,
+            double* out, int64_t so, double alpha, GemvEpi e, const int* active, const uint8_t* flag = nullptr) {
+    if (rows == 0) return;
+    dim3 grid((rows + 31) / 32, sh.batch);
+    LAUNCH(sh, k_gemv_n, grid, dim3(32, 8), 0, M, sM, ld, rows, cols, x, sx, out, so, alpha, e, active, flag);
+}
+
+template <int BT, int NW, int KT, bool KM>
+void syrk_launch(Shard& sh, const double* A, int64_t sA, int lda, int N, int K, double* C, int64_t sC, int ldc,
+                 double alpha, double beta, const double* addC, int64_t sAdd, int ldadd, const uint8_t* addFlag,
+                 const int* active) {
+    using Cfg = SyrkCfg<BT, NW, KT, KM>;
+    static bool configured[64] = {};
+    if (!configured[sh.device]) {
+        CK(cudaFuncSetAttribute(k_syrk<BT, NW, KT, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        configured[sh.device] = true;
+    }
+    const int nt = (N + BT - 1) / BT;
+    dim3 grid(nt * (nt + 1) / 2, sh.batch);
+    LAUNCH(sh, (k_syrk<BT, NW, KT, KM>), grid, Cfg::THREADS, Cfg::SMEM, A, sA, lda, N, K, C, sC, ldc, alpha, beta,
+           addC, sAdd, ldadd, addFlag, active);
+}
+void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, int K, double* C, int64_t sC, int ldc,
+          double alpha, double beta, const double* addC, int64_t sAdd, int ldadd, const uint8_t* addFlag,
+          const int* active) {
+    if (N <= 0) return;
+    const bool big = N > 256;
+    if (kmajor) {
+        if (big) syrk_launch<128, 4, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
+        else syrk_launch<64, 2, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
+    } else {
+        if (big) syrk_launch<128, 4, 16, false>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
+        else syrk_launch<64, 2, 16, false>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
+    }
+}
+
+// blocked Cholesky of `nn x nn` matrices (ld, stride), lower, in place
+void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, int* fail, const int* active) {
+    for (int j = 0; j < nn; j += CHOL_NB) {
+        const int below = nn - j - CHOL_NB;
+        dim3 grid(std::max(1, (below + 127) / 128), sh.batch);
+        LAUNCH(sh, k_potrf_panel, grid, 128, 0, H, sH, ld, nn, j, fail, active);
+        if (below > 0) {
+            const double* P = H + (int64_t)j * ld + (j + CHOL_NB);
+            double* T = H + (int64_t)(j + CHOL_NB) * ld + (j + CHOL_NB);
+            syrk(sh, false, P, sH, ld, below, CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active);
+        }
+    }
+}
+// X <- (L L')^-1 X, X is nn x nrhs (ld ldx)
+void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, double* X, int64_t sX, int ldx, int nrhs,
+           const int* active) {
+    if (nn == 0 || nrhs == 0) return;
+    dim3 grid(nrhs, sh.batch);
+    const size_t smem = (size_t)nn * sizeof(double);
+    LAUNCH(sh, k_trsv_fwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
+    LAUNCH(sh, k_trsv_bwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
+}
+
+ConeLayout& LY(Shard& sh) { return sh.w.L; }
+
+// KKT factor, reference src/densesolver.jl:41-52.  identity: W = I (initial point, sing test).
+void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
+    Ws& w = sh.w;
+    const int n = w.L.n, p = w.L.p;
+    const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)) );
+    dim3 g((n + cols_per_cta - 1) / cols_per_cta, sh.batch);
+    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active);
+    const bool aa = add_aa && p > 0 && sh.any_sing;
+    syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0,
+         aa ? w.AA : nullptr, (int64_t)w.ldh * n, w.ldh, w.sing, active);
+    potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, active);
+    if (p > 0) {
+        dim3 gt(std::max(1, std::min(64, (p * n + 255) / 256)), sh.batch);
+        LAUNCH(sh, k_transpose_A, gt, 256, 0, w.A, w.sA, p, n, w.HiAt, active);
+        potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.HiAt, (int64_t)n * p, n, p, active);
+        dim3 gm(std::max(1, std::min(64, (p * p + 255) / 256)), sh.batch);
+        LAUNCH(sh, k_small_gemm, gm, 256, 0, w.A, w.sA, p, n, w.HiAt, w.M, w.ldm, active);
+        potrf(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.fail, active);
+    }
+}
+
+// Middle of solve_kkt, reference src/densesolver.jl:66-85, between kkt_head and
+// kkt_tail.  On entry u = W^-2 k2; on exit rx = cx, ry = cy, u = G cx - k2.
+void kkt_middle(Shard& sh, const int* active) {
+    Ws& w = sh.w;
+    const int n = w.L.n, p = w.L.p, k = w.L.k;
+    // n0 = G'u + dx (+A'dy if sing)                                      :66-71
+    gemv_t(sh, w.G, w.sG, k, k, n, w.u, k, w.rx, n, 1.0, epi(w.dx, 1.0, n), active);
+    if (p > 0 && sh.any_sing)
+        gemv_t(sh, w.A, w.sA, p, p, n, w.dy, p, w.rx, n, 1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active, w.sing);
+    // t = H^-1 n0
+    potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.rx, n, n, 1, active);
+    if (p > 0) {
+        // m0 = A t - dy; cy = M^-1 m0                                     :73-75
+        gemv_n(sh, w.A, w.sA, p, p, n, w.rx, n, w.ry, p, 1.0, epi(w.dy, -1.0, p), active);
+        potrs(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.ry, p, p, 1, active);
+        // cx = H^-1 (n0 + A'(sing ? dy - cy : -cy)) = t - HiAt cy (+ HiAt dy if sing)   :76-83
+        gemv_n(sh, w.HiAt, (int64_t)n * p, n, n, p, w.ry, p, w.rx, n, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
+        if (sh.any_sing)
+            gemv_n(sh, w.HiAt, (int64_t)n * p, n, n, p, w.dy, p, w.rx, n, 1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active, w.sing);
+    }
+    // k1 = G cx - k2                                                      :84-85
+    gemv_n(sh, w.G, w.sG, k, k, n, w.rx, n, w.u, k, 1.0, epi(w.k2, -1.0, k), active);
+}
+
+__global__ void k_kkt_head(Ws w) { kkt_head(w, blockIdx.x); }
+__global__ void k_kkt_tail(Ws w) { kkt_tail(w, blockIdx.x); }
+
+// Initial point, reference src/solver.jl:68-104, by block elimination with W = I
+// (the oracle's initial_point_reduced).
+void initial_point(Shard& sh, const LoopParams& P) {
+    Ws& w = sh.w;
+    const int n = w.L.n, p = w.L.p, k = w.L.k, B = sh.batch;
+    factor(sh, true, true, w.active);
+    LAUNCH(sh, k_finalize, B, 32, 0, w, 0);
+    // n0 = -c + G'h (+A'b if sing)
+    gemv_t(sh, w.G, w.sG, k, k, n, w.h, k, w.x, n, 1.0, epi(w.c, -1.0, n), w.active);
+    if (p > 0 && sh.any_sing)
+        gemv_t(sh, w.A, w.sA, p, p, n, w.b, p, w.x, n, 1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), w.active, w.sing);
+    potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.x, n, n, 1, w.active);          // t = H^-1 n0
+    if (p > 0) {
+        gemv_n(sh, w.A, w.sA, p, p, n, w.x, n, w.y, p, 1.0, epi(w.b, -1.0, p), w.active);   // A t - b
+        potrs(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.y, p, p, 1, w.active);       // y
+        gemv_n(sh, w.HiAt, (int64_t)n * p, n, n, p, w.y, p, w.x, n, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), w.active);
+    }
+    gemv_n(sh, w.G, w.sG, k, k, n, w.x, n, w.z, k, 1.0, epi(w.h, -1.0, k), w.active);       // z0 = G x - h
+    LAUNCH(sh, k_init_shift, B, sh.threads, 0, w, P);
+}
+
+// The Mehrotra loop, reference src/solver.jl:105-151, over the shard.
+void solve_tiled(Shard& sh, const socp_params& prm) {
+    Ws& w = sh.w;
+    const int n = w.L.n, p = w.L.p, k = w.L.k, B = sh.batch;
+    LoopParams P{prm.max_iter, prm.tol, prm.step_damp, prm.init_eps};
+    LAUNCH(sh, k_reset, (B + 255) / 256, 256, 0, w, B);
+    CK(cudaMemsetAsync(w.nactive, 0, sizeof(int) * (prm.max_iter + 2), sh.stream));
+    initial_point(sh, P);
+    int itmax = 0;
+    for (int it = 0; it < prm.max_iter; ++it) {
+        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.eta, w.fail, w.active);   // :106
+        // negated residuals                                                           :110-118,:125
+        gemv_t(sh, w.G, w.sG, k, k, n, w.z, k, w.dx, n, -1.0, epi(w.c, -1.0, n), w.active);
+        if (p > 0) {
+            gemv_t(sh, w.A, w.sA, p, p, n, w.y, p, w.dx, n, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), w.active);
+            gemv_n(sh, w.A, w.sA, p, p, n, w.x, n, w.dy, p, -1.0, epi(w.b, 1.0, p), w.active);
+        }
+        gemv_n(sh, w.G, w.sG, k, k, n, w.x, n, w.dz, k, -1.0, epi(w.s, -1.0, k, w.h, 1.0, k), w.active);
+        LAUNCH(sh, k_pre, B, sh.threads, 0, w, P, it);
+        CK(cudaMemcpyAsync(sh.h_nactive, w.nactive + it, sizeof(int), cudaMemcpyDeviceToHost, sh.stream));
+        CK(cudaStreamSynchronize(sh.stream));
+        if (*sh.h_nactive == 0) break;
+        itmax = it + 1;
+        factor(sh, false, true, w.active);                                              // :126
+        kkt_middle(sh, w.active);                                                       // :127
+        LAUNCH(sh, k_mid, B, sh.threads, 0, w, P);                                     // :128-140
+        kkt_middle(sh, w.active);                                                       // :141
+        LAUNCH(sh, k_post, B, sh.threads, 0, w, P);                                    // :143-150
+    }
+    LAUNCH(sh, k_finalize, B, sh.threads, 0, w, 1);
+    sh.tim.iterations_max = itmax;
+    sh.tim.path_used = SOCP_PATH_TILED;
+}
+
+void build_shard(socp_handle* h, Shard& sh) {
+    CK(cudaSetDevice(sh.device));
+    CK(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+    for (auto& e : sh.ev) CK(cudaEventCreate(&e));
+    const int n = h->n, p = h->p, k = h->k, B = sh.batch;
+    const int nc = (int)h->wkind.size();
+    Ws& w = sh.w;
+    sh.d_kind = sh.alloc<int>(nc);
+    sh.d_offs = sh.alloc<int>(nc);
+    sh.d_dim = sh.alloc<int>(nc);
+    CK(cudaMemcpyAsync(sh.d_kind, h->wkind.data(), nc * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+    CK(cudaMemcpyAsync(sh.d_offs, h->woffs.data(), nc * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+    CK(cudaMemcpyAsync(sh.d_dim, h->wdim.data(), nc * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+    w.L = ConeLayout{n, p, k, nc, h->deg, sh.d_kind, sh.d_offs, sh.d_dim};
+    w.kpad = round_up(std::max(k, 1), 16);
+    w.ldgt = w.kpad;
+    w.ldh = round_up(std::max(n, 1), 2);
+    w.ppad = round_up(std::max(p, 1), 16);
+    w.ldap = w.ppad;
+    w.ldm = round_up(std::max(p, 1), 2);
+    sh.d_c = sh.alloc<double>((size_t)B * n);
+    sh.d_b = sh.alloc<double>((size_t)B * p);
+    sh.d_h = sh.alloc<double>((size_t)B * k);
+    sh.d_A = sh.alloc<double>((size_t)B * p * n);
+    sh.d_G = sh.alloc<double>((size_t)B * k * n);
+    sh.d_sing = sh.alloc<uint8_t>(B);
+    w.c = sh.d_c; w.A = sh.d_A; w.b = sh.d_b; w.G = sh.d_G; w.h = sh.d_h; w.sing = sh.d_sing;
+    w.sA = (int64_t)p * n; w.sG = (int64_t)k * n;
+    w.x = sh.alloc<double>((size_t)B * n);  w.y = sh.alloc<double>((size_t)B * p);
+    w.z = sh.alloc<double>((size_t)B * k);  w.s = sh.alloc<double>((size_t)B * k);
+    w.lam = sh.alloc<double>((size_t)B * k); w.wb = sh.alloc<double>((size_t)B * k);
+    w.eta = sh.alloc<double>((size_t)B * nc);
+    w.dx = sh.alloc<double>((size_t)B * n);  w.dy = sh.alloc<double>((size_t)B * p);
+    w.dz = sh.alloc<double>((size_t)B * k);  w.ds = sh.alloc<double>((size_t)B * k);
+    w.rx = sh.alloc<double>((size_t)B * n);  w.ry = sh.alloc<double>((size_t)B * p);
+    w.rz = sh.alloc<double>((size_t)B * k);  w.rs = sh.alloc<double>((size_t)B * k);
+    w.k0 = sh.alloc<double>((size_t)B * k);  w.k2 = sh.alloc<double>((size_t)B * k);
+    w.u = sh.alloc<double>((size_t)B * k);
+    w.kt2 = sh.alloc<double>((size_t)B * k); w.kt3 = sh.alloc<double>((size_t)B * k);
+    w.sc = sh.alloc<ProbScalars>(B);
+    w.status = sh.alloc<int>(B); w.iters = sh.alloc<int>(B);
+    w.active = sh.alloc<int>(B); w.fail = sh.alloc<int>(B);
+    w.nactive = sh.alloc<int>(4096);
+    CK(cudaMallocHost((void**)&sh.h_nactive, 64));
+    // tiled-path factor workspaces are allocated lazily (ensure_tiled): the fused
+    // path does not need them and they dominate the footprint
+    sh.threads = std::min(256, std::max(32, 32 * nc));
+    fused_plan(sh.fused, n, p, k, h->wkind, h->woffs, h->wdim, sh.device);
+    CK(cudaStreamSynchronize(sh.stream));
+}
+
+void ensure_tiled(Shard& sh) {
+    Ws& w = sh.w;
+    if (w.Gt) return;
+    const int n = w.L.n, p = w.L.p, B = sh.batch;
+    w.Gt = sh.alloc<double>((size_t)B * w.ldgt * n);
+    w.H = sh.alloc<double>((size_t)B * w.ldh * n);
+    w.HiAt = sh.alloc<double>((size_t)B * n * p);
+    w.M = sh.alloc<double>((size_t)B * w.ldm * p);
+    w.AA = sh.alloc<double>((size_t)B * w.ldh * n * (p > 0 ? 1 : 0));
+    w.Ap = sh.alloc<double>((size_t)B * w.ldap * n * (p > 0 ? 1 : 0));
+}
+
+// AA = A'A (reference src/densesolver.jl:32) and, when the caller gave no
+// `sing`, the test of src/Socp.jl:49-56: cholesky(G'G) fails.
+void prepare_problem(Shard& sh, bool have_sing) {
+    Ws& w = sh.w;
+    const int n = w.L.n, p = w.L.p, B = sh.batch;
+    ensure_tiled(sh);
+    if (p > 0) {
+        const int64_t sA = w.sA;
+        dim3 g(std::max(1, std::min(64, (p * n + 255) / 256)), sh.sharedA ? 1 : B);
+        LAUNCH(sh, k_pad_copy, g, 256, 0, w.A, sA, p, n, w.Ap, w.ldap);
+        // shared A: every problem reads slice 0 of Ap
+        syrk(sh, true, w.Ap, sh.sharedA ? 0 : (int64_t)w.ldap * n, w.ldap, n, w.ppad, w.AA, (int64_t)w.ldh * n, w.ldh,
+             1.0, 0.0, nullptr, 0, 0, nullptr, nullptr);
+    }
+    if (!have_sing) {
+        LAUNCH(sh, k_reset, (B + 255) / 256, 256, 0, w, B);
+        dim3 g2(n, B);
+        (void)g2;
+        const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
+        dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
+        LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.eta, w.Gt, w.ldgt, 1, cols_per_cta, (const int*)nullptr);
+        syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0,
+             0, nullptr, nullptr);
+        potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr);
+        LAUNCH(sh, k_fail_to_sing, (B + 255) / 256, 256, 0, w.fail, sh.d_sing, B);
+    }
+    std::vector<uint8_t> hs(B);
+    CK(cudaMemcpyAsync(hs.data(), sh.d_sing, B, cudaMemcpyDeviceToHost, sh.stream));
+    CK(cudaStreamSynchronize(sh.stream));
+    sh.any_sing = false;
+    for (uint8_t v : hs) sh.any_sing |= (v != 0);
+}
+
+template <class F>
+int guarded(socp_handle* h, F f) {
+    try {
+        f();
+        return 0;
+    } catch (const CudaErr& e) {
+        if (h) h->err = e.msg;
+        cudaGetLastError();
+        return e.code > 0 ? e.code : 999;
+    } catch (const UsageErr& e) {
+        if (h) h->err = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        if (h) h->err = e.what();
+        return SOCP_ERR_NOMEM;
+    }
+}
+
+template <class F>
+void for_each_shard(socp_handle* h, F f) {
+    if (h->shards.size() == 1) {
+        CK(cudaSetDevice(h->shards[0].device));
+        f(h->shards[0]);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<CudaErr> errs(h->shards.size(), CudaErr{0, ""});
+    for (size_t i = 0; i < h->shards.size(); ++i) {
+        th.emplace_back([&, i]() {
+            try {
+                CK(cudaSetDevice(h->shards[i].device));
+                f(h->shards[i]);
+            } catch (const CudaErr& e) {
+                errs[i] = e;
+            } catch (const UsageErr& e) {
+                errs[i] = CudaErr{e.code, e.msg};
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (e.code != 0) throw e;
+}
+
+void h2d(Shard& sh, void* dst, const void* src, size_t bytes) {
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sh.stream));
+}
+void d2h(Shard& sh, void* dst, const void* src, size_t bytes) {
+    if (bytes && dst) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sh.stream));
+}
+
+void need(bool cond, int code, const char* msg) {
+    if (!cond) throw UsageErr{code, msg};
+}
+
+int choose_path(const Shard& sh, const socp_params& prm) {
+    if (prm.path == SOCP_PATH_TILED) return SOCP_PATH_TILED;
+    if (prm.path == SOCP_PATH_FUSED) {
+        need(sh.fused.fits, SOCP_ERR_SIZE, "layout does not fit the fused shared-memory kernel");
+        return SOCP_PATH_FUSED;
+    }
+    return sh.fused.fits ? SOCP_PATH_FUSED : SOCP_PATH_TILED;
+}
+
+void run_solve(Shard& sh, const socp_params& prm) {
+    need(sh.have_data, SOCP_ERR_STATE, "solve called before set_data");
+    sh.launches = 0;
+    CK(cudaEventRecord(sh.ev[0], sh.stream));
+    if (choose_path(sh, prm) == SOCP_PATH_FUSED) {
+        solve_fused(sh.fused, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
+        sh.launches += 2;
+        sh.tim.path_used = SOCP_PATH_FUSED;
+        sh.tim.iterations_max = -1;
+    } else {
+        ensure_tiled(sh);
+        solve_tiled(sh, prm);
+    }
+    CK(cudaEventRecord(sh.ev[1], sh.stream));
+    CK(cudaStreamSynchronize(sh.stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
+    sh.tim.solve_ms = ms;
+    sh.tim.kernel_launches = sh.launches;
+    sh.have_scaling = sh.have_factor = false;
+}
+
+void fetch_results(socp_handle* h, Shard& sh, double* x, double* y, double* z, double* s, int32_t* status,
+                   int32_t* iters, double* pobj, double* dobj) {
+    const int n = h->n, p = h->p, k = h->k, B = sh.batch;
+    const int64_t f = sh.first;
+    CK(cudaEventRecord(sh.ev[2], sh.stream));
+    if (x) d2h(sh, x + f * n, sh.w.x, sizeof(double) * B * n);
+    if (y) d2h(sh, y + f * p, sh.w.y, sizeof(double) * B * p);
+    if (z) d2h(sh, z + f * k, sh.w.z, sizeof(double) * B * k);
+    if (s) d2h(sh, s + f * k, sh.w.s, sizeof(double) * B * k);
+    if (status) d2h(sh, status + f, sh.w.status, sizeof(int) * B);
+    if (iters) d2h(sh, iters + f, sh.w.iters, sizeof(int) * B);
+    std::vector<ProbScalars> sc;
+    if (pobj || dobj) {
+        sc.resize(B);
+        d2h(sh, sc.data(), sh.w.sc, sizeof(ProbScalars) * B);
+    }
+    CK(cudaEventRecord(sh.ev[3], sh.stream));
+    CK(cudaStreamSynchronize(sh.stream));
+    for (int b = 0; b < (int)sc.size(); ++b) {
+        if (pobj) pobj[f + b] = sc[b].pobj;
+        if (dobj) dobj[f + b] = sc[b].dobj;
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, sh.ev[2], sh.ev[3]));
+    sh.tim.d2h_ms = ms;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+int socp_b200_version(void) { return SOCP_B200_VERSION; }
+
+int socp_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void socp_b200_default_params(socp_params* out) {
+    if (!out) return;
+    out->max_iter = 40;      // reference src/solver.jl:105
+    out->path = SOCP_PATH_AUTO;
+    out->tol = 1e-5;         // :122
+    out->step_damp = 0.99;   // :146
+    out->init_eps = 1e-10;   // :91,:97
+}
+
+static thread_local std::string g_create_err;
+
+int socp_b200_create(socp_handle** out, const socp_layout* L, int64_t batch, const int32_t* devices, int32_t ndev) {
+    if (!out || !L) { g_create_err = "null argument"; return SOCP_ERR_NULL; }
+    *out = nullptr;
+    if (L->n <= 0 || L->p < 0 || L->k <= 0 || L->ncones <= 0 || batch <= 0) { g_create_err = "bad dimensions"; return SOCP_ERR_LAYOUT; }
+    if (!L->cone_kind || !L->cone_offs || !L->cone_dim) { g_create_err = "null cone arrays"; return SOCP_ERR_NULL; }
+    int off = 0;
+    bool seen_soc = false;
+    for (int i = 0; i < L->ncones; ++i) {
+        const int kd = L->cone_kind[i];
+        if (kd != SOCP_CONE_POC && kd != SOCP_CONE_SOC) { g_create_err = "unknown cone kind"; return SOCP_ERR_LAYOUT; }
+        if (L->cone_dim[i] <= 0 || L->cone_offs[i] != off) { g_create_err = "cones must tile 0..k-1 contiguously"; return SOCP_ERR_LAYOUT; }
+        if (kd == SOCP_CONE_SOC) seen_soc = true;
+        else if (seen_soc) { g_create_err = "POC blocks must precede SOC blocks"; return SOCP_ERR_LAYOUT; }
+        off += L->cone_dim[i];
+    }
+    if (off != L->k) { g_create_err = "cone dims do not sum to k"; return SOCP_ERR_LAYOUT; }
+    if (L->n > 8192 || L->p > 8192) { g_create_err = "n, p limited to 8192 (triangular-solve staging)"; return SOCP_ERR_SIZE; }
+    socp_handle* h = new socp_handle();
+    h->n = L->n; h->p = L->p; h->k = L->k; h->batch = batch;
+    for (int i = 0; i < L->ncones; ++i) {
+        h->kind.push_back(L->cone_kind[i]);
+        h->offs.push_back(L->cone_offs[i]);
+        h->dim.push_back(L->cone_dim[i]);
+        h->first_work.push_back((int)h->wkind.size());
+        if (L->cone_kind[i] == SOCP_CONE_POC) {
+            h->deg += L->cone_dim[i];
+            for (int o = 0; o < L->cone_dim[i]; o += POC_CHUNK) {
+                h->wkind.push_back(KIND_POC);
+                h->woffs.push_back(L->cone_offs[i] + o);
+                h->wdim.push_back(std::min(POC_CHUNK, L->cone_dim[i] - o));
+            }
+        } else {
+            h->deg += 1;
+            h->wkind.push_back(KIND_SOC);
+            h->woffs.push_back(L->cone_offs[i]);
+            h->wdim.push_back(L->cone_dim[i]);
+        }
+    }
+    std::vector<int> devs;
+    if (devices && ndev > 0) devs.assign(devices, devices + ndev);
+    else {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
+        devs.push_back(cur);
+    }
+    if ((int64_t)devs.size() > batch) devs.resize((size_t)batch);
+    const int64_t per = (batch + (int64_t)devs.size() - 1) / (int64_t)devs.size();
+    int64_t first = 0;
+    for (size_t d = 0; d < devs.size() && first < batch; ++d) {
+        Shard sh;
+        sh.device = devs[d];
+        sh.first = first;
+        sh.batch = (int)std::min<int64_t>(per, batch - first);
+        first += sh.batch;
+        h->shards.push_back(sh);
+    }
+    int rc = guarded(h, [&]() {
+        for (auto& sh : h->shards) build_shard(h, sh);
+    });
+    if (rc != 0) {
+        g_create_err = h->err;
+        for (auto& sh : h->shards) sh.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+int socp_b200_destroy(socp_handle* h) {
+    if (!h) return SOCP_ERR_NULL;
+    for (auto& sh : h->shards) sh.release();
+    delete h;
+    return 0;
+}
+
+const char* socp_b200_last_error(const socp_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int socp_b200_set_data(socp_handle* h, const double* c, const double* A, const double* b, const double* G,
+                       const double* hvec, const uint8_t* sing, int32_t flags) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        need(c && G && hvec, SOCP_ERR_NULL, "c, G, h must not be null");
+        need(h->p == 0 || (A && b), SOCP_ERR_NULL, "A, b must not be null when p > 0");
+        const int n = h->n, p = h->p, k = h->k;
+        for_each_shard(h, [&](Shard& sh) {
+            const int64_t f = sh.first;
+            const int B = sh.batch;
+            sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
+            sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
+            CK(cudaEventRecord(sh.ev[0], sh.stream));
+            h2d(sh, sh.d_c, c + f * n, sizeof(double) * B * n);
+            h2d(sh, sh.d_h, hvec + f * k, sizeof(double) * B * k);
+            if (p > 0) {
+                h2d(sh, sh.d_b, b + f * p, sizeof(double) * B * p);
+                if (sh.sharedA) h2d(sh, sh.d_A, A, sizeof(double) * p * n);
+                else h2d(sh, sh.d_A, A + f * p * n, sizeof(double) * B * p * n);
+            }
+            if (sh.sharedG) h2d(sh, sh.d_G, G, sizeof(double) * k * n);
+            else h2d(sh, sh.d_G, G + f * (int64_t)k * n, sizeof(double) * B * k * n);
+            sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
+            sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
+            if (sing) h2d(sh, sh.d_sing, sing + f, B);
+            CK(cudaEventRecord(sh.ev[1], sh.stream));
+            // sing / A'A are only needed when there are equalities or the caller
+            // asks for the test; with p == 0 and sing given the tiled buffers stay unallocated
+            if (sing && p == 0) {
+                std::vector<uint8_t> hs(sing + f, sing + f + B);
+                sh.any_sing = false;
+                for (uint8_t v : hs) sh.any_sing |= (v != 0);
+                CK(cudaStreamSynchronize(sh.stream));
+            } else {
+                prepare_problem(sh, sing != nullptr);
+            }
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
+            sh.tim.h2d_ms = ms;
+            sh.have_data = true;
+            sh.have_scaling = sh.have_factor = false;
+        });
+    });
+}
+
+int socp_b200_solve_dev(socp_handle* h, const socp_params* params) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        socp_params prm;
+        socp_b200_default_params(&prm);
+        if (params) prm = *params;
+        need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
+        for_each_shard(h, [&](Shard& sh) { run_solve(sh, prm); });
+    });
+}
+
+int socp_b200_get_results(socp_handle* h, double* x, double* y, double* z, double* s, int32_t* status,
+                          int32_t* iters, double* pobj, double* dobj) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        for_each_shard(h, [&](Shard& sh) { fetch_results(h, sh, x, y, z, s, status, iters, pobj, dobj); });
+    });
+}
+
+int socp_b200_solve(socp_handle* h, const socp_params* params, double* x, double* y, double* z, double* s,
+                    int32_t* status, int32_t* iters, double* pobj, double* dobj) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        socp_params prm;
+        socp_b200_default_params(&prm);
+        if (params) prm = *params;
+        need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
+        for_each_shard(h, [&](Shard& sh) {
+            run_solve(sh, prm);
+            fetch_results(h, sh, x, y, z, s, status, iters, pobj, dobj);
+        });
+    });
+}
+
+int socp_b200_get_sing(socp_handle* h, uint8_t* sing) {
+    if (!h || !sing) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        for_each_shard(h, [&](Shard& sh) {
+            need(sh.have_data, SOCP_ERR_STATE, "get_sing called before set_data");
+            d2h(sh, sing + sh.first, sh.d_sing, sh.batch);
+            CK(cudaStreamSynchronize(sh.stream));
+        });
+    });
+}
+
+int socp_b200_timings(const socp_handle* h, socp_timings* out) {
+    if (!h || !out) return SOCP_ERR_NULL;
+    socp_timings t{};
+    for (const auto& sh : h->shards) {
+        t.h2d_ms = std::max(t.h2d_ms, sh.tim.h2d_ms);
+        t.solve_ms = std::max(t.solve_ms, sh.tim.solve_ms);
+        t.d2h_ms = std::max(t.d2h_ms, sh.tim.d2h_ms);
+        t.kernel_launches += sh.tim.kernel_launches;
+        t.iterations_max = std::max(t.iterations_max, sh.tim.iterations_max);
+        t.path_used = sh.tim.path_used;
+    }
+    *out = t;
+    return 0;
+}
+
+// ------------------------------------------------------------------ step level
+#define STEP_PROLOGUE(cond_state, msg)                                        \
+    if (!h) return SOCP_ERR_NULL;                                             \
+    return guarded(h, [&]() {                                                 \
+        const int n = h->n, p = h->p, k = h->k;                               \
+        (void)n; (void)p; (void)k;                                            \
+        for_each_shard(h, [&](Shard& sh) {                                    \
+            Ws& w = sh.w;                                                     \
+            const int64_t f = sh.first;                                       \
+            const int B = sh.batch;                                           \
+            (void)w; (void)f; (void)B;                                        \
+            need(cond_state, SOCP_ERR_STATE, msg);
+
+#define STEP_EPILOGUE                                                         \
+            CK(cudaStreamSynchronize(sh.stream));                             \
+        });                                                                   \
+    });
+
+int socp_b200_compute_scaling(socp_handle* h, const double* s, const double* z, double* lambda, double* wbs,
+                              double* mu, int32_t* fail) {
+    if (h && (!s || !z)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(true, "")
+        h2d(sh, w.s, s + f * k, sizeof(double) * B * k);
+        h2d(sh, w.z, z + f * k, sizeof(double) * B * k);
+        CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
+        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.eta, w.fail, (const int*)nullptr);
+        if (lambda) d2h(sh, lambda + f * k, w.lam, sizeof(double) * B * k);
+        if (wbs) d2h(sh, wbs + f * k, w.wb, sizeof(double) * B * k);
+        if (fail) d2h(sh, fail + f, w.fail, sizeof(int) * B);
+        std::vector<double> eta;
+        const int nc = w.L.ncones;
+        if (mu) { eta.resize((size_t)B * nc); d2h(sh, eta.data(), w.eta, sizeof(double) * B * nc); }
+        CK(cudaStreamSynchronize(sh.stream));
+        if (mu) {
+            const int no = (int)h->kind.size();
+            for (int b = 0; b < B; ++b)
+                for (int c = 0; c < no; ++c)
+                    mu[(f + b) * no + c] = h->kind[c] == SOCP_CONE_SOC ? eta[(size_t)b * nc + h->first_work[c]] : 0.0;
+        }
+        sh.have_scaling = true;
+        sh.have_factor = false;
+    STEP_EPILOGUE
+}
+
+int socp_b200_setup_iter(socp_handle* h, int32_t* fail) {
+    STEP_PROLOGUE(sh.have_data && sh.have_scaling, "setup_iter needs set_data and compute_scaling first")
+        ensure_tiled(sh);
+        CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
+        factor(sh, false, true, nullptr);
+        if (fail) d2h(sh, fail + f, w.fail, sizeof(int) * B);
+        sh.have_factor = true;
+    STEP_EPILOGUE
+}
+
+int socp_b200_solve_kkt(socp_handle* h, const double* dx, const double* dy, const double* dz, const double* ds,
+                        double* cx, double* cy, double* cz, double* cs) {
+    if (h && (!dx || !dz || !ds || (h->p > 0 && !dy))) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(sh.have_factor, "solve_kkt needs setup_iter first")
+        h2d(sh, w.dx, dx + f * n, sizeof(double) * B * n);
+        if (p > 0) h2d(sh, w.dy, dy + f * p, sizeof(double) * B * p);
+        h2d(sh, w.dz, dz + f * k, sizeof(double) * B * k);
+        h2d(sh, w.ds, ds + f * k, sizeof(double) * B * k);
+        LAUNCH(sh, k_kkt_head, B, sh.threads, 0, w);
+        kkt_middle(sh, nullptr);
+        LAUNCH(sh, k_kkt_tail, B, sh.threads, 0, w);
+        if (cx) d2h(sh, cx + f * n, w.rx, sizeof(double) * B * n);
+        if (cy && p > 0) d2h(sh, cy + f * p, w.ry, sizeof(double) * B * p);
+        if (cz) d2h(sh, cz + f * k, w.rz, sizeof(double) * B * k);
+        if (cs) d2h(sh, cs + f * k, w.rs, sizeof(double) * B * k);
+    STEP_EPILOGUE
+}
+
+static int apply_common(socp_handle* h, const double* in, double* out, int mode) {
+    if (h && (!in || !out)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(sh.have_scaling, "needs compute_scaling first")
+        h2d(sh, w.kt2, in + f * k, sizeof(double) * B * k);
+        if (mode == 0) LAUNCH(sh, k_apply<APPLY_W>, B, sh.threads, 0, w.L, w.wb, w.eta, w.kt2, w.kt3);
+        else if (mode == 1) LAUNCH(sh, k_apply<APPLY_WINV>, B, sh.threads, 0, w.L, w.wb, w.eta, w.kt2, w.kt3);
+        else LAUNCH(sh, k_apply<APPLY_WINV2>, B, sh.threads, 0, w.L, w.wb, w.eta, w.kt2, w.kt3);
+        d2h(sh, out + f * k, w.kt3, sizeof(double) * B * k);
+    STEP_EPILOGUE
+}
+int socp_b200_scale(socp_handle* h, const double* in, double* out) { return apply_common(h, in, out, 0); }
+int socp_b200_iscale(socp_handle* h, const double* in, double* out) { return apply_common(h, in, out, 1); }
+int socp_b200_iwiw(socp_handle* h, const double* in, double* out) { return apply_common(h, in, out, 2); }
+
+int socp_b200_make_e(socp_handle* h, double* out) {
+    if (h && !out) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(true, "")
+        LAUNCH(sh, k_make_e, B, sh.threads, 0, w.L, w.kt3);
+        d2h(sh, out + f * k, w.kt3, sizeof(double) * B * k);
+    STEP_EPILOGUE
+}
+int socp_b200_vprod(socp_handle* h, const double* u, const double* v, double* out) {
+    if (h && (!u || !v || !out)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(true, "")
+        h2d(sh, w.kt2, u + f * k, sizeof(double) * B * k);
+        h2d(sh, w.kt3, v + f * k, sizeof(double) * B * k);
+        LAUNCH(sh, k_vprod, B, sh.threads, 0, w.L, w.kt2, w.kt3, w.k0);
+        d2h(sh, out + f * k, w.k0, sizeof(double) * B * k);
+    STEP_EPILOGUE
+}
+int socp_b200_iprod(socp_handle* h, const double* lambda, const double* v, double* out) {
+    if (h && (!lambda || !v || !out)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(true, "")
+        h2d(sh, w.kt2, lambda + f * k, sizeof(double) * B * k);
+        h2d(sh, w.kt3, v + f * k, sizeof(double) * B * k);
+        LAUNCH(sh, k_iprod, B, sh.threads, 0, w.L, w.kt2, w.kt3, w.k0);
+        d2h(sh, out + f * k, w.k0, sizeof(double) * B * k);
+    STEP_EPILOGUE
+}
+int socp_b200_max_step(socp_handle* h, const double* x, double* out) {
+    if (h && (!x || !out)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(true, "")
+        h2d(sh, w.kt2, x + f * k, sizeof(double) * B * k);
+        LAUNCH(sh, k_max_step, B, sh.threads, 0, w.L, w.kt2, w.k0);
+        d2h(sh, out + f, w.k0, sizeof(double) * B);
+    STEP_EPILOGUE
+}
+int socp_b200_compute_step(socp_handle* h, const double* lambda, const double* ds, const double* dz, double* out) {
+    if (h && (!lambda || !ds || !dz || !out)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(true, "")
+        h2d(sh, w.k2, lambda + f * k, sizeof(double) * B * k);
+        h2d(sh, w.kt2, ds + f * k, sizeof(double) * B * k);
+        h2d(sh, w.kt3, dz + f * k, sizeof(double) * B * k);
+        LAUNCH(sh, k_compute_step, B, sh.threads, 0, w.L, w.k2, w.kt2, w.kt3, w.k0);
+        d2h(sh, out + f, w.k0, sizeof(double) * B);
+    STEP_EPILOGUE
+}
+
+static int get_mat(socp_handle* h, double* out, bool lower_only) {
+    if (h && !out) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(sh.have_factor, "needs setup_iter first")
+        std::vector<double> tmp((size_t)B * w.ldh * n);
+        d2h(sh, tmp.data(), w.H, sizeof(double) * tmp.size());
+        CK(cudaStreamSynchronize(sh.stream));
+        for (int b = 0; b < B; ++b)
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < n; ++i) {
+                    const double lo = tmp[((size_t)b * n + std::min(i, j)) * w.ldh + std::max(i, j)];
+                    out[((f + b) * n + j) * n + i] = lower_only ? (i >= j ? lo : 0.0) : lo;
+                }
+    STEP_EPILOGUE
+}
+// NB: the Cholesky is in place, so after setup_iter the buffer holds L; get_H
+// rebuilds H = L L' on the host from it (debug only).
+int socp_b200_get_L(socp_handle* h, double* out) { return get_mat(h, out, true); }
+int socp_b200_get_H(socp_handle* h, double* out) {
+    if (!h || !out) return SOCP_ERR_NULL;
+    const int n = h->n;
+    std::vector<double> L((size_t)h->batch * n * n);
+    int rc = get_mat(h, L.data(), true);
+    if (rc) return rc;
+    for (int64_t b = 0; b < h->batch; ++b) {
+        const double* Lb = L.data() + b * n * n;
+        double* Hb = out + b * n * n;
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) {
+                double acc = 0.0;
+                for (int c = 0; c <= std::min(i, j); ++c) acc += Lb[(size_t)c * n + i] * Lb[(size_t)c * n + j];
+                Hb[(size_t)j * n + i] = acc;
+            }
+    }
+    return 0;
+}
+
+}  // extern "C"

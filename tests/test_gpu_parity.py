@@ -1,0 +1,284 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, on a B200.
+Step level: <= 1e-10 relative from identical inputs.  End to end: status
+identical, iterations within +-1, objectives within 1e-8 relative."""
+import numpy as np
+import pytest
+
+import socp_b200 as sb
+from socp_b200 import generators as gen
+from oracle import socp_oracle as so
+import refcases as rc
+
+pytestmark = pytest.mark.gpu
+
+
+def ocones(cones):
+    return tuple((c.kind, c.offs, c.dim) for c in sb.api._as_cones(cones))
+
+
+def bcones(cones):
+    return tuple(sb.Cone(*c) for c in cones)
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b)), 1.0))
+
+
+LAYOUTS = {
+    "ref_vec": ((0, 0, 3), (1, 3, 3)),
+    "c2": ((0, 0, 50), (1, 50, 51)),
+    "c3": tuple((1, 4 * j, 4) for j in range(10)),
+    "mixed": ((0, 0, 5), (0, 5, 140), (1, 145, 2), (1, 147, 33), (1, 180, 70)),
+    "c4small": tuple((1, 50 * j, 50) for j in range(3)),
+}
+
+
+def interior(cones, rng, B):
+    k = so.total_dim(cones)
+    v = np.empty((B, k))
+    for kind, offs, dim in cones:
+        if kind == 0:
+            v[:, offs:offs + dim] = rng.uniform(0.5, 2.0, (B, dim))
+        else:
+            tail = rng.standard_normal((B, dim - 1))
+            v[:, offs + 1:offs + dim] = tail
+            v[:, offs] = np.linalg.norm(tail, axis=1) + rng.uniform(0.5, 1.5, B)
+    return v
+
+
+# ---------------------------------------------------------------- golden vectors of the reference
+def test_vector_ops_golden():
+    cones = bcones(rc.VEC_CONES)
+    assert np.array_equal(sb.vprod(cones, rc.VEC_TV1, rc.VEC_TV1), [1, 1, 1, 14, 4, 6])      # runtests.jl:15
+    assert np.array_equal(sb.vprod(cones, rc.VEC_TV1, rc.VEC_TV2), [1, 1, 1, 29, 7, 9])      # :16
+    t = sb.iprod(cones, rc.VEC_TV1, rc.VEC_TV2)
+    assert np.linalg.norm(sb.vprod(cones, rc.VEC_TV1, t) - rc.VEC_TV2) < 1e-4                # :17
+    tid = sb.make_e(cones)
+    assert np.array_equal(sb.vprod(cones, tid, rc.VEC_TV1), rc.VEC_TV1)                       # :18
+    assert np.array_equal(sb.vprod(cones, tid, rc.VEC_TV2), rc.VEC_TV2)                       # :19
+    x = np.array([1.0, 2, 3])
+    assert sb.max_step((sb.POC(0, 3),), x) == -1                                              # :25
+    assert abs(sb.max_step((sb.SOC(0, 3),), x) - (np.sqrt(13.0) - 1.0)) < 1e-15               # :26
+
+
+def test_nt_scaling_golden():
+    cones = bcones(rc.NT_CONES)
+    prob = sb.Problem(np.zeros(1), np.zeros((0, 1)), np.zeros(0), np.zeros((6, 1)), np.zeros(6), cones, sing=False)
+    ss = sb.SolverState(prob, sb.B200Solver(prob))
+    sc = sb.compute_scaling(cones, ss.scaling, rc.NT_S, rc.NT_Z)
+    osc = so.Scaling.create(rc.NT_CONES)
+    so.compute_scaling(rc.NT_CONES, osc, rc.NT_S, rc.NT_Z)
+    assert relerr(sc.l[0], osc.l) < 1e-14 and relerr(sc.wbs[0], osc.wbs) < 1e-14 and relerr(sc.mu[0], osc.mu) < 1e-14
+    op, op2 = np.zeros(6), np.zeros(6)
+    sb.scale_(cones, sc, rc.NT_Z, op)
+    assert np.linalg.norm(osc.W @ rc.NT_Z - op) < 1e-12                                       # :44
+    assert np.linalg.norm(osc.iW.T @ rc.NT_S - sc.l[0]) < 1e-12                               # :41
+    sb.iscale_(cones, sc, op, op2)
+    assert np.linalg.norm(rc.NT_Z - op2) < 1e-12                                              # :47
+    sb.iwiw(cones, sc, rc.NT_Z, op)
+    assert np.linalg.norm(osc.iWiW @ rc.NT_Z - op) < 1e-12
+
+
+def test_kkt_golden():
+    g = rc.KKT
+    cones = bcones(g["cones"])
+    prob = sb.Problem(g["c"], g["A"], g["b"], g["G"], g["h"], cones)
+    solver = sb.B200Solver(prob)
+    ss = sb.SolverState(prob, solver)
+    ss.load(prob)
+    assert ss.get_sing()[0] == 0
+    sc = sb.compute_scaling(cones, ss.scaling, g["s"], g["z"])
+    st = sb.State(g["x"], g["y"], g["z"], g["s"])
+    fail = sb.setup_iter(solver, prob, st, sc)
+    assert fail[0] == 0
+    cx, cy, cz, cs = np.zeros(3), np.zeros(0), np.zeros(4), np.zeros(4)
+    sb.solve_kkt(solver, prob, st, sc, g["dx"], g["dy"], g["dz"], g["ds"], cx, cy, cz, cs)
+    assert np.linalg.norm(cx - g["cxr"]) < 1e-10                                              # :124 (ref tol 1e-3)
+    assert np.linalg.norm(cz - g["czr"]) < 1e-10                                              # :126
+    assert np.linalg.norm(cs - g["csr"]) < 1e-10                                              # :127
+
+
+# ---------------------------------------------------------------- cone ops vs oracle, random batches
+@pytest.mark.parametrize("name", list(LAYOUTS))
+def test_cone_ops_vs_oracle(name):
+    cones = LAYOUTS[name]
+    bc = bcones(cones)
+    k = so.total_dim(cones)
+    rng = np.random.default_rng(7)
+    B = 5
+    s, z = interior(cones, rng, B), interior(cones, rng, B)
+    u, v = rng.standard_normal((B, k)), rng.standard_normal((B, k))
+    prob = sb.BatchProblem(np.zeros((B, 1)), np.zeros((B, 0, 1)), np.zeros((B, 0)), np.zeros((B, k, 1)),
+                           np.zeros((B, k)), bc, sing=np.zeros(B, np.uint8))
+    ss = sb.SolverState(prob)
+    sc = sb.compute_scaling(bc, ss.scaling, s, z)
+    assert not sc.fail.any()
+    got = dict(vprod=sb.vprod(bc, u, v), iprod=sb.iprod(bc, s, v), max_step=sb.max_step(bc, u),
+               step=sb.compute_step(bc, sc.l, u, v), e=sb.make_e(bc, B))
+    W, iW, i2 = np.zeros((B, k)), np.zeros((B, k)), np.zeros((B, k))
+    sb.scale_(bc, sc, u, W)
+    sb.iscale_(bc, sc, u, iW)
+    sb.iwiw(bc, sc, u, i2)
+    for b in range(B):
+        osc = so.Scaling.create(cones)
+        so.compute_scaling(cones, osc, s[b], z[b])
+        assert relerr(sc.l[b], osc.l) < 1e-13
+        assert relerr(sc.wbs[b], osc.wbs) < 1e-13
+        assert relerr(sc.mu[b], osc.mu) < 1e-13
+        assert relerr(got["vprod"][b], so.vprod(cones, u[b], v[b])) < 1e-13
+        assert relerr(got["iprod"][b], so.iprod(cones, s[b], v[b])) < 1e-11
+        assert abs(got["max_step"][b] - so.max_step(cones, u[b])) < 1e-13
+        assert abs(got["step"][b] - so.compute_step(cones, osc.l, u[b], v[b])) < 1e-12
+        assert np.array_equal(got["e"][b], so.make_e(cones))
+        assert relerr(W[b], so.scale(cones, osc, u[b])) < 1e-13
+        assert relerr(iW[b], so.iscale(cones, osc, u[b])) < 1e-13
+        assert relerr(i2[b], osc.iWiW @ u[b]) < 1e-12
+
+
+def test_scaling_failure_flag():
+    cones = LAYOUTS["c3"]
+    bc = bcones(cones)
+    rng = np.random.default_rng(1)
+    s, z = interior(cones, rng, 3), interior(cones, rng, 3)
+    s[1, 4] = 0.0          # head of cone 1 -> outside the cone: sqrt of a negative in the reference
+    prob = sb.BatchProblem(np.zeros((3, 1)), np.zeros((3, 0, 1)), np.zeros((3, 0)), np.zeros((3, 40, 1)),
+                           np.zeros((3, 40)), bc, sing=np.zeros(3, np.uint8))
+    ss = sb.SolverState(prob)
+    sc = sb.compute_scaling(bc, ss.scaling, s, z)
+    assert list(sc.fail != 0) == [False, True, False]
+
+
+# ---------------------------------------------------------------- factor + solve vs oracle
+def _kkt_case(n, p, cones, B, seed, sing_mode=False):
+    rng = np.random.default_rng(seed)
+    k = so.total_dim(cones)
+    G = rng.standard_normal((B, k, n)) / np.sqrt(n)
+    if sing_mode:
+        G[:, :, : n // 3] = 0.0            # rank deficient: G'G singular -> sing = true
+    A = rng.standard_normal((B, p, n)) / np.sqrt(n)
+    return G, A, rng
+
+
+@pytest.mark.parametrize("n,p,lay,sing_mode", [
+    (3, 0, "ref_vec", False), (50, 1, "c2", False), (12, 0, "c3", False), (70, 5, "mixed", False),
+    (130, 0, "c4small", False), (40, 30, "c4small", True), (201, 7, "mixed", False),
+])
+def test_factor_solve_vs_oracle(n, p, lay, sing_mode):
+    cones = LAYOUTS[lay]
+    bc = bcones(cones)
+    k = so.total_dim(cones)
+    B = 3
+    G, A, rng = _kkt_case(n, p, cones, B, 11 + n, sing_mode)
+    c, b, h = rng.standard_normal((B, n)), rng.standard_normal((B, p)), rng.standard_normal((B, k))
+    s, z = interior(cones, rng, B), interior(cones, rng, B)
+    dx, dy = rng.standard_normal((B, n)), rng.standard_normal((B, p))
+    dz, ds = rng.standard_normal((B, k)), rng.standard_normal((B, k))
+    prob = sb.BatchProblem(c, A, b, G, h, bc)
+    solver = sb.B200Solver(prob)
+    ss = sb.SolverState(prob, solver)
+    ss.load(prob)
+    sing = ss.get_sing()
+    sc = sb.compute_scaling(bc, ss.scaling, s, z)
+    fail = sb.setup_iter(solver, prob, None, sc)
+    assert not fail.any()
+    cx, cy, cz, cs = np.zeros((B, n)), np.zeros((B, p)), np.zeros((B, k)), np.zeros((B, k))
+    sb.solve_kkt(solver, prob, None, sc, dx, dy, dz, ds, cx, cy, cz, cs)
+    for q in range(B):
+        pr = so.Problem.create(c[q], A[q], b[q], G[q], h[q], cones)
+        assert bool(sing[q]) == pr.sing == sing_mode
+        osc = so.Scaling.create(cones)
+        so.compute_scaling(cones, osc, s[q], z[q])
+        dsol = so.DenseSolver(pr)
+        dsol.setup_iter(pr, osc)
+        ox, oy, oz, os_ = dsol.solve_kkt(pr, osc, dx[q], dy[q], dz[q], ds[q], fast_iprod=True)
+        tol = 1e-10 if not sing_mode else 1e-8
+        assert relerr(cx[q], ox) < tol, ("cx", relerr(cx[q], ox))
+        assert relerr(cy[q], oy) < tol, ("cy", relerr(cy[q], oy))
+        assert relerr(cz[q], oz) < tol, ("cz", relerr(cz[q], oz))
+        assert relerr(cs[q], os_) < tol, ("cs", relerr(cs[q], os_))
+
+
+# ---------------------------------------------------------------- end to end, the reference's instances (C1)
+EXPECT_ITERS = {"socp1": 5, "socp2": 12, "socp3": 10, "control": 4}
+
+
+@pytest.mark.parametrize("name", ["socp1", "socp2", "socp3", "control"])
+@pytest.mark.parametrize("path", [sb.PATH_TILED, sb.PATH_AUTO])
+def test_reference_instances(name, path):
+    d = rc.ALL_C1[name]()
+    cones = bcones(d["cones"])
+    prob = sb.Problem(d["c"], d["A"], d["b"], d["G"], d["h"], cones)
+    ss = sb.SolverState(prob, sb.B200Solver(prob))
+    st = sb.solve_socp(prob, ss, sb.default_params(path=path))
+    pr = so.Problem.create(d["c"], d["A"], d["b"], d["G"], d["h"], d["cones"])
+    ref = so.solve_socp(pr, init="full")
+    assert st.status == ref.status == sb.STATUS_CONVERGED
+    assert st.iters == ref.iters == EXPECT_ITERS[name]
+    if d["xstar"] is not None:
+        assert np.linalg.norm(st.x - d["xstar"]) < 1e-3          # runtests.jl:142,166,187
+    assert abs(st.pobj - ref.pobj) <= 1e-8 * max(1.0, abs(ref.pobj))
+    assert abs(st.dobj - ref.dobj) <= 1e-8 * max(1.0, abs(ref.dobj))
+    assert relerr(st.x, ref.state.x) < 1e-6
+
+
+def _check_batch(prob, res, sample, fast=True):
+    worst = dict(pobj=0.0, dobj=0.0, x=0.0)
+    for q in sample:
+        pr = so.Problem.create(prob.c[q], prob.A_dense(q), prob.b[q], prob.G_dense(q), prob.h[q], ocones(prob.cones),
+                               sing=False if prob.sing is not None and not prob.sing[q] else None)
+        ref = so.solve_socp(pr, init="reduced", fast_iprod=fast)
+        assert res.status[q] == ref.status, (q, res.status[q], ref.status)
+        assert abs(int(res.iters[q]) - ref.iters) <= 1, (q, res.iters[q], ref.iters)
+        if ref.status == so.STATUS_CONVERGED and res.iters[q] == ref.iters:
+            worst["pobj"] = max(worst["pobj"], abs(res.pobj[q] - ref.pobj) / max(1.0, abs(ref.pobj)))
+            worst["dobj"] = max(worst["dobj"], abs(res.dobj[q] - ref.dobj) / max(1.0, abs(ref.dobj)))
+            worst["x"] = max(worst["x"], relerr(res.x[q], ref.state.x))
+    assert worst["pobj"] <= 1e-8 and worst["dobj"] <= 1e-8, worst
+    return worst
+
+
+@pytest.mark.parametrize("cfg,B,path", [("C2", 48, sb.PATH_TILED), ("C3", 64, sb.PATH_TILED),
+                                        ("C2", 48, sb.PATH_AUTO), ("C3", 64, sb.PATH_AUTO)])
+def test_batch_vs_oracle(cfg, B, path):
+    prob = gen.make_config(cfg, batch=B)
+    ss = sb.SolverState(prob)
+    res = sb.solve_socp_batch(prob, ss, sb.default_params(path=path))
+    assert (res.status == sb.STATUS_CONVERGED).all()
+    _check_batch(prob, res, range(0, B, 3))
+
+
+def test_mid_size_multi_panel():
+    # n = 150 > one Cholesky panel; random feasible with equalities
+    cones = tuple((1, 40 * j, 40) for j in range(5))
+    prob = gen.random_feasible(4, 150, 6, bcones(cones), 0.05)
+    ss = sb.SolverState(prob)
+    res = sb.solve_socp_batch(prob, ss)
+    assert (res.status == sb.STATUS_CONVERGED).all()
+    _check_batch(prob, res, range(4))
+
+
+def test_maxiter_and_reuse():
+    prob = gen.make_config("C3", batch=8)
+    ss = sb.SolverState(prob)
+    r3 = sb.solve_socp_batch(prob, ss, sb.default_params(max_iter=3))
+    assert (r3.status == sb.STATUS_MAXITER).all() and (r3.iters == 3).all()
+    # the same SolverState is reusable (reference test/runtests.jl:243) and deterministic
+    r1 = sb.solve_socp_batch(prob, ss)
+    r2 = sb.solve_socp_batch(prob, ss)
+    assert np.array_equal(r1.x, r2.x) and np.array_equal(r1.iters, r2.iters)
+
+
+def test_shared_G_batch():
+    base = gen.make_config("C3", batch=1)
+    B = 6
+    rng = np.random.default_rng(3)
+    h = base.h[0] + 0.01 * np.abs(rng.standard_normal((B, base.k))) * (np.arange(base.k) % 4 == 0)
+    c = np.repeat(base.c, B, axis=0)
+    shared = sb.BatchProblem(c, np.zeros((B, 0, base.n)), np.zeros((B, 0)), base.G_dense(0), h, base.cones,
+                             sing=np.zeros(B, np.uint8))
+    full = sb.BatchProblem(c, np.zeros((B, 0, base.n)), np.zeros((B, 0)), np.repeat(base.G_dense(0)[None], B, 0), h,
+                           base.cones, sing=np.zeros(B, np.uint8))
+    ra = sb.solve_socp_batch(shared, sb.SolverState(shared), sb.default_params(path=sb.PATH_TILED))
+    rb = sb.solve_socp_batch(full, sb.SolverState(full), sb.default_params(path=sb.PATH_TILED))
+    assert np.array_equal(ra.status, rb.status) and np.array_equal(ra.x, rb.x)
