@@ -59,9 +59,11 @@ class NumericalFailure(Exception):
 
 def _sqrt(v: float) -> float:
     # Julia's sqrt throws DomainError for negative reals and returns NaN for NaN.
+    # The result is a numpy float64 so that a later 1/0 gives Inf as in Julia
+    # instead of Python's ZeroDivisionError.
     if v < 0.0:
         raise NumericalFailure("sqrt of negative")
-    return math.sqrt(v)
+    return np.float64(math.sqrt(v))
 
 
 def _cholesky(M: np.ndarray) -> np.ndarray:
@@ -728,42 +730,43 @@ def solve_socp(pr: Problem, params: Params = Params(), init: str = "full",
     dg = deg(cones)
     for it in range(params.max_iter):                      # :105
         try:
-            compute_scaling(cones, sc, st.s, st.z)         # :106
-            l = sc.l
-            dx = pr.A.T @ st.y + pr.G.T @ st.z + pr.c      # :110-112
-            dy = pr.A @ st.x - pr.b                        # :114-115
-            dz = pr.G @ st.x + st.s - pr.h                 # :117-118
-            ds = vprod(cones, l, l)                        # :120
-            gap = float(st.z @ st.s)
-            resid = float(np.linalg.norm(dx) + np.linalg.norm(dy) + gap)
-            if trace:
-                tr.append(dict(it=it, resid=resid, gap=gap))
-            if resid < params.tol:                         # :122-124
-                status = STATUS_CONVERGED
-                break
-            dx, dy, dz, ds = -dx, -dy, -dz, -ds            # :125
-            solver.setup_iter(pr, sc)                      # :126
-            rx, ry, rz, rs = solver.solve_kkt(pr, sc, dx, dy, dz, ds, fast_iprod)   # :127
-            kt3 = scale(cones, sc, rz)                     # :128
-            kt2 = iscale(cones, sc, rs)                    # :129
-            t = compute_step(cones, l, kt3, kt2)           # :130
-            ll = float(l @ l)
-            rho = 1.0 - t - t ** 2 * float(kt2 @ kt3) / ll  # :132  (minus: reference quirk)
-            sig = max(0.0, min(1.0, rho)) ** 3             # :133
-            mu = ll / dg                                   # :134
-            scfact = 1.0 - sig                             # :136
-            kt1 = vprod(cones, kt2, kt3)                   # :137
-            kt2 = (sig * mu) * idel                        # :138
-            ds = ds + (kt2 - kt1)                          # :139
-            dx, dy, dz = dx * scfact, dy * scfact, dz * scfact   # :140
-            rx, ry, rz, rs = solver.solve_kkt(pr, sc, dx, dy, dz, ds, fast_iprod)   # :141
-            kt3 = scale(cones, sc, rz)                     # :143
-            kt2 = iscale(cones, sc, rs)                    # :144
-            step = compute_step(cones, l, kt3, kt2)        # :145
-            step *= params.step_damp                       # :146
-            if not (np.all(np.isfinite(rx)) and np.all(np.isfinite(rz)) and np.all(np.isfinite(rs))
-                    and np.all(np.isfinite(ry)) and math.isfinite(step)):
-                raise NumericalFailure("non-finite step")
+          with np.errstate(all="ignore"):                  # Julia: Inf/NaN propagate silently
+              compute_scaling(cones, sc, st.s, st.z)         # :106
+              l = sc.l
+              dx = pr.A.T @ st.y + pr.G.T @ st.z + pr.c      # :110-112
+              dy = pr.A @ st.x - pr.b                        # :114-115
+              dz = pr.G @ st.x + st.s - pr.h                 # :117-118
+              ds = vprod(cones, l, l)                        # :120
+              gap = float(st.z @ st.s)
+              resid = float(np.linalg.norm(dx) + np.linalg.norm(dy) + gap)
+              if trace:
+                  tr.append(dict(it=it, resid=resid, gap=gap))
+              if resid < params.tol:                         # :122-124
+                  status = STATUS_CONVERGED
+                  break
+              dx, dy, dz, ds = -dx, -dy, -dz, -ds            # :125
+              solver.setup_iter(pr, sc)                      # :126
+              rx, ry, rz, rs = solver.solve_kkt(pr, sc, dx, dy, dz, ds, fast_iprod)   # :127
+              kt3 = scale(cones, sc, rz)                     # :128
+              kt2 = iscale(cones, sc, rs)                    # :129
+              t = compute_step(cones, l, kt3, kt2)           # :130
+              ll = float(l @ l)
+              rho = 1.0 - t - t ** 2 * float(kt2 @ kt3) / ll  # :132  (minus: reference quirk)
+              sig = max(0.0, min(1.0, rho)) ** 3             # :133
+              mu = ll / dg                                   # :134
+              scfact = 1.0 - sig                             # :136
+              kt1 = vprod(cones, kt2, kt3)                   # :137
+              kt2 = (sig * mu) * idel                        # :138
+              ds = ds + (kt2 - kt1)                          # :139
+              dx, dy, dz = dx * scfact, dy * scfact, dz * scfact   # :140
+              rx, ry, rz, rs = solver.solve_kkt(pr, sc, dx, dy, dz, ds, fast_iprod)   # :141
+              kt3 = scale(cones, sc, rz)                     # :143
+              kt2 = iscale(cones, sc, rs)                    # :144
+              step = compute_step(cones, l, kt3, kt2)        # :145
+              step *= params.step_damp                       # :146
+              if not (np.all(np.isfinite(rx)) and np.all(np.isfinite(rz)) and np.all(np.isfinite(rs))
+                      and np.all(np.isfinite(ry)) and math.isfinite(step)):
+                  raise NumericalFailure("non-finite step")
         except NumericalFailure:
             status = STATUS_NUMERICAL
             break
