@@ -336,6 +336,7 @@ void build_shard(socp_handle* h, Shard& sh) {
     // path does not need them and they dominate the footprint
     sh.threads = std::min(256, std::max(32, 32 * nc));
     fused_plan(sh.fused, n, p, k, h->wkind, h->woffs, h->wdim, sh.device);
+    sh.fused.d_counter = sh.alloc<int>(1);
     CK(cudaStreamSynchronize(sh.stream));
 }
 
@@ -441,11 +442,12 @@ void need(bool cond, int code, const char* msg) {
 
 int choose_path(const Shard& sh, const socp_params& prm) {
     if (prm.path == SOCP_PATH_TILED) return SOCP_PATH_TILED;
+    const bool ok = sh.fused.fits && !sh.any_sing;
     if (prm.path == SOCP_PATH_FUSED) {
-        need(sh.fused.fits, SOCP_ERR_SIZE, "layout does not fit the fused shared-memory kernel");
+        need(ok, SOCP_ERR_SIZE, "the fused shared-memory kernel needs a layout that fits and no sing problems");
         return SOCP_PATH_FUSED;
     }
-    return sh.fused.fits ? SOCP_PATH_FUSED : SOCP_PATH_TILED;
+    return ok ? SOCP_PATH_FUSED : SOCP_PATH_TILED;
 }
 
 void run_solve(Shard& sh, const socp_params& prm) {
@@ -454,7 +456,8 @@ void run_solve(Shard& sh, const socp_params& prm) {
     CK(cudaEventRecord(sh.ev[0], sh.stream));
     if (choose_path(sh, prm) == SOCP_PATH_FUSED) {
         solve_fused(sh.fused, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
-        sh.launches += 2;
+        CK(cudaGetLastError());
+        sh.launches += 1;
         sh.tim.path_used = SOCP_PATH_FUSED;
         sh.tim.iterations_max = -1;
     } else {

@@ -45,11 +45,8 @@ struct LoopParams {
 #define SOCP_VEC(ptr, len) ((ptr) + (int64_t)b * (len))
 
 // ------------------------------------------------------------ step-level kernels
-__global__ void k_scaling(ConeLayout L, const double* __restrict__ s, const double* __restrict__ z,
-                          double* __restrict__ lam, double* __restrict__ wb, double* __restrict__ eta,
-                          int* __restrict__ fail, const int* __restrict__ active) {
-    const int b = blockIdx.x;
-    if (active && !active[b]) return;
+__device__ __forceinline__ void dev_scaling(const ConeLayout& L, int b, const double* s, const double* z,
+                                            double* lam, double* wb, double* eta, int* fail) {
     const int lane = threadIdx.x & 31;
     const double* sb = SOCP_VEC(s, L.k);
     const double* zb = SOCP_VEC(z, L.k);
@@ -66,6 +63,13 @@ __global__ void k_scaling(ConeLayout L, const double* __restrict__ s, const doub
         }
     }
     if (f && lane == 0) atomicOr(fail + b, 1);
+}
+__global__ void k_scaling(ConeLayout L, const double* __restrict__ s, const double* __restrict__ z,
+                          double* __restrict__ lam, double* __restrict__ wb, double* __restrict__ eta,
+                          int* __restrict__ fail, const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    dev_scaling(L, b, s, z, lam, wb, eta, fail);
 }
 
 template <int MODE>
@@ -242,10 +246,7 @@ __device__ __forceinline__ void kkt_tail(const Ws& w, int b) {
 }
 
 // Initial shift, reference src/solver.jl:86-104.  On entry z holds z0 = G x - h.
-__global__ void k_init_shift(Ws w, LoopParams P) {
-    __shared__ double scratch[32];
-    const int b = blockIdx.x;
-    if (!w.active[b]) return;
+__device__ __forceinline__ void dev_init_shift(const Ws& w, int b, const LoopParams& P, double* scratch) {
     const ConeLayout& L = w.L;
     const int lane = threadIdx.x & 31;
     double* z = SOCP_VEC(w.z, L.k);
@@ -265,17 +266,20 @@ __global__ void k_init_shift(Ws w, LoopParams P) {
         }
     }
 }
-
-// After the residual gemvs (dx,dy,dz hold the NEGATED residuals, src/solver.jl:125):
-// stop test (:122-124), ds = -lambda o lambda (:120,:125), solve_kkt head.
-__global__ void k_pre(Ws w, LoopParams P, int it) {
+__global__ void k_init_shift(Ws w, LoopParams P) {
     __shared__ double scratch[32];
     const int b = blockIdx.x;
     if (!w.active[b]) return;
+    dev_init_shift(w, b, P, scratch);
+}
+
+// After the residual gemvs (dx,dy,dz hold the NEGATED residuals, src/solver.jl:125):
+// stop test (:122-124), ds = -lambda o lambda (:120,:125), solve_kkt head.
+__device__ __forceinline__ int dev_pre(const Ws& w, int b, const LoopParams& P, int it, double* scratch) {
     const ConeLayout& L = w.L;
     if (w.fail[b]) {                      // compute_scaling threw
         if (threadIdx.x == 0) { w.status[b] = ST_NUMERICAL; w.active[b] = 0; }
-        return;
+        return 0;
     }
     const double* dx = SOCP_VEC(w.dx, L.n);
     const double* dy = SOCP_VEC(w.dy, L.p);
@@ -302,27 +306,30 @@ __global__ void k_pre(Ws w, LoopParams P, int it) {
     }
     if (resid < P.tol) {                  // :122-124
         if (threadIdx.x == 0) { w.status[b] = ST_CONVERGED; w.active[b] = 0; }
-        return;
+        return 0;
     }
-    if (threadIdx.x == 0) atomicAdd(w.nactive + it, 1);
+    if (threadIdx.x == 0 && w.nactive) atomicAdd(w.nactive + it, 1);
     cta_vprod(L, lam, lam, ds);           // :120
     __syncthreads();
     for (int i = threadIdx.x; i < L.k; i += blockDim.x) ds[i] = -ds[i];      // :125
     __syncthreads();
     kkt_head(w, b);
+    return 1;
+}
+__global__ void k_pre(Ws w, LoopParams P, int it) {
+    __shared__ double scratch[32];
+    const int b = blockIdx.x;
+    if (!w.active[b]) return;
+    dev_pre(w, b, P, it, scratch);
 }
 
 // Between the two solves: finish solve #1, centering parameter (:130-134),
 // combined right-hand side (:136-140), head of solve #2.
-__global__ void k_mid(Ws w, LoopParams P) {
-    __shared__ double scratch[32];
-    __shared__ int iscratch[32];
-    const int b = blockIdx.x;
-    if (!w.active[b]) return;
+__device__ __forceinline__ int dev_mid(const Ws& w, int b, const LoopParams& P, double* scratch, int* iscratch) {
     const ConeLayout& L = w.L;
     if (w.fail[b]) {                      // cholesky! threw
         if (threadIdx.x == 0) { w.status[b] = ST_NUMERICAL; w.active[b] = 0; }
-        return;
+        return 0;
     }
     const int lane = threadIdx.x & 31;
     kkt_tail(w, b);
@@ -348,7 +355,7 @@ __global__ void k_mid(Ws w, LoopParams P) {
     if (threadIdx.x == 0) { w.sc[b].t = t; w.sc[b].sigma = sig; w.sc[b].mu = mu; }
     if (f) {
         if (threadIdx.x == 0) { w.status[b] = ST_NUMERICAL; w.active[b] = 0; }
-        return;
+        return 0;
     }
     // ds += sig*mu*e - kt2 o kt3      :137-139   (kt2 is reused as scratch for the product)
     cta_vprod(L, kt2, kt3, kt2);
@@ -365,14 +372,18 @@ __global__ void k_mid(Ws w, LoopParams P) {
     for (int i = threadIdx.x; i < L.k; i += blockDim.x) dz[i] *= scf;
     __syncthreads();
     kkt_head(w, b);
+    return 1;
 }
-
-// After solve #2: tail, step length (:143-146), iterate update (:147-150).
-__global__ void k_post(Ws w, LoopParams P) {
+__global__ void k_mid(Ws w, LoopParams P) {
     __shared__ double scratch[32];
     __shared__ int iscratch[32];
     const int b = blockIdx.x;
     if (!w.active[b]) return;
+    dev_mid(w, b, P, scratch, iscratch);
+}
+
+// After solve #2: tail, step length (:143-146), iterate update (:147-150).
+__device__ __forceinline__ int dev_post(const Ws& w, int b, const LoopParams& P, double* scratch, int* iscratch) {
     const ConeLayout& L = w.L;
     kkt_tail(w, b);
     __syncthreads();
@@ -399,7 +410,7 @@ __global__ void k_post(Ws w, LoopParams P) {
     f = block_or(f, iscratch);
     if (f) {
         if (threadIdx.x == 0) { w.status[b] = ST_NUMERICAL; w.active[b] = 0; }
-        return;
+        return 0;
     }
     for (int i = threadIdx.x; i < L.n; i += blockDim.x) x[i] = fma(rx[i], step, x[i]);   // :147
     for (int i = threadIdx.x; i < L.p; i += blockDim.x) y[i] = fma(ry[i], step, y[i]);   // :148
@@ -408,6 +419,14 @@ __global__ void k_post(Ws w, LoopParams P) {
         s[i] = fma(rs[i], step, s[i]);                                                    // :150
     }
     if (threadIdx.x == 0) { w.sc[b].step = step; w.iters[b] += 1; }
+    return 1;
+}
+__global__ void k_post(Ws w, LoopParams P) {
+    __shared__ double scratch[32];
+    __shared__ int iscratch[32];
+    const int b = blockIdx.x;
+    if (!w.active[b]) return;
+    dev_post(w, b, P, scratch, iscratch);
 }
 
 // Problems that failed in the initial factorisation / still running at the end.
