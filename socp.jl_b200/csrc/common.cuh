@@ -41,6 +41,41 @@ struct ProbScalars {
     double dobj;
 };
 
+// ---------------------------------------------------------------------------
+// Fast FP64 reciprocal / rsqrt / sqrt: MUFU seed (rcp.approx / rsqrt.approx, ~20
+// bits) + two Newton steps, accurate to ~1-2 ulp.  The IEEE div/sqrt sequences
+// cost hundreds of cycles of dependent latency and sit on every serial chain of
+// the interior-point iteration; the differences are at the 1e-16 level, far
+// inside the parity tolerances (1e-10 per step).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    const double h = 0.5 * a;
+    double e = fma(-h * x, x, 0.5);
+    x = fma(x, e, x);
+    e = fma(-h * x, x, 0.5);
+    x = fma(x, e, x);
+    return x;
+}
+// sqrt(a) for a >= 0 (0 -> 0); negative / NaN inputs give NaN like the IEEE one.
+__device__ __forceinline__ double fast_sqrt(double a) {
+    const double r = fast_rsqrt(a);
+    double y = a * r;
+    const double d = fma(-y, y, a);
+    y = fma(0.5 * r, d, y);
+    return (a == 0.0) ? 0.0 : y;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
@@ -73,6 +108,18 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     double r = (lane < nw) ? scratch[lane] : 0.0;
     r = warp_sum(r);
     return r;
+}
+// four sums at once (scratch >= 4*32 doubles): one barrier pair instead of four
+__device__ __forceinline__ void block_sum4(double& a, double& b, double& c, double& d, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+    __syncthreads();
+    if (lane == 0) { scratch[warp] = a; scratch[32 + warp] = b; scratch[64 + warp] = c; scratch[96 + warp] = d; }
+    __syncthreads();
+    a = warp_sum((lane < nw) ? scratch[lane] : 0.0);
+    b = warp_sum((lane < nw) ? scratch[32 + lane] : 0.0);
+    c = warp_sum((lane < nw) ? scratch[64 + lane] : 0.0);
+    d = warp_sum((lane < nw) ? scratch[96 + lane] : 0.0);
 }
 __device__ __forceinline__ double block_max(double v, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

@@ -28,7 +28,7 @@ namespace socp {
 
 struct FusedOffsets {   // offsets (in doubles) into the dynamic shared memory
     int G, GtH, A, HiAt, M, Mi;
-    int c, b, h, x, y, z, s, lam, wb, eta, dx, dy, dz, ds, rx, ry, rz, rs, k0, k2, u, kt2, kt3, t1, t2, dinv;
+    int c, b, h, x, y, z, s, lam, wb, iwb, eta, dx, dy, dz, ds, rx, ry, rz, rs, k0, k2, u, kt2, kt3, t1, t2, dinv;
     int ldg, npad, kpad4, ldh, ldm;
     int Hoff, Lioff;    // inside the GtH region
     int total;
@@ -76,12 +76,12 @@ inline void fused_plan(FusedPlan& plan, int n, int p, int k, const std::vector<i
     o.Mi = take(o.ldm * p);
     o.c = take(n); o.x = take(n); o.dx = take(n); o.rx = take(n); o.t1 = take(n); o.t2 = take(n); o.dinv = take(n + p);
     o.b = take(p); o.y = take(p); o.dy = take(p); o.ry = take(p);
-    o.h = take(k); o.z = take(k); o.s = take(k); o.lam = take(k); o.wb = take(k);
+    o.h = take(k); o.z = take(k); o.s = take(k); o.lam = take(k); o.wb = take(k); o.iwb = take(k);
     o.dz = take(k); o.ds = take(k); o.rz = take(k); o.rs = take(k); o.k0 = take(k); o.k2 = take(k); o.u = take(k);
     o.kt2 = take(k); o.kt3 = take(k);
-    o.eta = take(nc);
+    o.eta = take(4 * nc);
     o.total = at;
-    plan.smem = (size_t)at * sizeof(double) + 512;   // + static scratch headroom
+    plan.smem = (size_t)at * sizeof(double) + 256;   // + static scratch headroom
     int dev_smem = 0, sms = 148;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) {
         cudaGetLastError();
@@ -102,7 +102,8 @@ inline void fused_plan(FusedPlan& plan, int n, int p, int k, const std::vector<i
     if (plan.variant == 2 && o.npad > 56) plan.variant = 3;                 // 57..64 -> 36 tiles > 4*8
     // resident CTAs per SM: shared memory (1 KB reserved per CTA) and threads
     const int per_sm = 228 * 1024;
-    plan.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (plan.smem + 1024)), 2048 / plan.threads, 16}));
+    const int reg_cap = plan.variant == 0 ? 12 : (plan.variant == 1 ? 4 : (plan.variant == 2 ? 2 : 1));
+    plan.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (plan.smem + 1024)), 2048 / plan.threads, reg_cap}));
     plan.fits = true;
 }
 
@@ -244,7 +245,7 @@ __device__ __forceinline__ int cta_chol_inv(double* H, double* Li, int n, int ld
                     for (int a = 1; a < RPW; ++a) v = (a == aj) ? wk[a][b] : v;
                     const int c = lane + 32 * b;
                     if (c < j) Li[c * ld + j] = v;
-                    else if (c == j) { Li[c * ld + j] = 1.0; ipiv[j] = __drcp_rn(v); }
+                    else if (c == j) { Li[c * ld + j] = 1.0; ipiv[j] = fast_rcp(v); }
                 }
             }
             __syncthreads();
@@ -282,7 +283,7 @@ __device__ __forceinline__ int cta_chol_inv(double* H, double* Li, int n, int ld
     }
     __syncthreads();
     // deferred scaling of the inverse: Li[i][c] = y[i][c] / sqrt(pivot_i)
-    for (int i = tid; i < n; i += NWARPS * 32) ipiv[i] = rsqrt(H[i * ld + i]);
+    for (int i = tid; i < n; i += NWARPS * 32) ipiv[i] = fast_rsqrt(H[i * ld + i]);
     __syncthreads();
     for (int c = warp; c < n; c += NWARPS)
         for (int i = c + lane; i < n; i += 32) Li[c * ld + i] *= ipiv[i];
@@ -319,6 +320,25 @@ __device__ __forceinline__ void cta_potrs_inv(const double* Li, int n, int ld, d
     __syncthreads();
 }
 
+// Optional per-phase cycle counters (profiling build only: -DSOCP_PHASE_TIMING).  CTA 0 / thread 0 adds the
+// clock64() deltas of every phase into phase_clk[]; read back by tools/phase_timing.py.
+#ifdef SOCP_PHASE_TIMING
+__device__ unsigned long long g_phase_clk[16];
+#define PT_INIT() long long pt_t0 = clock64()
+#define PT_MARK(idx)                                                              \
+    do {                                                                          \
+        if (tid == 0 && blockIdx.x == 0) {                                        \
+            const long long t_ = clock64();                                       \
+            atomicAdd(&g_phase_clk[idx], (unsigned long long)(t_ - pt_t0));       \
+            pt_t0 = t_;                                                           \
+        }                                                                         \
+    } while (0)
+#else
+#define PT_INIT()
+#define PT_MARK(idx)
+#endif
+enum { PT_LOAD = 0, PT_SYRK, PT_CHOL, PT_EQ, PT_SOLVE, PT_INITSHIFT, PT_MID, PT_POST, PT_SCAL_RESID, PT_PRE, PT_BUILD, PT_OUT };
+
 struct FusedArgs {
     Ws g;                 // global arrays of the shard (problem data, outputs, per-problem words)
     FusedOffsets off;
@@ -329,10 +349,10 @@ struct FusedArgs {
 
 constexpr int FUSED_MAX_CONES = 64;
 
-template <int MAXT, int NP, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
+template <int MAXT, int NP, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) k_fused_solve(FusedArgs a) {
     extern __shared__ __align__(16) double sm[];
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     __shared__ int iscratch[32];
     __shared__ int s_prob;
     __shared__ int s_kind[FUSED_MAX_CONES], s_offs[FUSED_MAX_CONES], s_dim[FUSED_MAX_CONES];
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
     const ConeLayout& L = w.L;
     const int n = L.n, p = L.p, k = L.k;
     w.x = sm + o.x; w.y = sm + o.y; w.z = sm + o.z; w.s = sm + o.s;
-    w.lam = sm + o.lam; w.wb = sm + o.wb; w.eta = sm + o.eta;
+    w.lam = sm + o.lam; w.wb = sm + o.wb; w.iwb = sm + o.iwb; w.eta = sm + o.eta;
     w.dx = sm + o.dx; w.dy = sm + o.dy; w.dz = sm + o.dz; w.ds = sm + o.ds;
     w.rx = sm + o.rx; w.ry = sm + o.ry; w.rz = sm + o.rz; w.rs = sm + o.rs;
     w.k0 = sm + o.k0; w.k2 = sm + o.k2; w.u = sm + o.u; w.kt2 = sm + o.kt2; w.kt3 = sm + o.kt3;
@@ -382,6 +402,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
         const int b = s_prob;
         __syncthreads();
         if (b >= a.batch) break;
+        PT_INIT();
 
         // ---- load the problem (global -> shared)
         {
@@ -406,6 +427,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
         for (int i = tid; i < p; i += blockDim.x) w.dy[i] = bs[i];
         __syncthreads();
 
+        PT_MARK(PT_LOAD);
         const double* src = G;      // operand of the SYRK: G for the initial point, Gt = W^-1 G afterwards
         int phase = 0;              // 0: initial point, 1: affine direction (solve #1), 2: combined (solve #2)
         int it = 0;
@@ -415,7 +437,9 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
                 // ---- KKT factor, src/densesolver.jl:41-52
                 cta_syrk_dmma<MAXT>(src, o.ldg, o.kpad4, n, o.npad, H, o.ldh);          // :42-43
                 __syncthreads();
+                PT_MARK(PT_SYRK);
                 int ok = cta_chol_inv<NP, NWARPS>(H, Li, n, o.ldh, dinv, w.fail, tid, lane, warp);        // :47-48
+                PT_MARK(PT_CHOL);
                 if (ok && p > 0) {
                     for (int q = 0; q < p; ++q) {                                        // HiAt[:,q] = H^-1 A[q,:]'  :49
                         for (int i = tid; i < n; i += blockDim.x) HiAt[q * n + i] = A[i * p + q];
@@ -431,6 +455,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
                     __syncthreads();
                     cta_chol_inv<NP, NWARPS>(M, Mi, p, o.ldm, dinv + n, w.fail, tid, lane, warp);         // :51
                 }
+                PT_MARK(PT_EQ);
             }
             if (!*w.fail) {
                 // ---- middle of solve_kkt, src/densesolver.jl:66-85: in u = W^-2 k2, out rx, ry, u = G cx - k2
@@ -447,6 +472,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
                 cta_gemv_n(G, o.ldg, k, n, w.rx, w.u, 1.0, w.k2, -1.0, nullptr, 0.0);   // k1 = G cx - k2  :84-85
             }
             __syncthreads();
+            PT_MARK(PT_SOLVE);
 
             if (phase == 0) {
                 if (*w.fail) {
@@ -462,20 +488,23 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
                 __syncthreads();
                 dev_init_shift(w, 0, a.P, scratch);                                      // src/solver.jl:86-104
                 __syncthreads();
+                PT_MARK(PT_INITSHIFT);
             } else if (phase == 1) {
                 if (!dev_mid(w, 0, a.P, scratch, iscratch)) break;                       // :128-140 + head of solve #2
                 __syncthreads();
+                PT_MARK(PT_MID);
                 phase = 2;
                 need_factor = false;
                 continue;
             } else {
                 if (!dev_post(w, 0, a.P, scratch, iscratch)) break;                      // :143-150
                 __syncthreads();
+                PT_MARK(PT_POST);
                 ++it;
             }
             // ---- top of a Mehrotra iteration, src/solver.jl:105-126
             if (it >= a.P.max_iter) break;
-            dev_scaling(L, 0, w.s, w.z, w.lam, w.wb, w.eta, w.fail);                     // :106
+            dev_scaling(L, 0, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail);                     // :106
             cta_gemv_t(G, o.ldg, k, n, w.z, w.dx, -1.0, cs, -1.0, nullptr, 0.0);         // negated residuals :110-118,:125
             cta_gemv_n(G, o.ldg, k, n, w.x, w.dz, -1.0, w.s, -1.0, hs, 1.0);
             __syncthreads();
@@ -484,8 +513,10 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
                 cta_gemv_n(A, p, p, n, w.x, w.dy, -1.0, bs, 1.0, nullptr, 0.0);
                 __syncthreads();
             }
+            PT_MARK(PT_SCAL_RESID);
             if (!dev_pre(w, 0, a.P, it, scratch)) break;                                 // :120-125 + head of solve #1
             __syncthreads();
+            PT_MARK(PT_PRE);
             // Gt = W^-1 G, column by column (setup_iter, :41-43).  H/Li of the previous factorisation alias Gt:
             // its pad rows / pad columns must be zero again.
             {
@@ -495,16 +526,16 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
                     Gt[(n + q / o.kpad4) * o.ldg + (q % o.kpad4)] = 0.0;
                 for (int c = 0; c < L.ncones; ++c) {
                     const int kind = s_kind[c], offs = s_offs[c], dim = s_dim[c];
-                    const double eta = w.eta[c];
                     for (int col = warp; col < n; col += nw) {
                         const double* sp = G + col * o.ldg + offs;
                         double* dp = Gt + col * o.ldg + offs;
-                        if (kind == KIND_POC) warp_poc_apply<APPLY_WINV>(w.wb + offs, sp, dp, dim, lane);
-                        else warp_soc_apply<APPLY_WINV>(w.wb + offs, eta, sp, dp, dim, lane);
+                        if (kind == KIND_POC) warp_poc_apply<APPLY_WINV>(w.wb + offs, w.iwb + offs, sp, dp, dim, lane);
+                        else warp_soc_apply<APPLY_WINV>(w.wb + offs, w.eta + c, L.ncones, sp, dp, dim, lane);
                     }
                 }
             }
             __syncthreads();
+            PT_MARK(PT_BUILD);
             src = Gt;
             phase = 1;
             need_factor = true;
@@ -536,13 +567,14 @@ __global__ void __launch_bounds__(NWARPS * 32) k_fused_solve(FusedArgs a) {
             if (tid == 0) { w.sc->pobj = po; w.sc->dobj = d; }
         }
         __syncthreads();
+        PT_MARK(PT_OUT);
     }
 }
 
-template <int MAXT, int NP, int NWARPS>
+template <int MAXT, int NP, int NWARPS, int MINB>
 inline void fused_launch(const FusedPlan& plan, const FusedArgs& args, int grid, cudaStream_t stream) {
-    cudaFuncSetAttribute(k_fused_solve<MAXT, NP, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    k_fused_solve<MAXT, NP, NWARPS><<<grid, NWARPS * 32, plan.smem, stream>>>(args);
+    cudaFuncSetAttribute(k_fused_solve<MAXT, NP, NWARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    k_fused_solve<MAXT, NP, NWARPS, MINB><<<grid, NWARPS * 32, plan.smem, stream>>>(args);
 }
 
 inline void solve_fused(FusedPlan& plan, const Ws& g, int batch, int max_iter, double tol, double step_damp,
@@ -556,10 +588,11 @@ inline void solve_fused(FusedPlan& plan, const Ws& g, int batch, int max_iter, d
     args.counter = plan.d_counter;
     const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
     switch (plan.variant) {
-        case 0: fused_launch<2, 16, 2>(plan, args, grid, stream); break;     // n <= 16  (64 threads)
-        case 1: fused_launch<4, 32, 4>(plan, args, grid, stream); break;     // n <= 32  (128 threads)
-        case 2: fused_launch<4, 64, 8>(plan, args, grid, stream); break;     // n <= 64  (256 threads)
-        default: fused_launch<12, 128, 8>(plan, args, grid, stream); break;  // n <= 104 (256 threads)
+        // last parameter: resident CTAs per SM the register allocation must allow
+        case 0: fused_launch<2, 16, 2, 12>(plan, args, grid, stream); break;     // n <= 16  (64 threads, <= 80 regs)
+        case 1: fused_launch<4, 32, 4, 4>(plan, args, grid, stream); break;      // n <= 32  (128 threads, <= 128 regs)
+        case 2: fused_launch<4, 64, 8, 2>(plan, args, grid, stream); break;      // n <= 64  (256 threads, <= 128 regs)
+        default: fused_launch<12, 128, 8, 1>(plan, args, grid, stream); break;   // n <= 104 (256 threads)
     }
 }
 

@@ -191,7 +191,7 @@ void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
     const int n = w.L.n, p = w.L.p;
     const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)) );
     dim3 g((n + cols_per_cta - 1) / cols_per_cta, sh.batch);
-    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active);
+    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active);
     const bool aa = add_aa && p > 0 && sh.any_sing;
     syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0,
          aa ? w.AA : nullptr, (int64_t)w.ldh * n, w.ldh, w.sing, active);
@@ -264,7 +264,7 @@ void solve_tiled(Shard& sh, const socp_params& prm) {
     initial_point(sh, P);
     int itmax = 0;
     for (int it = 0; it < prm.max_iter; ++it) {
-        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.eta, w.fail, w.active);   // :106
+        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, w.active);   // :106
         // negated residuals                                                           :110-118,:125
         gemv_t(sh, w.G, w.sG, k, k, n, w.z, k, w.dx, n, -1.0, epi(w.c, -1.0, n), w.active);
         if (p > 0) {
@@ -319,7 +319,8 @@ void build_shard(socp_handle* h, Shard& sh) {
     w.x = sh.alloc<double>((size_t)B * n);  w.y = sh.alloc<double>((size_t)B * p);
     w.z = sh.alloc<double>((size_t)B * k);  w.s = sh.alloc<double>((size_t)B * k);
     w.lam = sh.alloc<double>((size_t)B * k); w.wb = sh.alloc<double>((size_t)B * k);
-    w.eta = sh.alloc<double>((size_t)B * nc);
+    w.iwb = sh.alloc<double>((size_t)B * k);
+    w.eta = sh.alloc<double>((size_t)B * 4 * nc);
     w.dx = sh.alloc<double>((size_t)B * n);  w.dy = sh.alloc<double>((size_t)B * p);
     w.dz = sh.alloc<double>((size_t)B * k);  w.ds = sh.alloc<double>((size_t)B * k);
     w.rx = sh.alloc<double>((size_t)B * n);  w.ry = sh.alloc<double>((size_t)B * p);
@@ -372,7 +373,7 @@ void prepare_problem(Shard& sh, bool have_sing) {
         (void)g2;
         const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
         dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
-        LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.eta, w.Gt, w.ldgt, 1, cols_per_cta, (const int*)nullptr);
+        LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 1, cols_per_cta, (const int*)nullptr);
         syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0,
              0, nullptr, nullptr);
         potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr);
@@ -735,19 +736,19 @@ int socp_b200_compute_scaling(socp_handle* h, const double* s, const double* z, 
         h2d(sh, w.s, s + f * k, sizeof(double) * B * k);
         h2d(sh, w.z, z + f * k, sizeof(double) * B * k);
         CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
-        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.eta, w.fail, (const int*)nullptr);
+        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, (const int*)nullptr);
         if (lambda) d2h(sh, lambda + f * k, w.lam, sizeof(double) * B * k);
         if (wbs) d2h(sh, wbs + f * k, w.wb, sizeof(double) * B * k);
         if (fail) d2h(sh, fail + f, w.fail, sizeof(int) * B);
         std::vector<double> eta;
         const int nc = w.L.ncones;
-        if (mu) { eta.resize((size_t)B * nc); d2h(sh, eta.data(), w.eta, sizeof(double) * B * nc); }
+        if (mu) { eta.resize((size_t)B * 4 * nc); d2h(sh, eta.data(), w.eta, sizeof(double) * B * 4 * nc); }
         CK(cudaStreamSynchronize(sh.stream));
         if (mu) {
             const int no = (int)h->kind.size();
             for (int b = 0; b < B; ++b)
                 for (int c = 0; c < no; ++c)
-                    mu[(f + b) * no + c] = h->kind[c] == SOCP_CONE_SOC ? eta[(size_t)b * nc + h->first_work[c]] : 0.0;
+                    mu[(f + b) * no + c] = h->kind[c] == SOCP_CONE_SOC ? eta[(size_t)b * 4 * nc + h->first_work[c]] : 0.0;
         }
         sh.have_scaling = true;
         sh.have_factor = false;
@@ -786,9 +787,9 @@ static int apply_common(socp_handle* h, const double* in, double* out, int mode)
     if (h && (!in || !out)) return SOCP_ERR_NULL;
     STEP_PROLOGUE(sh.have_scaling, "needs compute_scaling first")
         h2d(sh, w.kt2, in + f * k, sizeof(double) * B * k);
-        if (mode == 0) LAUNCH(sh, k_apply<APPLY_W>, B, sh.threads, 0, w.L, w.wb, w.eta, w.kt2, w.kt3);
-        else if (mode == 1) LAUNCH(sh, k_apply<APPLY_WINV>, B, sh.threads, 0, w.L, w.wb, w.eta, w.kt2, w.kt3);
-        else LAUNCH(sh, k_apply<APPLY_WINV2>, B, sh.threads, 0, w.L, w.wb, w.eta, w.kt2, w.kt3);
+        if (mode == 0) LAUNCH(sh, k_apply<APPLY_W>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, w.kt2, w.kt3);
+        else if (mode == 1) LAUNCH(sh, k_apply<APPLY_WINV>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, w.kt2, w.kt3);
+        else LAUNCH(sh, k_apply<APPLY_WINV2>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, w.kt2, w.kt3);
         d2h(sh, out + f * k, w.kt3, sizeof(double) * B * k);
     STEP_EPILOGUE
 }
@@ -875,5 +876,17 @@ int socp_b200_get_H(socp_handle* h, double* out) {
     }
     return 0;
 }
+
+#ifdef SOCP_PHASE_TIMING
+// profiling build only (not declared in include/socp_b200.h)
+int socp_b200_debug_phase_clocks(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, socp::g_phase_clk, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(socp::g_phase_clk, z, sizeof z);
+    }
+    return 0;
+}
+#endif
 
 }  // extern "C"

@@ -23,7 +23,7 @@ struct Ws {
     // iterate
     double *x, *y, *z, *s;
     // scaling
-    double *lam, *wb, *eta;
+    double *lam, *wb, *iwb, *eta;   // eta: 4 scalars per cone (eta, 1/eta, 1/eta^2, 1/(1+wbar0)), [4][ncones]
     // right-hand side / direction
     double *dx, *dy, *dz, *ds;
     double *rx, *ry, *rz, *rs;
@@ -46,37 +46,39 @@ struct LoopParams {
 
 // ------------------------------------------------------------ step-level kernels
 __device__ __forceinline__ void dev_scaling(const ConeLayout& L, int b, const double* s, const double* z,
-                                            double* lam, double* wb, double* eta, int* fail) {
+                                            double* lam, double* wb, double* iwb, double* eta, int* fail) {
     const int lane = threadIdx.x & 31;
     const double* sb = SOCP_VEC(s, L.k);
     const double* zb = SOCP_VEC(z, L.k);
     double* lb = SOCP_VEC(lam, L.k);
     double* wbb = SOCP_VEC(wb, L.k);
-    double* eb = SOCP_VEC(eta, L.ncones);
+    double* iwbb = SOCP_VEC(iwb, L.k);
+    double* eb = SOCP_VEC(eta, 4 * L.ncones);
     int f = 0;
     SOCP_FOR_EACH_CONE(L, c, kind, offs, dim) {
         if (kind == KIND_POC) {
-            f |= warp_poc_scaling(sb + offs, zb + offs, dim, lane, lb + offs, wbb + offs);
+            f |= warp_poc_scaling(sb + offs, zb + offs, dim, lane, lb + offs, wbb + offs, iwbb + offs);
             if (lane == 0) eb[c] = 0.0;
         } else {
-            f |= warp_soc_scaling(sb + offs, zb + offs, dim, lane, lb + offs, wbb + offs, eb + c);
+            f |= warp_soc_scaling(sb + offs, zb + offs, dim, lane, lb + offs, wbb + offs, eb + c, L.ncones);
         }
     }
     if (f && lane == 0) atomicOr(fail + b, 1);
 }
 __global__ void k_scaling(ConeLayout L, const double* __restrict__ s, const double* __restrict__ z,
-                          double* __restrict__ lam, double* __restrict__ wb, double* __restrict__ eta,
-                          int* __restrict__ fail, const int* __restrict__ active) {
+                          double* __restrict__ lam, double* __restrict__ wb, double* __restrict__ iwb,
+                          double* __restrict__ eta, int* __restrict__ fail, const int* __restrict__ active) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
-    dev_scaling(L, b, s, z, lam, wb, eta, fail);
+    dev_scaling(L, b, s, z, lam, wb, iwb, eta, fail);
 }
 
 template <int MODE>
-__global__ void k_apply(ConeLayout L, const double* __restrict__ wb, const double* __restrict__ eta,
-                        const double* v, double* out) {
+__global__ void k_apply(ConeLayout L, const double* __restrict__ wb, const double* __restrict__ iwb,
+                        const double* __restrict__ eta, const double* v, double* out) {
     const int b = blockIdx.x;
-    cta_apply<MODE>(L, SOCP_VEC(wb, L.k), SOCP_VEC(eta, L.ncones), SOCP_VEC(v, L.k), SOCP_VEC(out, L.k));
+    cta_apply<MODE>(L, SOCP_VEC(wb, L.k), SOCP_VEC(iwb, L.k), SOCP_VEC(eta, 4 * L.ncones), SOCP_VEC(v, L.k),
+                    SOCP_VEC(out, L.k));
 }
 __global__ void k_vprod(ConeLayout L, const double* u, const double* v, double* t) {
     const int b = blockIdx.x;
@@ -95,13 +97,13 @@ __global__ void k_make_e(ConeLayout L, double* out) {
     }
 }
 __global__ void k_max_step(ConeLayout L, const double* x, double* out) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     const int b = blockIdx.x;
     const double m = block_max(cta_max_step_partial(L, SOCP_VEC(x, L.k)), scratch);
     if (threadIdx.x == 0) out[b] = m;
 }
 __global__ void k_compute_step(ConeLayout L, const double* lam, const double* ds, const double* dz, double* out) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     const int b = blockIdx.x;
     int f = 0;
     const double* lb = SOCP_VEC(lam, L.k);
@@ -115,15 +117,16 @@ __global__ void k_compute_step(ConeLayout L, const double* lam, const double* ds
 // identity != 0: Gt = G (initial point / sing detection, W = I).
 __global__ void __launch_bounds__(256)
 k_build_gt(ConeLayout L, const double* __restrict__ G, int64_t sG, const double* __restrict__ wb,
-           const double* __restrict__ eta, double* __restrict__ Gt, int ldgt, int identity, int cols_per_cta,
-           const int* __restrict__ active) {
+           const double* __restrict__ iwb, const double* __restrict__ eta, double* __restrict__ Gt, int ldgt,
+           int identity, int cols_per_cta, const int* __restrict__ active) {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double* Gb = G + (int64_t)b * sG;
     double* Gtb = Gt + (int64_t)b * ldgt * L.n;
     const double* wbb = SOCP_VEC(wb, L.k);
-    const double* eb = SOCP_VEC(eta, L.ncones);
+    const double* iwbb = SOCP_VEC(iwb, L.k);
+    const double* eb = SOCP_VEC(eta, 4 * L.ncones);
     const int c0 = blockIdx.x * cols_per_cta;
     const int c1 = min(L.n, c0 + cols_per_cta);
     const int ntask = (c1 - c0) * L.ncones;
@@ -135,9 +138,9 @@ k_build_gt(ConeLayout L, const double* __restrict__ G, int64_t sG, const double*
         if (identity) {
             for (int i = lane; i < dim; i += 32) dst[i] = src[i];
         } else if (kind == KIND_POC) {
-            warp_poc_apply<APPLY_WINV>(wbb + offs, src, dst, dim, lane);
+            warp_poc_apply<APPLY_WINV>(wbb + offs, iwbb + offs, src, dst, dim, lane);
         } else {
-            warp_soc_apply<APPLY_WINV>(wbb + offs, eb[c], src, dst, dim, lane);
+            warp_soc_apply<APPLY_WINV>(wbb + offs, eb + c, L.ncones, src, dst, dim, lane);
         }
     }
 }
@@ -188,7 +191,9 @@ __device__ __forceinline__ void kkt_head(const Ws& w, int b) {
     const int lane = threadIdx.x & 31;
     const double* lam = SOCP_VEC(w.lam, L.k);
     const double* wb = SOCP_VEC(w.wb, L.k);
-    const double* eta = SOCP_VEC(w.eta, L.ncones);
+    const double* iwb = SOCP_VEC(w.iwb, L.k);
+    const double* eta = SOCP_VEC(w.eta, 4 * L.ncones);
+    const int nc = L.ncones;
     const double* ds = SOCP_VEC(w.ds, L.k);
     const double* dz = SOCP_VEC(w.dz, L.k);
     double* k0 = SOCP_VEC(w.k0, L.k);
@@ -198,17 +203,17 @@ __device__ __forceinline__ void kkt_head(const Ws& w, int b) {
         if (kind == KIND_POC) {
             warp_poc_iprod(lam + offs, ds + offs, k0 + offs, dim, lane);
             __syncwarp();
-            warp_poc_apply<APPLY_W>(wb + offs, k0 + offs, k2 + offs, dim, lane);
+            warp_poc_apply<APPLY_W>(wb + offs, iwb + offs, k0 + offs, k2 + offs, dim, lane);
         } else {
             warp_soc_iprod(lam + offs, ds + offs, k0 + offs, dim, lane);
             __syncwarp();
-            warp_soc_apply<APPLY_W>(wb + offs, eta[c], k0 + offs, k2 + offs, dim, lane);
+            warp_soc_apply<APPLY_W>(wb + offs, eta + c, nc, k0 + offs, k2 + offs, dim, lane);
         }
         __syncwarp();
         for (int i = lane; i < dim; i += 32) k2[offs + i] = dz[offs + i] - k2[offs + i];
         __syncwarp();
-        if (kind == KIND_POC) warp_poc_apply<APPLY_WINV2>(wb + offs, k2 + offs, u + offs, dim, lane);
-        else warp_soc_apply<APPLY_WINV2>(wb + offs, eta[c], k2 + offs, u + offs, dim, lane);
+        if (kind == KIND_POC) warp_poc_apply<APPLY_WINV2>(wb + offs, iwb + offs, k2 + offs, u + offs, dim, lane);
+        else warp_soc_apply<APPLY_WINV2>(wb + offs, eta + c, nc, k2 + offs, u + offs, dim, lane);
     }
 }
 // solve_kkt tail, reference src/densesolver.jl:86-89: on entry u = G cx - k2;
@@ -219,7 +224,9 @@ __device__ __forceinline__ void kkt_tail(const Ws& w, int b) {
     const ConeLayout& L = w.L;
     const int lane = threadIdx.x & 31;
     const double* wb = SOCP_VEC(w.wb, L.k);
-    const double* eta = SOCP_VEC(w.eta, L.ncones);
+    const double* iwb = SOCP_VEC(w.iwb, L.k);
+    const double* eta = SOCP_VEC(w.eta, 4 * L.ncones);
+    const int nc = L.ncones;
     const double* u = SOCP_VEC(w.u, L.k);
     double* k0 = SOCP_VEC(w.k0, L.k);
     double* rz = SOCP_VEC(w.rz, L.k);
@@ -228,20 +235,20 @@ __device__ __forceinline__ void kkt_tail(const Ws& w, int b) {
     double* kt2 = SOCP_VEC(w.kt2, L.k);
     SOCP_FOR_EACH_CONE(L, c, kind, offs, dim) {
         const bool poc = (kind == KIND_POC);
-        if (poc) warp_poc_apply<APPLY_WINV2>(wb + offs, u + offs, rz + offs, dim, lane);
-        else warp_soc_apply<APPLY_WINV2>(wb + offs, eta[c], u + offs, rz + offs, dim, lane);
+        if (poc) warp_poc_apply<APPLY_WINV2>(wb + offs, iwb + offs, u + offs, rz + offs, dim, lane);
+        else warp_soc_apply<APPLY_WINV2>(wb + offs, eta + c, nc, u + offs, rz + offs, dim, lane);
         __syncwarp();
-        if (poc) warp_poc_apply<APPLY_W>(wb + offs, rz + offs, kt3 + offs, dim, lane);
-        else warp_soc_apply<APPLY_W>(wb + offs, eta[c], rz + offs, kt3 + offs, dim, lane);
+        if (poc) warp_poc_apply<APPLY_W>(wb + offs, iwb + offs, rz + offs, kt3 + offs, dim, lane);
+        else warp_soc_apply<APPLY_W>(wb + offs, eta + c, nc, rz + offs, kt3 + offs, dim, lane);
         __syncwarp();
         for (int i = lane; i < dim; i += 32) k0[offs + i] -= kt3[offs + i];      // :88  (k0 - W cz = W^-1 cs = kt2)
         __syncwarp();
-        if (poc) warp_poc_apply<APPLY_W>(wb + offs, k0 + offs, rs + offs, dim, lane);
-        else warp_soc_apply<APPLY_W>(wb + offs, eta[c], k0 + offs, rs + offs, dim, lane);
+        if (poc) warp_poc_apply<APPLY_W>(wb + offs, iwb + offs, k0 + offs, rs + offs, dim, lane);
+        else warp_soc_apply<APPLY_W>(wb + offs, eta + c, nc, k0 + offs, rs + offs, dim, lane);
         __syncwarp();
         // kt2 = W^-1 cs, reference src/solver.jl:129 (applied, not shortcut, to keep the rounding)
-        if (poc) warp_poc_apply<APPLY_WINV>(wb + offs, rs + offs, kt2 + offs, dim, lane);
-        else warp_soc_apply<APPLY_WINV>(wb + offs, eta[c], rs + offs, kt2 + offs, dim, lane);
+        if (poc) warp_poc_apply<APPLY_WINV>(wb + offs, iwb + offs, rs + offs, kt2 + offs, dim, lane);
+        else warp_soc_apply<APPLY_WINV>(wb + offs, eta + c, nc, rs + offs, kt2 + offs, dim, lane);
     }
 }
 
@@ -267,7 +274,7 @@ __device__ __forceinline__ void dev_init_shift(const Ws& w, int b, const LoopPar
     }
 }
 __global__ void k_init_shift(Ws w, LoopParams P) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     const int b = blockIdx.x;
     if (!w.active[b]) return;
     dev_init_shift(w, b, P, scratch);
@@ -294,10 +301,7 @@ __device__ __forceinline__ int dev_pre(const Ws& w, int b, const LoopParams& P, 
         gap = fma(z[i], s[i], gap);
         ll = fma(lam[i], lam[i], ll);
     }
-    nx = block_sum(nx, scratch);
-    ny = block_sum(ny, scratch);
-    gap = block_sum(gap, scratch);
-    ll = block_sum(ll, scratch);
+    block_sum4(nx, ny, gap, ll, scratch);
     const double resid = sqrt(nx) + sqrt(ny) + gap;
     if (threadIdx.x == 0) {
         w.sc[b].resid = resid;
@@ -317,7 +321,7 @@ __device__ __forceinline__ int dev_pre(const Ws& w, int b, const LoopParams& P, 
     return 1;
 }
 __global__ void k_pre(Ws w, LoopParams P, int it) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     const int b = blockIdx.x;
     if (!w.active[b]) return;
     dev_pre(w, b, P, it, scratch);
@@ -347,7 +351,7 @@ __device__ __forceinline__ int dev_mid(const Ws& w, int b, const LoopParams& P, 
     for (int i = threadIdx.x; i < L.k; i += blockDim.x) dot = fma(kt2[i], kt3[i], dot);
     dot = block_sum(dot, scratch);
     const double ll = w.sc[b].ll;
-    const double rho = 1.0 - t - t * t * dot / ll;             // :132 (minus: reference quirk)
+    const double rho = 1.0 - t - t * t * dot * fast_rcp(ll);   // :132 (minus: reference quirk)
     const double cl = fmax(0.0, fmin(1.0, rho));
     const double sig = cl * cl * cl;                           // :133
     const double mu = ll / (double)L.deg;                      // :134
@@ -375,7 +379,7 @@ __device__ __forceinline__ int dev_mid(const Ws& w, int b, const LoopParams& P, 
     return 1;
 }
 __global__ void k_mid(Ws w, LoopParams P) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     __shared__ int iscratch[32];
     const int b = blockIdx.x;
     if (!w.active[b]) return;
@@ -422,7 +426,7 @@ __device__ __forceinline__ int dev_post(const Ws& w, int b, const LoopParams& P,
     return 1;
 }
 __global__ void k_post(Ws w, LoopParams P) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     __shared__ int iscratch[32];
     const int b = blockIdx.x;
     if (!w.active[b]) return;
@@ -431,7 +435,7 @@ __global__ void k_post(Ws w, LoopParams P) {
 
 // Problems that failed in the initial factorisation / still running at the end.
 __global__ void k_finalize(Ws w, int phase) {
-    __shared__ double scratch[32];
+    __shared__ double scratch[128];
     const int b = blockIdx.x;
     const ConeLayout& L = w.L;
     if (phase == 0) {          // after the initial-point factorisation

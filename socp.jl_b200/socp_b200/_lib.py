@@ -63,7 +63,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # SOCP_B200_LIB lets tools/ load the profiling build; the product default is the in-tree library
+    return os.environ.get("SOCP_B200_LIB", _build.LIB_PATH)
 
 
 def load():

@@ -10,6 +10,7 @@ ROOT = os.path.dirname(PKG_DIR)                     # socp.jl_b200/
 CSRC = os.path.join(ROOT, "csrc")
 LIB_DIR = os.path.join(ROOT, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsocp_b200.so")
+PROF_LIB_PATH = os.path.join(LIB_DIR, "libsocp_b200_prof.so")   # -DSOCP_PHASE_TIMING build (tools/ only)
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -41,6 +42,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write(res.stderr)
     return LIB_PATH
+
+
+def build_prof() -> str:
+    """Profiling variant with per-phase clock64() counters in the fused kernel (tools/phase_timing.py)."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DSOCP_PHASE_TIMING", "-o", PROF_LIB_PATH,
+                                                          os.path.join(CSRC, "solver.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building the profiling library")
+    return PROF_LIB_PATH
 
 
 if __name__ == "__main__":

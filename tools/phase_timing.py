@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Per-phase cycle breakdown of the fused whole-solve kernel (CTA 0), using the -DSOCP_PHASE_TIMING build.
+usage: python tools/phase_timing.py C2 --batch 2960"""
+import argparse, ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "socp.jl_b200"))
+from socp_b200 import build as B
+os.environ["SOCP_B200_LIB"] = B.PROF_LIB_PATH
+if not os.path.exists(B.PROF_LIB_PATH):
+    B.build_prof()
+import numpy as np
+import socp_b200 as sb
+from socp_b200 import generators as gen, _lib
+ap = argparse.ArgumentParser(); ap.add_argument("config"); ap.add_argument("--batch", type=int, default=2960)
+a = ap.parse_args()
+prob = gen.make_config(a.config, batch=a.batch)
+ss = sb.SolverState(prob)
+lib = _lib.load()
+prm = sb.default_params(path=2)
+r = sb.solve_socp_batch(prob, ss, prm, want_iterates=False)      # warm
+buf = (C.c_ulonglong * 16)()
+lib.socp_b200_debug_phase_clocks(buf, 1)
+r = sb.solve_socp_batch(prob, ss, prm, want_iterates=False)
+lib.socp_b200_debug_phase_clocks(buf, 0)
+names = ["load", "syrk", "chol_inv", "eq(HiAt,M)", "solve_mid", "init_shift", "mid", "post", "scaling+resid", "pre", "build_gt", "out"]
+tot = sum(buf[i] for i in range(12))
+print(a.config, "batch", a.batch, "solve_ms %.3f" % r.timings["solve_ms"], "mean iters %.2f" % r.iters.mean())
+for i, nm in enumerate(names):
+    print(f"  {nm:14s} {buf[i]:12d} clk  {100.0*buf[i]/max(tot,1):5.1f}%")
+print("  total          %12d clk (CTA 0, all its problems)" % tot)
