@@ -272,22 +272,24 @@ k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
 }
 
 // ---------------------------------------------------------------------------
-// Blocked Cholesky, panel step (lower, in place, column-major, ld = ldh).
-// For panel starting at column j (width jb = min(NB, n-j)):
-//   every CTA factors the jb x jb diagonal block in shared memory (redundantly);
-//   CTA x == 0 writes it back; CTA x owns rows j+NB+128x .. +128 of the
-//   sub-panel and solves  L21 = A21 L11^-T  with one thread per row (row in
-//   registers).  fail[b] |= 1 on a pivot that is not > 0 (LAPACK dpotrf's info>0,
-//   Julia's PosDefException, reference src/densesolver.jl:47,51).
-// grid (max(1, ceil((n-j-NB)/128)), batch), block 128.
+// Blocked Cholesky, panel step (lower, in place, column-major, ld = ldh), for the
+// panel starting at column j (width jb = min(NB, n-j)), as TWO kernels so that no
+// CTA reads the diagonal block while another one overwrites it:
+//   k_potrf_diag : one CTA per problem factors the jb x jb diagonal block in shared
+//                  memory and writes L11 back; fail[b] |= 1 on a pivot that is not
+//                  > 0 (LAPACK dpotrf's info > 0, Julia's PosDefException, reference
+//                  src/densesolver.jl:47,51).            grid (batch), block 128
+//   k_trsm_panel : CTA x owns rows j+NB+128x .. +128 of the sub-panel and solves
+//                  L21 = A21 L11^-T, one thread per row (row in registers).
+//                                          grid (ceil((n-j-NB)/128), batch), block 128
 // ---------------------------------------------------------------------------
 constexpr int CHOL_NB = 64;
 
 __global__ void __launch_bounds__(128)
-k_potrf_panel(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, int* __restrict__ fail,
-              const int* __restrict__ active) {
+k_potrf_diag(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, int* __restrict__ fail,
+             const int* __restrict__ active) {
     constexpr int NB = CHOL_NB;
-    const int b = blockIdx.y;
+    const int b = blockIdx.x;
     if (active && !active[b]) return;
     __shared__ double D[NB][NB + 1];
     __shared__ int sfail;
@@ -295,9 +297,9 @@ k_potrf_panel(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, in
     const int jb = min(NB, n - j);
     const int tid = threadIdx.x;
     if (tid == 0) sfail = 0;
-    for (int q = tid; q < jb * jb; q += 128) {
-        const int r = q % jb, c = q / jb;
-        D[r][c] = (r >= c) ? Hb[(int64_t)(j + c) * ldh + j + r] : 0.0;
+    for (int c = tid >> 6; c < jb; c += 2) {
+        const int r = tid & 63;
+        if (r < jb) D[r][c] = (r >= c) ? Hb[(int64_t)(j + c) * ldh + j + r] : 0.0;
     }
     __syncthreads();
     for (int c = 0; c < jb; ++c) {
@@ -307,32 +309,46 @@ k_potrf_panel(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, in
             break;
         }
         const double rdiag = sqrt(piv);
+        const double idiag = 1.0 / rdiag;
         __syncthreads();               // everyone has read D[c][c]
-        for (int r = c + tid; r < jb; r += 128) D[r][c] = (r == c) ? rdiag : D[r][c] / rdiag;
+        for (int r = c + tid; r < jb; r += 128) D[r][c] = (r == c) ? rdiag : D[r][c] * idiag;
         __syncthreads();
-        // trailing update of the lower triangle: (r, cc) with c < cc <= r < jb
-        const int m = jb - c - 1;
-        for (int q = tid; q < m * m; q += 128) {
-            const int rr = q % m, cq = q / m;
-            if (rr >= cq) {
-                const int r = c + 1 + rr, cc = c + 1 + cq;
-                D[r][cc] = fma(-D[r][c], D[cc][c], D[r][cc]);
+        // trailing update of the lower triangle: (r, cc) with c < cc <= r < jb; lane -> row, thread group -> column
+        {
+            const int r = c + 1 + (tid & 63);
+            if (r < jb) {
+                const double lr = D[r][c];
+                for (int cc = c + 1 + (tid >> 6); cc <= r; cc += 2) D[r][cc] = fma(-lr, D[cc][c], D[r][cc]);
             }
         }
         __syncthreads();
     }
     __syncthreads();
     if (sfail) {
-        if (tid == 0 && blockIdx.x == 0) fail[b] = 1;
+        if (tid == 0) fail[b] = 1;
         return;
     }
-    if (blockIdx.x == 0) {
-        for (int q = tid; q < jb * jb; q += 128) {
-            const int r = q % jb, c = q / jb;
-            if (r >= c) Hb[(int64_t)(j + c) * ldh + j + r] = D[r][c];
-        }
+    for (int c = tid >> 6; c < jb; c += 2) {
+        const int r = tid & 63;
+        if (r < jb && r >= c) Hb[(int64_t)(j + c) * ldh + j + r] = D[r][c];
     }
-    if (jb < NB) return;               // last (ragged) panel has no rows below
+}
+
+__global__ void __launch_bounds__(128)
+k_trsm_panel(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const int* __restrict__ fail,
+             const int* __restrict__ active) {
+    constexpr int NB = CHOL_NB;
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    if (fail[b]) return;               // the factorisation already failed: leave the rest alone
+    __shared__ double D[NB][NB + 1];
+    double* Hb = H + (int64_t)b * strideH;
+    const int tid = threadIdx.x;
+    for (int c = tid >> 6; c < NB; c += 2) {
+        const int r = tid & 63;
+        D[r][c] = (r >= c) ? Hb[(int64_t)(j + c) * ldh + j + r] : 0.0;
+    }
+    __syncthreads();
     const int row = j + NB + blockIdx.x * 128 + tid;
     if (row >= n) return;
     double a[NB];

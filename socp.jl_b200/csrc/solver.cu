@@ -164,9 +164,10 @@ void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, i
 void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, int* fail, const int* active) {
     for (int j = 0; j < nn; j += CHOL_NB) {
         const int below = nn - j - CHOL_NB;
-        dim3 grid(std::max(1, (below + 127) / 128), sh.batch);
-        LAUNCH(sh, k_potrf_panel, grid, 128, 0, H, sH, ld, nn, j, fail, active);
+        LAUNCH(sh, k_potrf_diag, sh.batch, 128, 0, H, sH, ld, nn, j, fail, active);
         if (below > 0) {
+            dim3 grid((below + 127) / 128, sh.batch);
+            LAUNCH(sh, k_trsm_panel, grid, 128, 0, H, sH, ld, nn, j, (const int*)fail, active);
             const double* P = H + (int64_t)j * ld + (j + CHOL_NB);
             double* T = H + (int64_t)(j + CHOL_NB) * ld + (j + CHOL_NB);
             syrk(sh, false, P, sH, ld, below, CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active);
