@@ -1,0 +1,1035 @@
+// fused_v2.cuh -- whole-solve kernel for layouts that fit in shared memory (second generation).
+//
+// One CTA ("team" of NW warps; a single warp for n <= 16) owns one problem from the initial point
+// to the last Mehrotra step (reference src/solver.jl:68-152).  G, Gt = W^-1 G, the reduced KKT
+// matrix H, the explicit inverse X = L^-1 of its Cholesky factor and every work vector live in
+// shared memory; global traffic is the problem in and the iterate out.  CTAs are persistent and
+// pull problems from an atomic counter.
+//
+// What bounds this kernel is the serial dependency chain of one interior-point iteration, so the
+// design minimises team barriers and reduction rounds:
+//   * cone chains (compute_scaling; solve_kkt head: iprod -> W -> W^-2; tail: W^-2 -> W -> W ->
+//     W^-1 -> scmax) run register-resident on a group of LPC lanes per second-order cone (LPC = 1
+//     for SOC(4): one thread per cone, no shuffles; LPC = 16 for SOC(51)), reductions are xor
+//     shuffles inside the group; positive-orthant rows are elementwise over the whole team
+//   * H = Gt'Gt and every block operation of the factorisation are mma.sync m8n8k4 f64 (SASS
+//     DMMA.8x8x4) on shared-memory tiles with leading dimension == 4 (mod 8): conflict-free
+//     fragment loads
+//   * blocked right-looking Cholesky on 8x8 tiles that carries the inverse along: one warp factors
+//     the diagonal tile redundantly in registers (no shuffles, no barriers), the panel and the
+//     trailing update (of H and of the partially built inverse) are DMMA tile products; two team
+//     barriers per block column instead of one per column
+//   * the solves are two triangular gemvs with X (the reference also applies an explicit inverse,
+//     src/densesolver.jl:48,83); the equality rows ride along (B = X A', K = H^-1 A' M^-1
+//     precomputed per factorisation), so p > 0 adds no barrier to a solve
+//   * stop-test norms, sigma/mu and step-length reductions share one scratch exchange per phase
+//
+// Restrictions (the tiled path takes everything else): no `sing` problems, n <= 64, p <= 32,
+// second-order cones of dimension <= 128, at most 64 of them.
+#pragma once
+#include "tiled_kernels.cuh"
+#include "linalg.cuh"
+#include <vector>
+#include <algorithm>
+
+namespace socp {
+
+constexpr int F2_MAX_SOC = 64;
+constexpr int F2_CS = 8;          // scalars kept per second-order cone
+enum { CS_ETA = 0, CS_IE, CS_IE2, CS_R1W, CS_W0, CS_LAM0, CS_A, CS_LLT };
+
+struct F2Plan {
+    bool fits = false;
+    int variant = 0;       // 0: 1 warp (n<=16), 1: 4 warps (n<=32), 2: 8 warps (n<=56), 3: 8 warps (n<=64)
+    int nw = 1;
+    int ctas_per_sm = 1, num_sms = 148;
+    size_t smem = 0;
+    int* d_counter = nullptr;
+    // layout
+    int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
+    int npad = 0, nb = 0, kpad = 0, ldg = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
+    int split_k = 1, split_n = 1, split_p = 1;    // lanes per output row of the row gemvs (k, n, p rows)
+    int soc_offs[F2_MAX_SOC], soc_dim[F2_MAX_SOC];
+    // offsets into the dynamic shared memory, in doubles
+    int oG, oR, oX, oA, oB, oHiAt, oK, oM, oMX, oMinv, oDinv;
+    int oc, ob, oh, ox, oy, oz, os, olam, owb, oiwb, ocs, odx, ody, odz, ods, ok0, ok2, ou;
+    int on0, ot1, ot, ocx, om0, ocy, oscr;
+    int total = 0;
+};
+
+inline int f2_ld(int rows) {      // smallest ld >= rows with ld == 4 (mod 8)
+    int ld = rows;
+    while (ld % 8 != 4) ++ld;
+    return ld;
+}
+inline int f2_split(int rows, int nw) {   // lanes per row so that one pass of the team covers the rows if possible
+    int split = 32;
+    while (split > 1 && (rows + (32 / split) - 1) / (32 / split) > nw) split >>= 1;
+    return split;
+}
+
+// kind/offs/dim: the CALLER's cones (POC blocks first).
+inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
+                    const std::vector<int>& dim, int device) {
+    P.fits = false;
+    P.n = n; P.p = p; P.k = k;
+    P.kpoc = 0; P.nsoc = 0;
+    int maxd = 1;
+    for (size_t i = 0; i < kind.size(); ++i) {
+        if (kind[i] == KIND_POC) P.kpoc += dim[i];
+        else {
+            if (P.nsoc >= F2_MAX_SOC) return;
+            P.soc_offs[P.nsoc] = offs[i];
+            P.soc_dim[P.nsoc] = dim[i];
+            maxd = std::max(maxd, dim[i]);
+            ++P.nsoc;
+        }
+    }
+    if (maxd > 128 || n > 64 || p > 32) return;
+    P.lpc = 1;
+    while (P.lpc * 4 < maxd) P.lpc <<= 1;
+    if (n <= 16 && p <= 16) { P.variant = 0; P.nw = 1; }
+    else if (n <= 32) { P.variant = 1; P.nw = 4; }
+    else if (n <= 56) { P.variant = 2; P.nw = 8; }
+    else { P.variant = 3; P.nw = 8; }
+    P.npad = (n + 7) / 8 * 8; P.nb = P.npad / 8;
+    P.kpad = (k + 3) / 4 * 4;
+    P.ldg = f2_ld(P.kpad);
+    P.ldh = f2_ld(P.npad);
+    P.ppad = (std::max(p, 1) + 7) / 8 * 8; P.pb = P.ppad / 8;
+    P.ldm = f2_ld(P.ppad);
+    P.split_k = f2_split(k, P.nw);
+    P.split_n = f2_split(n, P.nw);
+    P.split_p = f2_split(std::max(p, 1), P.nw);
+    int at = 0;
+    auto take = [&](int cnt) { int r = at; at += (cnt + 1) / 2 * 2; return r; };
+    P.oG = take(P.ldg * n);
+    const int gt_sz = P.ldg * P.npad, hx_sz = 2 * P.ldh * P.npad;
+    P.oR = take(std::max(gt_sz, hx_sz));
+    P.oX = P.oR + P.ldh * P.npad;
+    P.oA = take(p * n); P.oB = take(n * p); P.oHiAt = take(n * p); P.oK = take(n * p);
+    P.oM = take(p ? P.ldm * P.ppad : 0); P.oMX = take(p ? P.ldm * P.ppad : 0); P.oMinv = take(p * p);
+    P.oDinv = take(2 * 8 * 12);
+    P.oc = take(n); P.ox = take(n); P.odx = take(n); P.on0 = take(n); P.ot1 = take(n); P.ot = take(n); P.ocx = take(n);
+    P.ob = take(p); P.oy = take(p); P.ody = take(p); P.om0 = take(p); P.ocy = take(p);
+    P.oh = take(k); P.oz = take(k); P.os = take(k); P.olam = take(k); P.owb = take(k); P.oiwb = take(P.kpoc);
+    P.odz = take(k); P.ods = take(k); P.ok0 = take(k); P.ok2 = take(k); P.ou = take(k);
+    P.ocs = take(F2_CS * std::max(P.nsoc, 1));
+    P.oscr = take(2 * 8 * 8);
+    P.total = at;
+    P.smem = (size_t)at * sizeof(double);
+    int dev_smem = 0, sms = 148;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    P.num_sms = sms;
+    if (P.smem + 512 > (size_t)dev_smem) return;
+    const int per_sm = 228 * 1024;
+    const int threads = P.nw * 32;
+    const int reg_cap = P.variant == 0 ? 16 : (P.variant == 1 ? 4 : 2);     // matches the __launch_bounds__ below
+    P.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (P.smem + 1024 + 512)), 2048 / threads, 32, reg_cap}));
+    P.fits = true;
+}
+
+// ------------------------------------------------------------------------------------------------ team helpers
+template <int NW>
+__device__ __forceinline__ void tsync() {
+    if (NW == 1) __syncwarp();
+    else __syncthreads();
+}
+__device__ __forceinline__ double grp_sum(double v, int lpc) {
+    for (int o = lpc >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+// Team-wide reduction of four sums, two maxima and one flag through a scratch slot (8 doubles per warp).
+// Contains one team barrier (none for a one-warp team); the caller alternates `scr` between two slots.
+template <int NW>
+__device__ __forceinline__ void team_reduce(double& a, double& b, double& c, double& d, double& mx, double& mx2,
+                                            int& flag, double* scr, int lane, int warp) {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+    mx = warp_max(mx); mx2 = warp_max(mx2);
+    flag = __any_sync(FULL_MASK, flag) ? 1 : 0;
+    if (NW == 1) return;
+    if (lane == 0) {
+        double* q = scr + warp * 8;
+        q[0] = a; q[1] = b; q[2] = c; q[3] = d; q[4] = mx; q[5] = mx2; q[6] = (double)flag;
+    }
+    __syncthreads();
+    a = b = c = d = 0.0; mx = mx2 = -INFINITY;
+    double f = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const double* q = scr + w * 8;
+        a += q[0]; b += q[1]; c += q[2]; d += q[3]; mx = fmax(mx, q[4]); mx2 = fmax(mx2, q[5]); f += q[6];
+    }
+    flag = f != 0.0;
+}
+
+// out(c) = sum_{r in [r_lo(c), rows)} M[c*ld + r] * x[r], four lanes per column; epi(c, acc) runs on one lane.
+template <int NW, bool TRI, class Epi>
+__device__ __forceinline__ void gemv_cols(const double* __restrict__ M, int ld, int rows, int cols,
+                                          const double* __restrict__ x, int lane, int warp, Epi epi) {
+    const int cq = lane >> 2, rl = lane & 3;
+    for (int c0 = warp * 8; c0 < cols; c0 += NW * 8) {
+        const int c = c0 + cq;
+        const bool ok = c < cols;
+        const double* col = M + (ok ? c : 0) * ld;
+        double a0 = 0.0, a1 = 0.0;
+        int r = rl + (TRI ? (c & ~3) : 0);
+        if (TRI && r < c) r += 4;
+        if (ok) {
+            for (; r + 4 < rows; r += 8) {
+                a0 = fma(col[r], x[r], a0);
+                a1 = fma(col[r + 4], x[r + 4], a1);
+            }
+            if (r < rows) a0 = fma(col[r], x[r], a0);
+        }
+        double acc = a0 + a1;
+        acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+        acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+        if (rl == 0 && ok) epi(c, acc);
+    }
+}
+// out(r) = sum_{c in [0, c_hi(r))} M[c*ld + r] * x[c*xs]; `split` lanes per row (power of two); epi(r, acc) on one lane.
+template <int NW, bool TRI, class Epi>
+__device__ __forceinline__ void gemv_rows(const double* __restrict__ M, int ld, int rows, int cols,
+                                          const double* __restrict__ x, int xs, int split, int lane, int warp, Epi epi) {
+    const int rpw = 32 / split;
+    const int rr = lane & (rpw - 1), part = lane / rpw;
+    for (int r0 = warp * rpw; r0 < rows; r0 += NW * rpw) {
+        const int r = r0 + rr;
+        const bool ok = r < rows;
+        const int chi = TRI ? min(cols, r + 1) : cols;
+        double a0 = 0.0, a1 = 0.0;
+        if (ok) {
+            const double* row = M + r;
+            int c = part;
+            for (; c + split < chi; c += 2 * split) {
+                a0 = fma(row[c * ld], x[c * xs], a0);
+                a1 = fma(row[(c + split) * ld], x[(c + split) * xs], a1);
+            }
+            if (c < chi) a0 = fma(row[c * ld], x[c * xs], a0);
+        }
+        double acc = a0 + a1;
+        for (int o = rpw; o < 32; o <<= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+        if (part == 0 && ok) epi(r, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ SYRK
+// H (lower 8x8 tiles, n x n padded to npad with a unit pad diagonal, ld ldh) = S' S for S = kpad x npad (ld ldg,
+// pad rows/columns zero).  Accumulates in registers; tsync; stores (H may alias S).  The caller syncs afterwards.
+template <int NW, int MAXT>
+__device__ __forceinline__ void f2_syrk(const double* S, int ldg, int kpad, int n, int nb, double* H, int ldh,
+                                        int lane, int warp) {
+    const int ntl = nb * (nb + 1) / 2;
+    const int fr = lane >> 2, fk = lane & 3;
+    const double* pa[MAXT];
+    const double* pb[MAXT];
+    int ti[MAXT], tj[MAXT];
+    double acc[MAXT][2];
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        int t = warp + q * NW;
+        if (t >= ntl) t = ntl - 1;                 // duplicates compute a valid tile and skip the store
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= t) ++a;
+        ti[q] = a;
+        tj[q] = t - a * (a + 1) / 2;
+        pa[q] = S + (ti[q] * 8 + fr) * ldg + fk;
+        pb[q] = S + (tj[q] * 8 + fr) * ldg + fk;
+        acc[q][0] = acc[q][1] = 0.0;
+    }
+#pragma unroll 2
+    for (int kk = 0; kk < kpad; kk += 4) {
+#pragma unroll
+        for (int q = 0; q < MAXT; ++q) dmma884(acc[q][0], acc[q][1], pa[q][kk], pb[q][kk]);
+    }
+    tsync<NW>();
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        if (warp + q * NW < ntl) {
+            const int gi = ti[q] * 8 + fr;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = tj[q] * 8 + 2 * fk + e;
+                double v = acc[q][e];
+                if (gi == gj && gi >= n) v = 1.0;
+                H[gj * ldh + gi] = v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ blocked Cholesky + inverse
+// Factor of one 8x8 diagonal tile by one warp.  The Cholesky factor is computed by all lanes redundantly in
+// registers (no shuffles); lane c (mod 8) then computes column c of its inverse by forward substitution, so that
+// on exit xc[i] = (L^-1)[i][c], c = lane & 7 (zero above the diagonal).  Returns 0 on a pivot that is not > 0.
+__device__ __forceinline__ int f2_diag_factor(const double* T, int ld, int lane, double (&xc)[8]) {
+    double a[36];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = T[j * ld + i];
+    double r[8];
+    int ok = 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double d = a[j * (j + 1) / 2 + j];
+        ok &= (d > 0.0);
+        const double rj = fast_rsqrt(d);
+        r[j] = rj;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) a[i * (i + 1) / 2 + j] *= rj;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+            for (int c = j + 1; c <= i; ++c)
+                a[i * (i + 1) / 2 + c] = fma(-a[i * (i + 1) / 2 + j], a[c * (c + 1) / 2 + j], a[i * (i + 1) / 2 + c]);
+    }
+    // column c of the inverse: x_i = 0 (i < c), r_c (i == c), -r_i sum_{m<i} l_im x_m (i > c)
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int m = 0; m < i; ++m) sacc = fma(a[i * (i + 1) / 2 + m], xc[m], sacc);
+        xc[i] = (i == c) ? r[i] : -r[i] * sacc;      // i < c: sacc == 0
+    }
+    return ok;
+}
+
+// H: nbl x nbl lower tiles (column-major, ld), unit pad diagonal.  On exit X (same shape, zero-initialised by
+// the caller in its lower tiles) holds L^-1; H is destroyed.  Dinv: 2 x (8 x 12) scratch, zero above the diagonal.
+// *fail is set (and 0 returned) on a non-positive pivot: cholesky!'s PosDefException, src/densesolver.jl:47,51.
+template <int NW>
+__device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, int nbl, int ld, int* fail,
+                                           int lane, int warp) {
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int b = 0; b < nbl; ++b) {
+        const int b0 = b * 8;
+        double* Db = Dinv + (b & 1) * 96;
+        if (warp == 0) {
+            __syncwarp();
+            double xc[8];
+            const int ok = f2_diag_factor(H + b0 * ld + b0, ld, lane, xc);
+            if (!ok && lane == 0) *fail = 1;
+            // publish column c = lane of the tile's inverse: Dinv (row-major, ld 12) and the diagonal tile of X
+            if (lane < 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    Db[i * 12 + lane] = xc[i];
+                    X[(b0 + lane) * ld + b0 + i] = xc[i];
+                }
+            }
+        }
+        tsync<NW>();                                   // (1) Dinv_b visible; trailing update of step b-1 complete
+        if (*fail) return 0;
+        // ---- panel: H(i,b) <- H(i,b) Dinv_b'  (i > b);   X(b,c) <- Dinv_b X(b,c)  (c < b)
+        for (int t = warp; t < nbl - 1; t += NW) {
+            double c0 = 0.0, c1 = 0.0;
+            if (t < nbl - 1 - b) {
+                const int i0 = (b + 1 + t) * 8;
+                double* T = H + b0 * ld + i0;
+                const double a0 = T[fk * ld + fr], a1 = T[(4 + fk) * ld + fr];
+                const double d0 = Db[fr * 12 + fk], d1 = Db[fr * 12 + 4 + fk];
+                dmma884(c0, c1, a0, d0);
+                dmma884(c0, c1, a1, d1);
+                T[(2 * fk) * ld + fr] = c0;
+                T[(2 * fk + 1) * ld + fr] = c1;
+            } else {
+                const int cc0 = (t - (nbl - 1 - b)) * 8;
+                double* T = X + cc0 * ld + b0;
+                const double d0 = Db[fr * 12 + fk], d1 = Db[fr * 12 + 4 + fk];
+                const double x0 = T[fr * ld + fk], x1 = T[fr * ld + 4 + fk];
+                dmma884(c0, c1, d0, x0);
+                dmma884(c0, c1, d1, x1);
+                T[(2 * fk) * ld + fr] = c0;
+                T[(2 * fk + 1) * ld + fr] = c1;
+            }
+        }
+        tsync<NW>();                                   // (2) panel visible
+        // ---- trailing update: rows i > b, tiles j = 0..i:  j > b: H(i,j) -= L_ib L_jb';  j <= b: X(i,j) -= L_ib X(b,j)
+        // Warp 0 takes the next diagonal tile only (then goes on to factor it); the others share the rest.
+        // Flat tile index over rows i = b+1.. (row i has i+1 tiles, j = 0..i); the next diagonal tile is index b+1.
+        {
+            const int ntile = (nbl * (nbl + 1) - (b + 1) * (b + 2)) / 2;
+            const int stride = (NW > 1) ? NW - 1 : 1;
+            for (int t = (NW > 1) ? warp - 1 : 0;; t += stride) {
+                int tf;
+                if (NW > 1) {
+                    if (warp == 0) { if (t != -1) break; tf = b + 1; }
+                    else { tf = t + (t >= b + 1); }
+                } else tf = t;
+                if (tf >= ntile) break;
+                int i = b + 1, j = tf;
+                while (j > i) { j -= i + 1; ++i; }
+                const int i0 = i * 8;
+                const int j0 = j * 8;
+                const double* Lp = H + b0 * ld + i0;
+                const double a0 = -Lp[fk * ld + fr], a1 = -Lp[(4 + fk) * ld + fr];
+                double c0, c1, q0, q1;
+                double* C;
+                if (j > b) {
+                    C = H + j0 * ld + i0;
+                    const double* Lj = H + b0 * ld + j0;
+                    q0 = Lj[fk * ld + fr]; q1 = Lj[(4 + fk) * ld + fr];
+                    c0 = C[(2 * fk) * ld + fr]; c1 = C[(2 * fk + 1) * ld + fr];
+                } else {
+                    C = X + j0 * ld + i0;
+                    const double* Xb = X + j0 * ld + b0;
+                    q0 = Xb[fr * ld + fk]; q1 = Xb[fr * ld + 4 + fk];
+                    if (j == b) { c0 = 0.0; c1 = 0.0; }
+                    else { c0 = C[(2 * fk) * ld + fr]; c1 = C[(2 * fk + 1) * ld + fr]; }
+                }
+                dmma884(c0, c1, a0, q0);
+                dmma884(c0, c1, a1, q1);
+                C[(2 * fk) * ld + fr] = c0;
+                C[(2 * fk + 1) * ld + fr] = c1;
+            }
+        }
+    }
+    tsync<NW>();
+    return 1;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct F2Args {
+    Ws g;                 // global arrays of the shard
+    F2Plan P;
+    LoopParams prm;
+    int batch;
+    int* counter;
+};
+
+#ifdef SOCP_PHASE_TIMING
+__device__ unsigned long long g_phase_clk2[16];
+#define PT2_DECL() long long pt_t0 = 0
+#define PT2_INIT() pt_t0 = clock64()
+#define PT2_MARK(idx)                                                             \
+    do {                                                                          \
+        if (tid == 0 && blockIdx.x == 0) {                                        \
+            const long long t_ = clock64();                                       \
+            atomicAdd(&g_phase_clk2[idx], (unsigned long long)(t_ - pt_t0));      \
+            pt_t0 = t_;                                                           \
+        }                                                                         \
+    } while (0)
+#else
+#define PT2_DECL()
+#define PT2_INIT()
+#define PT2_MARK(idx)
+#endif
+enum { P2_LOAD = 0, P2_RESID, P2_HEAD_GT, P2_SYRK, P2_CHOL, P2_EQ, P2_SOLVE, P2_INIT, P2_MID, P2_POST, P2_OUT };
+
+// per-thread view of one second-order cone slot: element e of this lane is index g + e*lpc of the cone
+struct SocLane {
+    int offs, dim, g, lpc;
+    bool valid;
+    __device__ __forceinline__ int idx(int e) const { return g + e * lpc; }
+    __device__ __forceinline__ bool tail(int e) const { return valid && idx(e) < dim && idx(e) > 0; }
+    __device__ __forceinline__ bool head() const { return valid && g == 0; }
+};
+struct TailOut { double mx, dot; int fail; };
+
+#define F2_FOR_E _Pragma("unroll") for (int e = 0; e < 4; ++e)
+
+template <int NW, int MAXT, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_prob, s_fail;
+    const F2Plan& P = a.P;
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int T = NW * 32;
+    const int n = P.n, p = P.p, k = P.k, kpoc = P.kpoc, nsoc = P.nsoc, lpc = P.lpc;
+    const int ldg = P.ldg, ldh = P.ldh, npad = P.npad, nb = P.nb, kpad = P.kpad, ldm = P.ldm;
+    double* G = sm + P.oG;
+    double* Gt = sm + P.oR;
+    double* H = sm + P.oR;
+    double* X = sm + P.oX;
+    double* A = sm + P.oA;
+    double* Bm = sm + P.oB;          // X A'            (n x p)
+    double* HiAt = sm + P.oHiAt;     // H^-1 A'         (n x p)
+    double* Km = sm + P.oK;          // H^-1 A' M^-1    (n x p)
+    double* Mm = sm + P.oM;
+    double* MX = sm + P.oMX;
+    double* Minv = sm + P.oMinv;
+    double* Dinv = sm + P.oDinv;
+    double* cv = sm + P.oc;
+    double* bv = sm + P.ob;
+    double* hv = sm + P.oh;
+    double* x = sm + P.ox; double* y = sm + P.oy; double* z = sm + P.oz; double* s = sm + P.os;
+    double* lam = sm + P.olam; double* wb = sm + P.owb; double* iwb = sm + P.oiwb; double* cs = sm + P.ocs;
+    double* dx = sm + P.odx; double* dy = sm + P.ody; double* dz = sm + P.odz; double* ds = sm + P.ods;
+    double* k0 = sm + P.ok0; double* k2 = sm + P.ok2; double* u = sm + P.ou;
+    double* n0 = sm + P.on0; double* t1 = sm + P.ot1; double* tt = sm + P.ot; double* cx = sm + P.ocx;
+    double* m0 = sm + P.om0; double* cy = sm + P.ocy;
+    double* scr = sm + P.oscr;
+    int scr_par = 0;
+    const LoopParams prm = a.prm;
+    PT2_DECL();
+
+    for (int q = tid; q < P.total; q += T) sm[q] = 0.0;
+    tsync<NW>();
+    for (int i = p + tid; i < P.ppad; i += T) Mm[i * ldm + i] = 1.0;       // unit pad diagonal of M (never overwritten)
+
+    // ------------------------------------------------------------------ building blocks (lambdas over the work set)
+    // calls f(SocLane, slot) for every cone slot of this lane's group; all 32 lanes take part in every pass
+    auto for_each_slot = [&](auto&& f) {
+        const int spw = 32 / lpc;
+        for (int base = warp * spw; base < nsoc; base += NW * spw) {
+            SocLane L;
+            const int slot = base + lane / lpc;
+            L.valid = slot < nsoc;
+            L.offs = L.valid ? P.soc_offs[slot] : 0;
+            L.dim = L.valid ? P.soc_dim[slot] : 0;
+            L.g = lane & (lpc - 1);
+            L.lpc = lpc;
+            f(L, L.valid ? slot : 0);
+        }
+    };
+    auto load_tail = [&](const SocLane& L, const double* v, double (&r)[4]) {
+        F2_FOR_E r[e] = L.tail(e) ? v[L.offs + L.idx(e)] : 0.0;
+    };
+    auto wdot = [&](const double (&w)[4], const double (&v)[4]) {     // tails only: masked entries are zero
+        double d = 0.0;
+        F2_FOR_E d = fma(w[e], v[e], d);
+        return grp_sum(d, lpc);
+    };
+
+    // compute_scaling for one second-order cone, src/scalings.jl:32-99 (closed forms)
+    auto soc_scaling = [&](const SocLane& L, int slot, double& gap, double& ll) -> int {
+        double sv[4], zv[4];
+        load_tail(L, s, sv);
+        load_tail(L, z, zv);
+        const double s0 = L.valid ? s[L.offs] : 1.0, z0 = L.valid ? z[L.offs] : 1.0;
+        double ss = 0.0, zz = 0.0, sz = 0.0;
+        F2_FOR_E { ss = fma(sv[e], sv[e], ss); zz = fma(zv[e], zv[e], zz); sz = fma(sv[e], zv[e], sz); }
+        ss = grp_sum(ss, lpc); zz = grp_sum(zz, lpc); sz = grp_sum(sz, lpc);
+        const double onrms = s0 * s0 - ss, onrmz = z0 * z0 - zz;          // :39-45
+        int fail = !(onrms >= 0.0) | !(onrmz >= 0.0);
+        const double is = fast_rsqrt(onrms), iz = fast_rsqrt(onrmz);      // :46-49
+        const double nrms = onrms * is, nrmz = onrmz * iz;
+        const double sb0 = s0 * is, zb0 = z0 * iz;
+        const double ns = sz * (is * iz) + zb0 * sb0;                     // :53-56
+        const double g2 = (1.0 + ns) / 2.0;
+        fail |= !(g2 >= 0.0);
+        const double rg = fast_rsqrt(g2);
+        const double gamma = g2 * rg, ig = 0.5 * rg;                      // :57, :64
+        const double eta = fast_sqrt(nrms * iz);                          // :68
+        const double tmv1 = fast_sqrt(nrms * nrmz);                       // :91
+        const double mult = tmv1 * fast_rcp(zb0 + sb0 + 2.0 * gamma);     // :92
+        const double csf = gamma + zb0, czf = gamma + sb0;                // :93-94
+        double llt = 0.0;
+        F2_FOR_E if (L.tail(e)) {
+            const double sb = sv[e] * is, zb = zv[e] * iz;
+            const double lv = (sb * csf + zb * czf) * mult;               // :95-97
+            const int i = L.offs + L.idx(e);
+            wb[i] = (sb - zb) * ig;                                       // :62,:64
+            lam[i] = lv;
+            llt = fma(lv, lv, llt);
+        }
+        llt = grp_sum(llt, lpc);
+        if (L.head()) {
+            const double w0 = (sb0 + zb0) * ig, l0 = gamma * tmv1, ie = fast_rcp(eta);
+            wb[L.offs] = w0;                                              // :60
+            lam[L.offs] = l0;                                             // :98
+            double* c = cs + slot * F2_CS;
+            c[CS_ETA] = eta; c[CS_IE] = ie; c[CS_IE2] = ie * ie; c[CS_R1W] = fast_rcp(1.0 + w0);
+            c[CS_W0] = w0; c[CS_LAM0] = l0; c[CS_A] = l0 * l0 - llt; c[CS_LLT] = llt;
+            gap += s0 * z0 + sz;
+            ll += l0 * l0 + llt;
+        }
+        return L.valid ? fail : 0;
+    };
+
+    // solve_kkt head for one cone (src/densesolver.jl:61-66, then the W^-2 of :86 applied to k2):
+    // k0 = lam \ ds, k2 = dzs*dz - W k0, u = W^-2 k2.  dsv/ds0: the cone's ds (tail in registers, head scalar).
+    auto soc_head = [&](const SocLane& L, int slot, const double (&lv)[4], const double (&wv)[4],
+                        const double (&dsv)[4], double ds0, double dzs) {
+        const double* c = cs + slot * F2_CS;
+        const double eta = c[CS_ETA], ie2 = c[CS_IE2], r1w = c[CS_R1W], w0 = c[CS_W0], l0 = c[CS_LAM0], aa = c[CS_A];
+        const double beta = wdot(lv, dsv);
+        const double ia = fast_rcp(aa), il0 = fast_rcp(l0);
+        double k0v[4], k2v[4];
+        const double k00 = (l0 * ds0 - beta) * ia;                                   // src/vectors.jl:105-125, O(d) form
+        F2_FOR_E k0v[e] = L.tail(e) ? (-ds0 * lv[e] + (aa * dsv[e] + beta * lv[e]) * il0) * ia : 0.0;
+        const double dl = wdot(wv, k0v);
+        const double cst = k00 + dl * r1w;                                           // src/scalings.jl:135
+        const double k20 = (L.valid ? dz[L.offs] * dzs : 0.0) - eta * (w0 * k00 + dl);   // :136, densesolver :65
+        F2_FOR_E k2v[e] = L.tail(e) ? dz[L.offs + L.idx(e)] * dzs - eta * (k0v[e] + cst * wv[e]) : 0.0;   // :137-139
+        const double qv = w0 * k20 - wdot(wv, k2v);                                  // W^-2 = eta^-2 (2 q q' - J)
+        F2_FOR_E if (L.tail(e)) {
+            const int i = L.offs + L.idx(e);
+            k0[i] = k0v[e];
+            k2[i] = k2v[e];
+            u[i] = ie2 * (k2v[e] - 2.0 * wv[e] * qv);
+        }
+        if (L.head()) {
+            k0[L.offs] = k00;
+            k2[L.offs] = k20;
+            u[L.offs] = ie2 * (2.0 * w0 * qv - k20);
+        }
+    };
+
+    // solve_kkt tail (src/densesolver.jl:86-89), the driver's scale!/iscale! (src/solver.jl:128-129) and scmax of both
+    // results (src/mats.jl:64-86) for one cone.  On exit u <- cz, k0 <- cs, k2 <- kt2 o kt3 (Jordan product).
+    auto soc_tail = [&](const SocLane& L, int slot) -> TailOut {
+        TailOut o;
+        const double* c = cs + slot * F2_CS;
+        const double eta = c[CS_ETA], ie = c[CS_IE], ie2 = c[CS_IE2], r1w = c[CS_R1W], w0 = c[CS_W0], l0 = c[CS_LAM0],
+                     aa = c[CS_A];
+        double wv[4], lv[4], uv[4], k0v[4], czv[4], csv[4], kt2v[4], kt3v[4];
+        load_tail(L, wb, wv);
+        load_tail(L, lam, lv);
+        load_tail(L, u, uv);
+        load_tail(L, k0, k0v);
+        const double u0 = L.valid ? u[L.offs] : 0.0;
+        const double k00 = L.valid ? k0[L.offs] : 0.0;
+        const double qv = w0 * u0 - wdot(wv, uv);                                    // cz = W^-2 u          :86
+        const double cz0 = ie2 * (2.0 * w0 * qv - u0);
+        F2_FOR_E czv[e] = L.tail(e) ? ie2 * (uv[e] - 2.0 * wv[e] * qv) : 0.0;
+        double dl = wdot(wv, czv);                                                   // kt3 = W cz           :87, solver :128
+        double cst = cz0 + dl * r1w;
+        const double kt30 = eta * (w0 * cz0 + dl);
+        F2_FOR_E kt3v[e] = L.tail(e) ? eta * (czv[e] + cst * wv[e]) : 0.0;
+        const double kk0 = k00 - kt30;                                               // k0 -= W cz           :88
+        F2_FOR_E k0v[e] -= kt3v[e];
+        dl = wdot(wv, k0v);                                                          // cs = W k0            :89
+        cst = kk0 + dl * r1w;
+        const double cs0 = eta * (w0 * kk0 + dl);
+        F2_FOR_E csv[e] = L.tail(e) ? eta * (k0v[e] + cst * wv[e]) : 0.0;
+        dl = wdot(wv, csv);                                                          // kt2 = W^-1 cs        solver :129
+        cst = -cs0 + dl * r1w;
+        const double kt20 = ie * (w0 * cs0 - dl);
+        F2_FOR_E kt2v[e] = L.tail(e) ? ie * (csv[e] + cst * wv[e]) : 0.0;
+        double lx3 = 0.0, lx2 = 0.0, dot = 0.0;
+        F2_FOR_E {
+            lx3 = fma(lv[e], kt3v[e], lx3);
+            lx2 = fma(lv[e], kt2v[e], lx2);
+            dot = fma(kt2v[e], kt3v[e], dot);
+        }
+        lx3 = grp_sum(lx3, lpc); lx2 = grp_sum(lx2, lpc); dot = grp_sum(dot, lpc);
+        dot += kt20 * kt30;
+        o.fail = L.valid && !(aa >= 0.0);
+        const double as = fast_rsqrt(aa);                                            // src/mats.jl:67-71
+        const double r13 = as * l0 * kt30 - as * lx3, r12 = as * l0 * kt20 - as * lx2;      // :74-77
+        const double den = fast_rcp(as * l0 + 1.0);
+        const double c3 = (r13 + kt30) * den, c2 = (r12 + kt20) * den;               // :80
+        double q3 = 0.0, q2 = 0.0;
+        F2_FOR_E if (L.tail(e)) {
+            const double v3 = as * (kt3v[e] - c3 * as * lv[e]);                      // :83
+            const double v2 = as * (kt2v[e] - c2 * as * lv[e]);
+            q3 = fma(v3, v3, q3);
+            q2 = fma(v2, v2, q2);
+        }
+        q3 = grp_sum(q3, lpc); q2 = grp_sum(q2, lpc);
+        o.mx = L.valid ? fmax(fast_sqrt(q3) - as * r13, fast_sqrt(q2) - as * r12) : -INFINITY;   // :85
+        o.dot = L.head() ? dot : 0.0;
+        F2_FOR_E if (L.tail(e)) {
+            const int i = L.offs + L.idx(e);
+            u[i] = czv[e];
+            k0[i] = csv[e];
+            k2[i] = kt20 * kt3v[e] + kt30 * kt2v[e];                                 // src/vectors.jl:73-75
+        }
+        if (L.head()) {
+            u[L.offs] = cz0;
+            k0[L.offs] = cs0;
+            k2[L.offs] = dot;                                                        // src/vectors.jl:66-69
+        }
+        return o;
+    };
+    // the same for the positive-orthant rows (elementwise); returns partial max / dot
+    auto poc_tail = [&](double& mx, double& dot) {
+        for (int i = tid; i < kpoc; i += T) {
+            const double w = wb[i], iw = iwb[i], il = fast_rcp(lam[i]);
+            const double cz = iw * iw * u[i];
+            const double kt3 = w * cz;
+            const double kk = k0[i] - kt3;
+            const double csx = w * kk;
+            const double kt2 = iw * csx;
+            mx = fmax(mx, fmax(-kt3 * il, -kt2 * il));                               // src/mats.jl:53-62
+            dot = fma(kt2, kt3, dot);
+            u[i] = cz;
+            k0[i] = csx;
+            k2[i] = kt2 * kt3;
+        }
+    };
+
+    // middle of solve_kkt, src/densesolver.jl:66-85.  In: n0 (= G'u + dx ...) formed by the caller, no barrier needed
+    // before the call.  Out: cx (returned pointer), cy, u = G cx - k2.  dys: factor applied to dy.
+    auto solve_middle = [&](double dys) -> const double* {
+        tsync<NW>();
+        gemv_rows<NW, true>(X, ldh, n, n, n0, 1, P.split_n, lane, warp, [&](int r, double acc) { t1[r] = acc; });
+        tsync<NW>();
+        gemv_cols<NW, true>(X, ldh, n, n, t1, lane, warp, [&](int c, double acc) { tt[c] = acc; });
+        if (p > 0)       // m0 = A H^-1 n0 - dy = B' t1 - dy                    :73-74
+            gemv_cols<NW, false>(Bm, n, n, p, t1, lane, warp, [&](int c, double acc) { m0[c] = acc - dys * dy[c]; });
+        tsync<NW>();
+        if (p > 0) {     // cy = M^-1 m0 (:75);  cx = H^-1 (n0 - A'cy) = t - K m0  (:76-83)
+            for (int i = tid; i < n; i += T) {
+                double acc = tt[i];
+                for (int q = 0; q < p; ++q) acc = fma(-Km[q * n + i], m0[q], acc);
+                cx[i] = acc;
+            }
+            for (int i = tid; i < p; i += T) {
+                double acc = 0.0;
+                for (int q = 0; q < p; ++q) acc = fma(Minv[q * p + i], m0[q], acc);
+                cy[i] = acc;
+            }
+            tsync<NW>();
+        }
+        const double* cxv = p > 0 ? cx : tt;
+        gemv_rows<NW, false>(G, ldg, k, n, cxv, 1, P.split_k, lane, warp, [&](int r, double acc) { u[r] = acc - k2[r]; });   // :84-85
+        tsync<NW>();
+        return cxv;
+    };
+
+    // KKT factor, src/densesolver.jl:41-52, from S = Gt (kpad x npad, pads zero).  Returns 0 when cholesky! would throw.
+    auto factor = [&]() -> int {
+        f2_syrk<NW, MAXT>(Gt, ldg, kpad, n, nb, H, ldh, lane, warp);                       // :42-43
+        for (int q = tid; q < npad * ldh; q += T) X[q] = 0.0;
+        if (tid == 0) s_fail = 0;
+        tsync<NW>();
+        PT2_MARK(P2_SYRK);
+        int ok = f2_chol_inv<NW>(H, X, Dinv, nb, ldh, &s_fail, lane, warp);                // :47-48
+        PT2_MARK(P2_CHOL);
+        if (ok && p > 0) {
+            for (int q = 0; q < p; ++q)          // B = X A'
+                gemv_rows<NW, true>(X, ldh, n, n, A + q, p, P.split_n, lane, warp, [&](int r, double acc) { Bm[q * n + r] = acc; });
+            for (int q = tid; q < P.ppad * ldm; q += T) MX[q] = 0.0;
+            tsync<NW>();
+            for (int q = 0; q < p; ++q)          // HiAt = X' B = H^-1 A'                    :49
+                gemv_cols<NW, true>(X, ldh, n, n, Bm + q * n, lane, warp, [&](int c, double acc) { HiAt[q * n + c] = acc; });
+            tsync<NW>();
+            for (int j = 0; j < p; ++j)          // M = A HiAt                              :50
+                gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, P.split_p, lane, warp, [&](int r, double acc) { Mm[j * ldm + r] = acc; });
+            tsync<NW>();
+            ok = f2_chol_inv<NW>(Mm, MX, Dinv, P.pb, ldm, &s_fail, lane, warp);            // :51
+            if (ok) {
+                for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
+                    const int i = q % p, j = q / p;
+                    double acc = 0.0;
+                    for (int m = max(i, j); m < p; ++m) acc = fma(MX[i * ldm + m], MX[j * ldm + m], acc);
+                    Minv[j * p + i] = acc;
+                }
+                tsync<NW>();
+                for (int q = tid; q < n * p; q += T) {          // K = HiAt Minv
+                    const int i = q % n, j = q / n;
+                    double acc = 0.0;
+                    for (int r = 0; r < p; ++r) acc = fma(HiAt[r * n + i], Minv[j * p + r], acc);
+                    Km[j * n + i] = acc;
+                }
+            }
+        }
+        return ok;
+    };
+
+    for (;;) {
+        if (tid == 0) s_prob = atomicAdd(a.counter, 1);
+        tsync<NW>();
+        const int b = s_prob;
+        tsync<NW>();
+        if (b >= a.batch) break;
+        PT2_INIT();
+
+        // ---- load the problem (global -> shared)
+        {
+            const double* Gg = a.g.G + (int64_t)b * a.g.sG;
+            for (int col = warp; col < n; col += NW)
+                for (int r = lane; r < k; r += 32) G[col * ldg + r] = Gg[(int64_t)col * k + r];
+            const double* Ag = a.g.A + (int64_t)b * a.g.sA;
+            for (int q = tid; q < p * n; q += T) A[q] = Ag[q];
+            for (int i = tid; i < n; i += T) cv[i] = a.g.c[(int64_t)b * n + i];
+            for (int i = tid; i < p; i += T) bv[i] = a.g.b[(int64_t)b * p + i];
+            for (int i = tid; i < k; i += T) hv[i] = a.g.h[(int64_t)b * k + i];
+        }
+        int status = ST_RUNNING, iters = 0;
+        tsync<NW>();
+
+        // ---- initial point, src/solver.jl:68-104: the same factor + solve with W = I, u = h, dx = -c, dy = b, k2 = h;
+        //      then cx = x, cy = y and u = G x - h = z0
+        for (int q = tid; q < npad * ldg; q += T) {
+            const int col = q / ldg, r = q - col * ldg;
+            Gt[q] = (col < n && r < k) ? G[col * ldg + r] : 0.0;
+        }
+        for (int i = tid; i < k; i += T) { u[i] = hv[i]; k2[i] = hv[i]; }
+        for (int i = tid; i < n; i += T) dx[i] = -cv[i];
+        for (int i = tid; i < p; i += T) dy[i] = bv[i];
+        tsync<NW>();
+        PT2_MARK(P2_LOAD);
+        gemv_cols<NW, false>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + dx[c]; });
+        if (!factor()) status = ST_NUMERICAL;
+        PT2_MARK(P2_EQ);
+        if (status == ST_RUNNING) {
+            const double* cxv = solve_middle(1.0);
+            for (int i = tid; i < n; i += T) x[i] = cxv[i];
+            for (int i = tid; i < p; i += T) y[i] = cy[i];
+            // max_step(-z0), max_step(z0), src/mats.jl:1-28, then the shift of src/solver.jl:91-101
+            double mp = -INFINITY, md = -INFINITY, z4 = 0.0;
+            int fl = 0;
+            for (int i = tid; i < kpoc; i += T) { const double v = u[i]; mp = fmax(mp, v); md = fmax(md, -v); }
+            for_each_slot([&](const SocLane& L, int) {
+                double zv[4];
+                load_tail(L, u, zv);
+                double sq = 0.0;
+                F2_FOR_E sq = fma(zv[e], zv[e], sq);
+                const double nr = fast_sqrt(grp_sum(sq, lpc));
+                if (L.valid) {
+                    const double z0 = u[L.offs];
+                    mp = fmax(mp, nr + z0);          // ||-z1|| - (-z0)
+                    md = fmax(md, nr - z0);
+                }
+            });
+            team_reduce<NW>(z4, z4, z4, z4, mp, md, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+            const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(md) < prm.init_eps);
+            for (int i = tid; i < k; i += T) {
+                const double z0 = u[i];
+                s[i] = -z0;
+                z[i] = z0;
+            }
+            tsync<NW>();
+            for (int i = tid; i < kpoc; i += T) {
+                if (shp) s[i] += 1.0 + mp;
+                if (shd) z[i] += 1.0 + md;
+            }
+            for (int c = tid; c < nsoc; c += T) {
+                const int o = P.soc_offs[c];
+                if (shp) s[o] += 1.0 + mp;
+                if (shd) z[o] += 1.0 + md;
+            }
+            tsync<NW>();
+        }
+        PT2_MARK(P2_INIT);
+
+        // ---- Mehrotra loop, src/solver.jl:105-151
+        while (status == ST_RUNNING && iters < prm.max_iter) {
+            // (P1) compute_scaling (:106) and the negated residuals (:110-118,:125) in one phase
+            double nx = 0.0, ny = 0.0, gap = 0.0, ll = 0.0, dm1 = -INFINITY, dm2 = -INFINITY;
+            int fl = 0;
+            for_each_slot([&](const SocLane& L, int slot) { fl |= soc_scaling(L, slot, gap, ll); });
+            for (int i = tid; i < kpoc; i += T) {                                   // src/scalings.jl:22-30
+                const double si = s[i], zi = z[i];
+                const double q = si * fast_rcp(zi), qi = zi * fast_rcp(si), pz = si * zi;
+                fl |= !(q >= 0.0) | !(pz >= 0.0);
+                const double lv = fast_sqrt(pz);
+                wb[i] = fast_sqrt(q);
+                iwb[i] = fast_sqrt(qi);
+                lam[i] = lv;
+                gap = fma(si, zi, gap);
+                ll = fma(lv, lv, ll);
+            }
+            gemv_cols<NW, false>(G, ldg, k, n, z, lane, warp, [&](int c, double acc) {
+                double v = -acc - cv[c];
+                for (int q = 0; q < p; ++q) v = fma(-A[c * p + q], y[q], v);
+                dx[c] = v;
+                nx = fma(v, v, nx);
+            });
+            gemv_rows<NW, false>(G, ldg, k, n, x, 1, P.split_k, lane, warp, [&](int r, double acc) { dz[r] = -acc - s[r] + hv[r]; });
+            if (p > 0)
+                gemv_rows<NW, false>(A, p, p, n, x, 1, P.split_p, lane, warp, [&](int r, double acc) {
+                    const double v = -acc + bv[r];
+                    dy[r] = v;
+                    ny = fma(v, v, ny);
+                });
+            team_reduce<NW>(nx, ny, gap, ll, dm1, dm2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+            if (NW == 1) __syncwarp();
+            PT2_MARK(P2_RESID);
+            if (fl) { status = ST_NUMERICAL; break; }                              // compute_scaling threw
+            const double resid = sqrt(nx) + sqrt(ny) + gap;
+            if (resid < prm.tol) { status = ST_CONVERGED; break; }                  // :122-124
+
+            // (P2) affine right-hand side ds = -lam o lam (:120,:125), head of solve #1, Gt = W^-1 G (densesolver :41-43)
+            for_each_slot([&](const SocLane& L, int slot) {
+                const double* c = cs + slot * F2_CS;
+                double lv[4], wv[4], dsv[4];
+                load_tail(L, lam, lv);
+                load_tail(L, wb, wv);
+                const double l0 = c[CS_LAM0];
+                const double ds0 = -(c[CS_LLT] + l0 * l0);                          // src/vectors.jl:66-69
+                F2_FOR_E dsv[e] = -(l0 * lv[e] + l0 * lv[e]);                       // :73-75
+                F2_FOR_E if (L.tail(e)) ds[L.offs + L.idx(e)] = dsv[e];
+                if (L.head()) ds[L.offs] = ds0;
+                soc_head(L, slot, lv, wv, dsv, ds0, 1.0);
+            });
+            for (int i = tid; i < kpoc; i += T) {
+                const double lv = lam[i], w = wb[i], iw = iwb[i];
+                const double d = -(lv * lv);
+                const double kk = d * fast_rcp(lv);
+                const double kz = dz[i] - w * kk;
+                ds[i] = d; k0[i] = kk; k2[i] = kz; u[i] = iw * iw * kz;
+            }
+            {
+                // pad rows / pad columns of Gt (the region held H and X)
+                const int padr = kpad - k;
+                for (int q = tid; q < padr * n; q += T) Gt[(q / padr) * ldg + k + (q % padr)] = 0.0;
+                for (int q = tid; q < (npad - n) * kpad; q += T) Gt[(n + q / kpad) * ldg + (q % kpad)] = 0.0;
+                for (int col = warp; col < n; col += NW)
+                    for (int r = lane; r < kpoc; r += 32) Gt[col * ldg + r] = iwb[r] * G[col * ldg + r];
+                const int spw = 32 / lpc, npairs = n * nsoc;
+                for (int base = warp * spw; base < npairs; base += NW * spw) {
+                    const int pr = base + lane / lpc;
+                    SocLane L;
+                    L.valid = pr < npairs;
+                    const int col = L.valid ? pr / nsoc : 0;
+                    const int slot = L.valid ? pr - col * nsoc : 0;
+                    L.offs = L.valid ? P.soc_offs[slot] : 0;
+                    L.dim = L.valid ? P.soc_dim[slot] : 0;
+                    L.g = lane & (lpc - 1);
+                    L.lpc = lpc;
+                    const double* c = cs + slot * F2_CS;
+                    const double* gc = G + col * ldg;
+                    double wv[4], gv[4];
+                    load_tail(L, wb, wv);
+                    load_tail(L, gc, gv);
+                    const double dl = wdot(wv, gv);
+                    if (L.valid) {
+                        const double g0 = gc[L.offs], ie = c[CS_IE];
+                        const double cst = -g0 + dl * c[CS_R1W];                    // src/scalings.jl:151
+                        double* oc = Gt + col * ldg;
+                        F2_FOR_E if (L.tail(e)) oc[L.offs + L.idx(e)] = ie * (gv[e] + cst * wv[e]);   // :153-155
+                        if (L.g == 0) oc[L.offs] = ie * (c[CS_W0] * g0 - dl);       // :152
+                    }
+                }
+            }
+            tsync<NW>();
+            PT2_MARK(P2_HEAD_GT);
+            gemv_cols<NW, false>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + dx[c]; });   // densesolver :66-67
+            if (!factor()) { status = ST_NUMERICAL; break; }                        // :126
+            PT2_MARK(P2_EQ);
+            solve_middle(1.0);                                                      // :127
+            PT2_MARK(P2_SOLVE);
+
+            // (mid) tail of solve #1, centering parameter (:130-134), combined right-hand side (:136-140), head of solve #2
+            double mx = -INFINITY, dot = 0.0, z4 = 0.0;
+            fl = 0;
+            for_each_slot([&](const SocLane& L, int slot) {
+                const TailOut o = soc_tail(L, slot);
+                mx = fmax(mx, o.mx); dot += o.dot; fl |= o.fail;
+            });
+            poc_tail(mx, dot);
+            team_reduce<NW>(dot, z4, z4, z4, mx, dm2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+            if (NW == 1) __syncwarp();
+            const double tstep = step_from_t(mx);                                   // :130
+            const double rho = 1.0 - tstep - tstep * tstep * dot * fast_rcp(ll);    // :132 (minus: reference quirk)
+            const double cl = fmax(0.0, fmin(1.0, rho));
+            const double sig = cl * cl * cl;                                        // :133
+            const double mu = ll / (double)a.g.L.deg;                               // :134
+            const double scf = 1.0 - sig, sm_ = sig * mu;                           // :136
+            if (fl) { status = ST_NUMERICAL; break; }
+            for_each_slot([&](const SocLane& L, int slot) {
+                double lv[4], wv[4], dsv[4], pv[4];
+                load_tail(L, lam, lv);
+                load_tail(L, wb, wv);
+                load_tail(L, ds, dsv);
+                load_tail(L, k2, pv);
+                F2_FOR_E dsv[e] -= pv[e];                                           // :137-139 (e is 0 on the tail)
+                const double ds0 = L.valid ? ds[L.offs] + sm_ - k2[L.offs] : 0.0;
+                soc_head(L, slot, lv, wv, dsv, ds0, scf);
+            });
+            for (int i = tid; i < kpoc; i += T) {
+                const double lv = lam[i], w = wb[i], iw = iwb[i];
+                const double d = ds[i] + sm_ - k2[i];
+                const double kk = d * fast_rcp(lv);
+                const double kz = scf * dz[i] - w * kk;
+                k0[i] = kk; k2[i] = kz; u[i] = iw * iw * kz;
+            }
+            tsync<NW>();
+            PT2_MARK(P2_MID);
+            gemv_cols<NW, false>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + scf * dx[c]; });
+            const double* cxv = solve_middle(scf);                                  // :141
+            PT2_MARK(P2_SOLVE);
+
+            // (post) tail of solve #2, step length (:143-146), iterate update (:147-150)
+            mx = -INFINITY; dot = 0.0; fl = 0;
+            for_each_slot([&](const SocLane& L, int slot) {
+                const TailOut o = soc_tail(L, slot);
+                mx = fmax(mx, o.mx); fl |= o.fail;
+            });
+            poc_tail(mx, dot);
+            // the reference would carry NaN/Inf into the next cholesky! and throw there
+            for (int i = tid; i < n; i += T) fl |= !isfinite(cxv[i]);
+            for (int i = tid; i < p; i += T) fl |= !isfinite(cy[i]);
+            for (int i = tid; i < k; i += T) fl |= !isfinite(u[i]) | !isfinite(k0[i]);
+            team_reduce<NW>(z4, z4, z4, z4, mx, dm2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+            if (NW == 1) __syncwarp();
+            const double step = step_from_t(mx) * prm.step_damp;                    // :145-146
+            fl |= !isfinite(step);
+            if (fl) { status = ST_NUMERICAL; break; }
+            for (int i = tid; i < n; i += T) x[i] = fma(cxv[i], step, x[i]);        // :147
+            for (int i = tid; i < p; i += T) y[i] = fma(cy[i], step, y[i]);         // :148
+            for (int i = tid; i < k; i += T) {
+                z[i] = fma(u[i], step, z[i]);                                       // :149
+                s[i] = fma(k0[i], step, s[i]);                                      // :150
+            }
+            ++iters;
+            tsync<NW>();
+            PT2_MARK(P2_POST);
+        }
+        if (status == ST_RUNNING) status = ST_MAXITER;
+        tsync<NW>();
+
+        // ---- results: iterate and objectives (pobj = c'x, dobj = -b'y - h'z)
+        {
+            const bool dead = (status == ST_NUMERICAL && iters == 0 && s_fail);
+            double po = 0.0, d = 0.0, z2 = 0.0, m1 = -INFINITY, m2 = -INFINITY;
+            int fl = 0;
+            for (int i = tid; i < n; i += T) {
+                const double xi = dead ? 0.0 : x[i];
+                a.g.x[(int64_t)b * n + i] = xi;
+                po = fma(cv[i], xi, po);
+            }
+            for (int i = tid; i < p; i += T) {
+                const double yi = dead ? 0.0 : y[i];
+                a.g.y[(int64_t)b * p + i] = yi;
+                d = fma(-bv[i], yi, d);
+            }
+            for (int i = tid; i < k; i += T) {
+                const double zi = dead ? 0.0 : z[i];
+                a.g.z[(int64_t)b * k + i] = zi;
+                a.g.s[(int64_t)b * k + i] = dead ? 0.0 : s[i];
+                d = fma(-hv[i], zi, d);
+            }
+            team_reduce<NW>(po, d, z2, z2, m1, m2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+            if (tid == 0) {
+                a.g.sc[b].pobj = po;
+                a.g.sc[b].dobj = d;
+                a.g.status[b] = status;
+                a.g.iters[b] = iters;
+                a.g.active[b] = 0;
+                a.g.fail[b] = (status == ST_NUMERICAL);
+            }
+        }
+        tsync<NW>();
+        PT2_MARK(P2_OUT);
+    }
+}
+
+template <int NW, int MAXT, int MINB>
+inline void fused2_launch(const F2Plan& plan, const F2Args& args, int grid, cudaStream_t stream) {
+    cudaFuncSetAttribute(k_fused2<NW, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    k_fused2<NW, MAXT, MINB><<<grid, NW * 32, plan.smem, stream>>>(args);
+}
+
+inline void solve_fused2(F2Plan& plan, const Ws& g, int batch, int max_iter, double tol, double step_damp,
+                         double init_eps, cudaStream_t stream) {
+    cudaMemsetAsync(plan.d_counter, 0, sizeof(int), stream);
+    F2Args args;
+    args.g = g;
+    args.P = plan;
+    args.prm = LoopParams{max_iter, tol, step_damp, init_eps};
+    args.batch = batch;
+    args.counter = plan.d_counter;
+    const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
+    switch (plan.variant) {
+        case 0: fused2_launch<1, 3, 16>(plan, args, grid, stream); break;     // n <= 16: one warp per problem
+        case 1: fused2_launch<4, 3, 4>(plan, args, grid, stream); break;      // n <= 32: 10 tiles over 4 warps
+        case 2: fused2_launch<8, 4, 2>(plan, args, grid, stream); break;      // n <= 56: 28 tiles over 8 warps
+        default: fused2_launch<8, 5, 2>(plan, args, grid, stream); break;     // n <= 64: 36 tiles over 8 warps
+    }
+}
+
+}  // namespace socp

@@ -5,6 +5,7 @@
 #include "linalg.cuh"
 #include "tiled_kernels.cuh"
 #include "fused_small.cuh"
+#include "fused_v2.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -64,6 +65,7 @@ struct Shard {
     int threads = 256;     // CTA size of the per-problem cone kernels
     socp_timings tim{};
     FusedPlan fused{};
+    F2Plan fused2{};
 
     template <class T>
     T* alloc(size_t count, bool zero = true) {
@@ -339,6 +341,8 @@ void build_shard(socp_handle* h, Shard& sh) {
     sh.threads = std::min(256, std::max(32, 32 * nc));
     fused_plan(sh.fused, n, p, k, h->wkind, h->woffs, h->wdim, sh.device);
     sh.fused.d_counter = sh.alloc<int>(1);
+    f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
+    sh.fused2.d_counter = sh.fused.d_counter;
     CK(cudaStreamSynchronize(sh.stream));
 }
 
@@ -442,9 +446,15 @@ void need(bool cond, int code, const char* msg) {
     if (!cond) throw UsageErr{code, msg};
 }
 
+constexpr int PATH_FUSED_V1 = 3;   // first-generation fused kernel (A/B comparisons only; not in the public header)
+
 int choose_path(const Shard& sh, const socp_params& prm) {
     if (prm.path == SOCP_PATH_TILED) return SOCP_PATH_TILED;
-    const bool ok = sh.fused.fits && !sh.any_sing;
+    if (prm.path == PATH_FUSED_V1) {
+        need(sh.fused.fits && !sh.any_sing, SOCP_ERR_SIZE, "fused v1 does not fit");
+        return PATH_FUSED_V1;
+    }
+    const bool ok = sh.fused2.fits && !sh.any_sing;
     if (prm.path == SOCP_PATH_FUSED) {
         need(ok, SOCP_ERR_SIZE, "the fused shared-memory kernel needs a layout that fits and no sing problems");
         return SOCP_PATH_FUSED;
@@ -456,8 +466,12 @@ void run_solve(Shard& sh, const socp_params& prm) {
     need(sh.have_data, SOCP_ERR_STATE, "solve called before set_data");
     sh.launches = 0;
     CK(cudaEventRecord(sh.ev[0], sh.stream));
-    if (choose_path(sh, prm) == SOCP_PATH_FUSED) {
-        solve_fused(sh.fused, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
+    const int path = choose_path(sh, prm);
+    if (path == SOCP_PATH_FUSED || path == PATH_FUSED_V1) {
+        if (path == SOCP_PATH_FUSED)
+            solve_fused2(sh.fused2, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
+        else
+            solve_fused(sh.fused, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
         CK(cudaGetLastError());
         sh.launches += 1;
         sh.tim.path_used = SOCP_PATH_FUSED;
@@ -885,6 +899,14 @@ int socp_b200_debug_phase_clocks(unsigned long long* out16, int reset) {
     if (reset) {
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(socp::g_phase_clk, z, sizeof z);
+    }
+    return 0;
+}
+int socp_b200_debug_phase_clocks2(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, socp::g_phase_clk2, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(socp::g_phase_clk2, z, sizeof z);
     }
     return 0;
 }
