@@ -47,7 +47,8 @@ struct F2Plan {
     int* d_counter = nullptr;
     // layout
     int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
-    int npad = 0, nb = 0, kpad = 0, ldg = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
+    int npad = 0, nb = 0, kpad = 0, ldg = 0, ldt = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
+    int shape = 0;         // 0: generic kernel; > 0: index of a compile-time specialised layout (F2_SHAPES)
     int split_k = 1, split_n = 1, split_p = 1;    // lanes per output row of the row gemvs (k, n, p rows)
     int soc_offs[F2_MAX_SOC], soc_dim[F2_MAX_SOC];
     // offsets into the dynamic shared memory, in doubles
@@ -57,15 +58,25 @@ struct F2Plan {
     int total = 0;
 };
 
-inline int f2_ld(int rows) {      // smallest ld >= rows with ld == 4 (mod 8)
+__host__ __device__ constexpr int f2_ld(int rows) {      // smallest ld >= rows with ld == 4 (mod 8): DMMA fragment loads
     int ld = rows;
     while (ld % 8 != 4) ++ld;
     return ld;
 }
-inline int f2_split(int rows, int nw) {   // lanes per row so that one pass of the team covers the rows if possible
+__host__ __device__ constexpr int f2_ldv(int rows) {     // smallest ld >= rows with ld == 8 (mod 16): 128-bit column loads
+    int ld = rows;
+    while (ld % 16 != 8) ++ld;
+    return ld;
+}
+__host__ __device__ constexpr int f2_split(int units, int nw) {   // lanes per output unit so that one team pass covers them
     int split = 32;
-    while (split > 1 && (rows + (32 / split) - 1) / (32 / split) > nw) split >>= 1;
+    while (split > 1 && (units + (32 / split) - 1) / (32 / split) > nw) split >>= 1;
     return split;
+}
+__host__ __device__ constexpr int f2_lpc(int maxdim) {   // lanes per second-order cone: 4 elements per lane
+    int l = 1;
+    while (l * 4 < maxdim) l <<= 1;
+    return l;
 }
 
 // kind/offs/dim: the CALLER's cones (POC blocks first).
@@ -86,25 +97,25 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
         }
     }
     if (maxd > 128 || n > 64 || p > 32) return;
-    P.lpc = 1;
-    while (P.lpc * 4 < maxd) P.lpc <<= 1;
+    P.lpc = f2_lpc(maxd);
     if (n <= 16 && p <= 16) { P.variant = 0; P.nw = 1; }
     else if (n <= 32) { P.variant = 1; P.nw = 4; }
     else if (n <= 56) { P.variant = 2; P.nw = 8; }
     else { P.variant = 3; P.nw = 8; }
     P.npad = (n + 7) / 8 * 8; P.nb = P.npad / 8;
     P.kpad = (k + 3) / 4 * 4;
-    P.ldg = f2_ld(P.kpad);
+    P.ldg = f2_ldv(P.kpad);
+    P.ldt = f2_ld(P.kpad);
     P.ldh = f2_ld(P.npad);
     P.ppad = (std::max(p, 1) + 7) / 8 * 8; P.pb = P.ppad / 8;
     P.ldm = f2_ld(P.ppad);
-    P.split_k = f2_split(k, P.nw);
+    P.split_k = f2_split((k + 1) / 2, P.nw);      // row PAIRS per lane in the k-row gemv
     P.split_n = f2_split(n, P.nw);
     P.split_p = f2_split(std::max(p, 1), P.nw);
     int at = 0;
     auto take = [&](int cnt) { int r = at; at += (cnt + 1) / 2 * 2; return r; };
     P.oG = take(P.ldg * n);
-    const int gt_sz = P.ldg * P.npad, hx_sz = 2 * P.ldh * P.npad;
+    const int gt_sz = P.ldt * P.npad, hx_sz = 2 * P.ldh * P.npad;
     P.oR = take(std::max(gt_sz, hx_sz));
     P.oX = P.oR + P.ldh * P.npad;
     P.oA = take(p * n); P.oB = take(n * p); P.oHiAt = take(n * p); P.oK = take(n * p);
@@ -140,34 +151,72 @@ __device__ __forceinline__ void tsync() {
     else __syncthreads();
 }
 __device__ __forceinline__ double grp_sum(double v, int lpc) {
-    for (int o = lpc >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        if (o < lpc) v += __shfl_xor_sync(FULL_MASK, v, o);
     return v;
 }
-// Team-wide reduction of four sums, two maxima and one flag through a scratch slot (8 doubles per warp).
-// Contains one team barrier (none for a one-warp team); the caller alternates `scr` between two slots.
-template <int NW>
-__device__ __forceinline__ void team_reduce(double& a, double& b, double& c, double& d, double& mx, double& mx2,
-                                            int& flag, double* scr, int lane, int warp) {
-    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
-    mx = warp_max(mx); mx2 = warp_max(mx2);
+// Team-wide reduction of NS sums (v[0..NS)), NM maxima (v[NS..NS+NM)) and one flag through a scratch slot
+// (8 doubles per warp).  One team barrier (none for a one-warp team); the caller alternates `scr` between two slots.
+template <int NW, int NS, int NM>
+__device__ __forceinline__ void team_reduce(double (&v)[NS + NM], int& flag, double* scr, int lane, int warp) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) v[i] = warp_sum(v[i]);
+#pragma unroll
+    for (int i = NS; i < NS + NM; ++i) v[i] = warp_max(v[i]);
     flag = __any_sync(FULL_MASK, flag) ? 1 : 0;
     if (NW == 1) return;
     if (lane == 0) {
         double* q = scr + warp * 8;
-        q[0] = a; q[1] = b; q[2] = c; q[3] = d; q[4] = mx; q[5] = mx2; q[6] = (double)flag;
+#pragma unroll
+        for (int i = 0; i < NS + NM; ++i) q[i] = v[i];
+        q[7] = (double)flag;
     }
     __syncthreads();
-    a = b = c = d = 0.0; mx = mx2 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) v[i] = 0.0;
+#pragma unroll
+    for (int i = NS; i < NS + NM; ++i) v[i] = -INFINITY;
     double f = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
         const double* q = scr + w * 8;
-        a += q[0]; b += q[1]; c += q[2]; d += q[3]; mx = fmax(mx, q[4]); mx2 = fmax(mx2, q[5]); f += q[6];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) v[i] += q[i];
+#pragma unroll
+        for (int i = NS; i < NS + NM; ++i) v[i] = fmax(v[i], q[i]);
+        f += q[7];
     }
     flag = f != 0.0;
 }
 
-// out(c) = sum_{r in [r_lo(c), rows)} M[c*ld + r] * x[r], four lanes per column; epi(c, acc) runs on one lane.
+// out(c) = sum_r M[c*ld + r] * x[r] over rows [0, rows): four lanes per column, each lane takes the row pairs
+// {2rl, 2rl+1} + 8m with 128-bit loads (ld == 8 mod 16: conflict free).  M rows and x must be zero / finite up to
+// the next even row.  epi(c, acc) runs on one lane per column.
+template <int NW, class Epi>
+__device__ __forceinline__ void gemv_cols_v(const double* __restrict__ M, int ld, int rows, int cols,
+                                            const double* __restrict__ x, int lane, int warp, Epi epi) {
+    const int cq = lane >> 2, rl = lane & 3;
+    const double2* xv = reinterpret_cast<const double2*>(x) + rl;
+    const int npair = (rows + 1) >> 1;
+    for (int c0 = warp * 8; c0 < cols; c0 += NW * 8) {
+        const int c = c0 + cq;
+        const bool ok = c < cols;
+        const double2* col = reinterpret_cast<const double2*>(M + (ok ? c : 0) * ld) + rl;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+        for (int q = rl; q < npair; q += 4) {
+            const double2 g = col[q - rl], w = xv[q - rl];
+            a0 = fma(g.x, w.x, a0);
+            a1 = fma(g.y, w.y, a1);
+        }
+        double acc = a0 + a1;
+        acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+        acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+        if (rl == 0 && ok) epi(c, acc);
+    }
+}
+// out(c) = sum_{r >= r_lo(c)} M[c*ld + r] * x[r], four lanes per column, scalar loads (triangular / small operands).
 template <int NW, bool TRI, class Epi>
 __device__ __forceinline__ void gemv_cols(const double* __restrict__ M, int ld, int rows, int cols,
                                           const double* __restrict__ x, int lane, int warp, Epi epi) {
@@ -180,6 +229,7 @@ __device__ __forceinline__ void gemv_cols(const double* __restrict__ M, int ld, 
         int r = rl + (TRI ? (c & ~3) : 0);
         if (TRI && r < c) r += 4;
         if (ok) {
+#pragma unroll 2
             for (; r + 4 < rows; r += 8) {
                 a0 = fma(col[r], x[r], a0);
                 a1 = fma(col[r + 4], x[r + 4], a1);
@@ -192,7 +242,40 @@ __device__ __forceinline__ void gemv_cols(const double* __restrict__ M, int ld, 
         if (rl == 0 && ok) epi(c, acc);
     }
 }
-// out(r) = sum_{c in [0, c_hi(r))} M[c*ld + r] * x[c*xs]; `split` lanes per row (power of two); epi(r, acc) on one lane.
+// out(r) = sum_c M[c*ld + r] * x[c]: every lane owns the row PAIR (2q, 2q+1) (128-bit loads down a column), `split`
+// lanes share a pair and stride the columns.  epi(r, acc) is called for both rows of the pair (r < rows).
+template <int NW, class Epi>
+__device__ __forceinline__ void gemv_rows_v(const double* __restrict__ M, int ld, int rows, int cols,
+                                            const double* __restrict__ x, int split, int lane, int warp, Epi epi) {
+    const int ppw = 32 / split;                       // row pairs per warp pass
+    const int pr = lane & (ppw - 1), part = lane / ppw;
+    const int npair = (rows + 1) >> 1;
+    for (int q0 = warp * ppw; q0 < npair; q0 += NW * ppw) {
+        const int q = q0 + pr;
+        const bool ok = q < npair;
+        const double2* row = reinterpret_cast<const double2*>(M) + (ok ? q : 0);
+        const int ldv = ld >> 1;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+        for (int c = part; c < cols; c += split) {
+            const double2 g = row[c * ldv];
+            const double w = x[c];
+            a0 = fma(g.x, w, a0);
+            a1 = fma(g.y, w, a1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if (o >= ppw) {
+                a0 += __shfl_xor_sync(FULL_MASK, a0, o);
+                a1 += __shfl_xor_sync(FULL_MASK, a1, o);
+            }
+        if (part == 0 && ok) {
+            epi(2 * q, a0);
+            if (2 * q + 1 < rows) epi(2 * q + 1, a1);
+        }
+    }
+}
+// out(r) = sum_{c in [0, c_hi(r))} M[c*ld + r] * x[c*xs]; `split` lanes per row (power of two); scalar loads.
 template <int NW, bool TRI, class Epi>
 __device__ __forceinline__ void gemv_rows(const double* __restrict__ M, int ld, int rows, int cols,
                                           const double* __restrict__ x, int xs, int split, int lane, int warp, Epi epi) {
@@ -206,6 +289,7 @@ __device__ __forceinline__ void gemv_rows(const double* __restrict__ M, int ld, 
         if (ok) {
             const double* row = M + r;
             int c = part;
+#pragma unroll 2
             for (; c + split < chi; c += 2 * split) {
                 a0 = fma(row[c * ld], x[c * xs], a0);
                 a1 = fma(row[(c + split) * ld], x[(c + split) * xs], a1);
@@ -213,7 +297,9 @@ __device__ __forceinline__ void gemv_rows(const double* __restrict__ M, int ld, 
             if (c < chi) a0 = fma(row[c * ld], x[c * xs], a0);
         }
         double acc = a0 + a1;
-        for (int o = rpw; o < 32; o <<= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            if (o >= rpw) acc += __shfl_xor_sync(FULL_MASK, acc, o);
         if (part == 0 && ok) epi(r, acc);
     }
 }
@@ -242,7 +328,7 @@ __device__ __forceinline__ void f2_syrk(const double* S, int ldg, int kpad, int 
         pb[q] = S + (tj[q] * 8 + fr) * ldg + fk;
         acc[q][0] = acc[q][1] = 0.0;
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int kk = 0; kk < kpad; kk += 4) {
 #pragma unroll
         for (int q = 0; q < MAXT; ++q) dmma884(acc[q][0], acc[q][1], pa[q][kk], pb[q][kk]);
@@ -395,6 +481,64 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
     return 1;
 }
 
+// ------------------------------------------------------------------------------------------------ layout providers
+// The kernel reads every dimension through a provider.  DimsDyn takes them from the plan (any layout that fits);
+// DimsStatic<...> makes them compile-time constants for the BASELINE.json shapes -- the GPU analogue of the
+// reference's compile-time specialisation on the cone tuple (`@unroll`, Cone{D}; src/scalings.jl:101-110): loops
+// unroll, masks and index arithmetic fold away.
+struct DimsDyn {
+    static constexpr bool is_static = false;
+    __device__ __forceinline__ static int n(const F2Plan& P) { return P.n; }
+    __device__ __forceinline__ static int p(const F2Plan& P) { return P.p; }
+    __device__ __forceinline__ static int k(const F2Plan& P) { return P.k; }
+    __device__ __forceinline__ static int kpoc(const F2Plan& P) { return P.kpoc; }
+    __device__ __forceinline__ static int nsoc(const F2Plan& P) { return P.nsoc; }
+    __device__ __forceinline__ static int lpc(const F2Plan& P) { return P.lpc; }
+    __device__ __forceinline__ static int npad(const F2Plan& P) { return P.npad; }
+    __device__ __forceinline__ static int kpad(const F2Plan& P) { return P.kpad; }
+    __device__ __forceinline__ static int ldg(const F2Plan& P) { return P.ldg; }
+    __device__ __forceinline__ static int ldt(const F2Plan& P) { return P.ldt; }
+    __device__ __forceinline__ static int ldh(const F2Plan& P) { return P.ldh; }
+    __device__ __forceinline__ static int ppad(const F2Plan& P) { return P.ppad; }
+    __device__ __forceinline__ static int ldm(const F2Plan& P) { return P.ldm; }
+    __device__ __forceinline__ static int split_k(const F2Plan& P) { return P.split_k; }
+    __device__ __forceinline__ static int split_n(const F2Plan& P) { return P.split_n; }
+    __device__ __forceinline__ static int split_p(const F2Plan& P) { return P.split_p; }
+    __device__ __forceinline__ static int soc_offs(const F2Plan& P, int slot) { return P.soc_offs[slot]; }
+    __device__ __forceinline__ static int soc_dim(const F2Plan& P, int slot) { return P.soc_dim[slot]; }
+};
+// N variables, PE equality rows, one POC block of KPOC rows followed by NSOC second-order cones of dimension SDIM
+template <int NW, int N, int PE, int KPOC, int NSOC, int SDIM>
+struct DimsStatic {
+    static constexpr bool is_static = true;
+    static constexpr int K = KPOC + NSOC * SDIM;
+    static constexpr int NPAD = (N + 7) / 8 * 8, KPAD = (K + 3) / 4 * 4, PPAD = ((PE > 0 ? PE : 1) + 7) / 8 * 8;
+    __device__ __forceinline__ static constexpr int n(const F2Plan&) { return N; }
+    __device__ __forceinline__ static constexpr int p(const F2Plan&) { return PE; }
+    __device__ __forceinline__ static constexpr int k(const F2Plan&) { return K; }
+    __device__ __forceinline__ static constexpr int kpoc(const F2Plan&) { return KPOC; }
+    __device__ __forceinline__ static constexpr int nsoc(const F2Plan&) { return NSOC; }
+    __device__ __forceinline__ static constexpr int lpc(const F2Plan&) { return f2_lpc(SDIM); }
+    __device__ __forceinline__ static constexpr int npad(const F2Plan&) { return NPAD; }
+    __device__ __forceinline__ static constexpr int kpad(const F2Plan&) { return KPAD; }
+    __device__ __forceinline__ static constexpr int ldg(const F2Plan&) { return f2_ldv(KPAD); }
+    __device__ __forceinline__ static constexpr int ldt(const F2Plan&) { return f2_ld(KPAD); }
+    __device__ __forceinline__ static constexpr int ldh(const F2Plan&) { return f2_ld(NPAD); }
+    __device__ __forceinline__ static constexpr int ppad(const F2Plan&) { return PPAD; }
+    __device__ __forceinline__ static constexpr int ldm(const F2Plan&) { return f2_ld(PPAD); }
+    __device__ __forceinline__ static constexpr int split_k(const F2Plan&) { return f2_split((K + 1) / 2, NW); }
+    __device__ __forceinline__ static constexpr int split_n(const F2Plan&) { return f2_split(N, NW); }
+    __device__ __forceinline__ static constexpr int split_p(const F2Plan&) { return f2_split(PE > 0 ? PE : 1, NW); }
+    __device__ __forceinline__ static constexpr int soc_offs(const F2Plan&, int slot) { return KPOC + slot * SDIM; }
+    __device__ __forceinline__ static constexpr int soc_dim(const F2Plan&, int) { return SDIM; }
+    static bool matches(const F2Plan& P) {
+        if (P.n != N || P.p != PE || P.kpoc != KPOC || P.nsoc != NSOC || P.k != K || P.nw != NW) return false;
+        for (int i = 0; i < NSOC; ++i)
+            if (P.soc_dim[i] != SDIM || P.soc_offs[i] != KPOC + i * SDIM) return false;
+        return true;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------ kernel
 struct F2Args {
     Ws g;                 // global arrays of the shard
@@ -421,21 +565,22 @@ __device__ unsigned long long g_phase_clk2[16];
 #define PT2_INIT()
 #define PT2_MARK(idx)
 #endif
-enum { P2_LOAD = 0, P2_RESID, P2_HEAD_GT, P2_SYRK, P2_CHOL, P2_EQ, P2_SOLVE, P2_INIT, P2_MID, P2_POST, P2_OUT };
+enum { P2_LOAD = 0, P2_RESID, P2_HEAD_GT, P2_SYRK, P2_CHOL, P2_EQ, P2_SOLVE, P2_INIT, P2_TAIL, P2_MIDPOST, P2_OUT };
 
-// per-thread view of one second-order cone slot: element e of this lane is index g + e*lpc of the cone
+// per-thread view of one second-order cone slot: element e of this lane is index g + e*lpc of the cone; bit e of
+// `tm` says that this element exists and belongs to the tail (index > 0)
 struct SocLane {
-    int offs, dim, g, lpc;
+    int offs, g, lpc;
+    unsigned tm;
     bool valid;
-    __device__ __forceinline__ int idx(int e) const { return g + e * lpc; }
-    __device__ __forceinline__ bool tail(int e) const { return valid && idx(e) < dim && idx(e) > 0; }
+    __device__ __forceinline__ int at(int e) const { return offs + g + e * lpc; }
+    __device__ __forceinline__ bool tail(int e) const { return (tm >> e) & 1u; }
     __device__ __forceinline__ bool head() const { return valid && g == 0; }
 };
-struct TailOut { double mx, dot; int fail; };
 
 #define F2_FOR_E _Pragma("unroll") for (int e = 0; e < 4; ++e)
 
-template <int NW, int MAXT, int MINB>
+template <int NW, int MAXT, int MINB, class D>
 __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
     extern __shared__ __align__(16) double sm[];
     __shared__ int s_prob, s_fail;
@@ -444,12 +589,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int T = NW * 32;
-    const int n = P.n, p = P.p, k = P.k, kpoc = P.kpoc, nsoc = P.nsoc, lpc = P.lpc;
-    const int ldg = P.ldg, ldh = P.ldh, npad = P.npad, nb = P.nb, kpad = P.kpad, ldm = P.ldm;
+    const int n = D::n(P), p = D::p(P), k = D::k(P), kpoc = D::kpoc(P), nsoc = D::nsoc(P), lpc = D::lpc(P);
+    const int ldg = D::ldg(P), ldt = D::ldt(P), ldh = D::ldh(P), npad = D::npad(P), nb = npad / 8, kpad = D::kpad(P);
+    const int ppad = D::ppad(P), pb = ppad / 8, ldm = D::ldm(P);
     double* G = sm + P.oG;
     double* Gt = sm + P.oR;
     double* H = sm + P.oR;
-    double* X = sm + P.oX;
+    double* X = sm + P.oR + ldh * npad;
     double* A = sm + P.oA;
     double* Bm = sm + P.oB;          // X A'            (n x p)
     double* HiAt = sm + P.oHiAt;     // H^-1 A'         (n x p)
@@ -474,25 +620,31 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
 
     for (int q = tid; q < P.total; q += T) sm[q] = 0.0;
     tsync<NW>();
-    for (int i = p + tid; i < P.ppad; i += T) Mm[i * ldm + i] = 1.0;       // unit pad diagonal of M (never overwritten)
+    for (int i = p + tid; i < ppad; i += T) Mm[i * ldm + i] = 1.0;       // unit pad diagonal of M (never overwritten)
 
     // ------------------------------------------------------------------ building blocks (lambdas over the work set)
     // calls f(SocLane, slot) for every cone slot of this lane's group; all 32 lanes take part in every pass
+    auto make_lane = [&](int slot, bool valid) {
+        SocLane L;
+        L.valid = valid;
+        L.offs = valid ? D::soc_offs(P, slot) : 0;
+        const int dim = valid ? D::soc_dim(P, slot) : 0;
+        L.g = lane & (lpc - 1);
+        L.lpc = lpc;
+        L.tm = 0;
+        F2_FOR_E { const int i = L.g + e * lpc; if (i > 0 && i < dim) L.tm |= 1u << e; }
+        return L;
+    };
     auto for_each_slot = [&](auto&& f) {
         const int spw = 32 / lpc;
         for (int base = warp * spw; base < nsoc; base += NW * spw) {
-            SocLane L;
             const int slot = base + lane / lpc;
-            L.valid = slot < nsoc;
-            L.offs = L.valid ? P.soc_offs[slot] : 0;
-            L.dim = L.valid ? P.soc_dim[slot] : 0;
-            L.g = lane & (lpc - 1);
-            L.lpc = lpc;
-            f(L, L.valid ? slot : 0);
+            const bool valid = slot < nsoc;
+            f(make_lane(valid ? slot : 0, valid), valid ? slot : 0);
         }
     };
     auto load_tail = [&](const SocLane& L, const double* v, double (&r)[4]) {
-        F2_FOR_E r[e] = L.tail(e) ? v[L.offs + L.idx(e)] : 0.0;
+        F2_FOR_E r[e] = L.tail(e) ? v[L.at(e)] : 0.0;
     };
     auto wdot = [&](const double (&w)[4], const double (&v)[4]) {     // tails only: masked entries are zero
         double d = 0.0;
@@ -527,9 +679,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
         F2_FOR_E if (L.tail(e)) {
             const double sb = sv[e] * is, zb = zv[e] * iz;
             const double lv = (sb * csf + zb * czf) * mult;               // :95-97
-            const int i = L.offs + L.idx(e);
-            wb[i] = (sb - zb) * ig;                                       // :62,:64
-            lam[i] = lv;
+            wb[L.at(e)] = (sb - zb) * ig;                                 // :62,:64
+            lam[L.at(e)] = lv;
             llt = fma(lv, lv, llt);
         }
         llt = grp_sum(llt, lpc);
@@ -546,27 +697,29 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
         return L.valid ? fail : 0;
     };
 
-    // solve_kkt head for one cone (src/densesolver.jl:61-66, then the W^-2 of :86 applied to k2):
-    // k0 = lam \ ds, k2 = dzs*dz - W k0, u = W^-2 k2.  dsv/ds0: the cone's ds (tail in registers, head scalar).
-    auto soc_head = [&](const SocLane& L, int slot, const double (&lv)[4], const double (&wv)[4],
-                        const double (&dsv)[4], double ds0, double dzs) {
+    // solve_kkt head for one cone (src/densesolver.jl:61-66, then the W^-2 of :86 applied to k2), from ds (shared
+    // memory) and dz scaled by dzs:  k0 = lam \ ds, k2 = dzs*dz - W k0, u = W^-2 k2.
+    auto soc_head = [&](const SocLane& L, int slot, double dzs) {
         const double* c = cs + slot * F2_CS;
         const double eta = c[CS_ETA], ie2 = c[CS_IE2], r1w = c[CS_R1W], w0 = c[CS_W0], l0 = c[CS_LAM0], aa = c[CS_A];
+        double lv[4], wv[4], dsv[4], k0v[4], k2v[4];
+        load_tail(L, lam, lv);
+        load_tail(L, wb, wv);
+        load_tail(L, ds, dsv);
+        const double ds0 = L.valid ? ds[L.offs] : 0.0;
         const double beta = wdot(lv, dsv);
         const double ia = fast_rcp(aa), il0 = fast_rcp(l0);
-        double k0v[4], k2v[4];
         const double k00 = (l0 * ds0 - beta) * ia;                                   // src/vectors.jl:105-125, O(d) form
         F2_FOR_E k0v[e] = L.tail(e) ? (-ds0 * lv[e] + (aa * dsv[e] + beta * lv[e]) * il0) * ia : 0.0;
         const double dl = wdot(wv, k0v);
         const double cst = k00 + dl * r1w;                                           // src/scalings.jl:135
         const double k20 = (L.valid ? dz[L.offs] * dzs : 0.0) - eta * (w0 * k00 + dl);   // :136, densesolver :65
-        F2_FOR_E k2v[e] = L.tail(e) ? dz[L.offs + L.idx(e)] * dzs - eta * (k0v[e] + cst * wv[e]) : 0.0;   // :137-139
+        F2_FOR_E k2v[e] = L.tail(e) ? dz[L.at(e)] * dzs - eta * (k0v[e] + cst * wv[e]) : 0.0;   // :137-139
         const double qv = w0 * k20 - wdot(wv, k2v);                                  // W^-2 = eta^-2 (2 q q' - J)
         F2_FOR_E if (L.tail(e)) {
-            const int i = L.offs + L.idx(e);
-            k0[i] = k0v[e];
-            k2[i] = k2v[e];
-            u[i] = ie2 * (k2v[e] - 2.0 * wv[e] * qv);
+            k0[L.at(e)] = k0v[e];
+            k2[L.at(e)] = k2v[e];
+            u[L.at(e)] = ie2 * (k2v[e] - 2.0 * wv[e] * qv);
         }
         if (L.head()) {
             k0[L.offs] = k00;
@@ -577,8 +730,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
 
     // solve_kkt tail (src/densesolver.jl:86-89), the driver's scale!/iscale! (src/solver.jl:128-129) and scmax of both
     // results (src/mats.jl:64-86) for one cone.  On exit u <- cz, k0 <- cs, k2 <- kt2 o kt3 (Jordan product).
-    auto soc_tail = [&](const SocLane& L, int slot) -> TailOut {
-        TailOut o;
+    auto soc_tail = [&](const SocLane& L, int slot, double& mx, double& dotacc, int& fl, bool chk) {
         const double* c = cs + slot * F2_CS;
         const double eta = c[CS_ETA], ie = c[CS_IE], ie2 = c[CS_IE2], r1w = c[CS_R1W], w0 = c[CS_W0], l0 = c[CS_LAM0],
                      aa = c[CS_A];
@@ -614,7 +766,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
         }
         lx3 = grp_sum(lx3, lpc); lx2 = grp_sum(lx2, lpc); dot = grp_sum(dot, lpc);
         dot += kt20 * kt30;
-        o.fail = L.valid && !(aa >= 0.0);
+        fl |= L.valid && !(aa >= 0.0);
         const double as = fast_rsqrt(aa);                                            // src/mats.jl:67-71
         const double r13 = as * l0 * kt30 - as * lx3, r12 = as * l0 * kt20 - as * lx2;      // :74-77
         const double den = fast_rcp(as * l0 + 1.0);
@@ -627,105 +779,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             q2 = fma(v2, v2, q2);
         }
         q3 = grp_sum(q3, lpc); q2 = grp_sum(q2, lpc);
-        o.mx = L.valid ? fmax(fast_sqrt(q3) - as * r13, fast_sqrt(q2) - as * r12) : -INFINITY;   // :85
-        o.dot = L.head() ? dot : 0.0;
+        if (L.valid) mx = fmax(mx, fmax(fast_sqrt(q3) - as * r13, fast_sqrt(q2) - as * r12));   // :85
         F2_FOR_E if (L.tail(e)) {
-            const int i = L.offs + L.idx(e);
-            u[i] = czv[e];
-            k0[i] = csv[e];
-            k2[i] = kt20 * kt3v[e] + kt30 * kt2v[e];                                 // src/vectors.jl:73-75
+            u[L.at(e)] = czv[e];
+            k0[L.at(e)] = csv[e];
+            k2[L.at(e)] = kt20 * kt3v[e] + kt30 * kt2v[e];                           // src/vectors.jl:73-75
+            if (chk) fl |= !isfinite(czv[e]) | !isfinite(csv[e]);
         }
+        if (chk && L.valid) fl |= !isfinite(cz0) | !isfinite(cs0);
         if (L.head()) {
+            dotacc += dot;
             u[L.offs] = cz0;
             k0[L.offs] = cs0;
             k2[L.offs] = dot;                                                        // src/vectors.jl:66-69
         }
-        return o;
-    };
-    // the same for the positive-orthant rows (elementwise); returns partial max / dot
-    auto poc_tail = [&](double& mx, double& dot) {
-        for (int i = tid; i < kpoc; i += T) {
-            const double w = wb[i], iw = iwb[i], il = fast_rcp(lam[i]);
-            const double cz = iw * iw * u[i];
-            const double kt3 = w * cz;
-            const double kk = k0[i] - kt3;
-            const double csx = w * kk;
-            const double kt2 = iw * csx;
-            mx = fmax(mx, fmax(-kt3 * il, -kt2 * il));                               // src/mats.jl:53-62
-            dot = fma(kt2, kt3, dot);
-            u[i] = cz;
-            k0[i] = csx;
-            k2[i] = kt2 * kt3;
-        }
-    };
-
-    // middle of solve_kkt, src/densesolver.jl:66-85.  In: n0 (= G'u + dx ...) formed by the caller, no barrier needed
-    // before the call.  Out: cx (returned pointer), cy, u = G cx - k2.  dys: factor applied to dy.
-    auto solve_middle = [&](double dys) -> const double* {
-        tsync<NW>();
-        gemv_rows<NW, true>(X, ldh, n, n, n0, 1, P.split_n, lane, warp, [&](int r, double acc) { t1[r] = acc; });
-        tsync<NW>();
-        gemv_cols<NW, true>(X, ldh, n, n, t1, lane, warp, [&](int c, double acc) { tt[c] = acc; });
-        if (p > 0)       // m0 = A H^-1 n0 - dy = B' t1 - dy                    :73-74
-            gemv_cols<NW, false>(Bm, n, n, p, t1, lane, warp, [&](int c, double acc) { m0[c] = acc - dys * dy[c]; });
-        tsync<NW>();
-        if (p > 0) {     // cy = M^-1 m0 (:75);  cx = H^-1 (n0 - A'cy) = t - K m0  (:76-83)
-            for (int i = tid; i < n; i += T) {
-                double acc = tt[i];
-                for (int q = 0; q < p; ++q) acc = fma(-Km[q * n + i], m0[q], acc);
-                cx[i] = acc;
-            }
-            for (int i = tid; i < p; i += T) {
-                double acc = 0.0;
-                for (int q = 0; q < p; ++q) acc = fma(Minv[q * p + i], m0[q], acc);
-                cy[i] = acc;
-            }
-            tsync<NW>();
-        }
-        const double* cxv = p > 0 ? cx : tt;
-        gemv_rows<NW, false>(G, ldg, k, n, cxv, 1, P.split_k, lane, warp, [&](int r, double acc) { u[r] = acc - k2[r]; });   // :84-85
-        tsync<NW>();
-        return cxv;
-    };
-
-    // KKT factor, src/densesolver.jl:41-52, from S = Gt (kpad x npad, pads zero).  Returns 0 when cholesky! would throw.
-    auto factor = [&]() -> int {
-        f2_syrk<NW, MAXT>(Gt, ldg, kpad, n, nb, H, ldh, lane, warp);                       // :42-43
-        for (int q = tid; q < npad * ldh; q += T) X[q] = 0.0;
-        if (tid == 0) s_fail = 0;
-        tsync<NW>();
-        PT2_MARK(P2_SYRK);
-        int ok = f2_chol_inv<NW>(H, X, Dinv, nb, ldh, &s_fail, lane, warp);                // :47-48
-        PT2_MARK(P2_CHOL);
-        if (ok && p > 0) {
-            for (int q = 0; q < p; ++q)          // B = X A'
-                gemv_rows<NW, true>(X, ldh, n, n, A + q, p, P.split_n, lane, warp, [&](int r, double acc) { Bm[q * n + r] = acc; });
-            for (int q = tid; q < P.ppad * ldm; q += T) MX[q] = 0.0;
-            tsync<NW>();
-            for (int q = 0; q < p; ++q)          // HiAt = X' B = H^-1 A'                    :49
-                gemv_cols<NW, true>(X, ldh, n, n, Bm + q * n, lane, warp, [&](int c, double acc) { HiAt[q * n + c] = acc; });
-            tsync<NW>();
-            for (int j = 0; j < p; ++j)          // M = A HiAt                              :50
-                gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, P.split_p, lane, warp, [&](int r, double acc) { Mm[j * ldm + r] = acc; });
-            tsync<NW>();
-            ok = f2_chol_inv<NW>(Mm, MX, Dinv, P.pb, ldm, &s_fail, lane, warp);            // :51
-            if (ok) {
-                for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
-                    const int i = q % p, j = q / p;
-                    double acc = 0.0;
-                    for (int m = max(i, j); m < p; ++m) acc = fma(MX[i * ldm + m], MX[j * ldm + m], acc);
-                    Minv[j * p + i] = acc;
-                }
-                tsync<NW>();
-                for (int q = tid; q < n * p; q += T) {          // K = HiAt Minv
-                    const int i = q % n, j = q / n;
-                    double acc = 0.0;
-                    for (int r = 0; r < p; ++r) acc = fma(HiAt[r * n + i], Minv[j * p + r], acc);
-                    Km[j * n + i] = acc;
-                }
-            }
-        }
-        return ok;
     };
 
     for (;;) {
@@ -750,253 +817,310 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
         int status = ST_RUNNING, iters = 0;
         tsync<NW>();
 
-        // ---- initial point, src/solver.jl:68-104: the same factor + solve with W = I, u = h, dx = -c, dy = b, k2 = h;
-        //      then cx = x, cy = y and u = G x - h = z0
-        for (int q = tid; q < npad * ldg; q += T) {
-            const int col = q / ldg, r = q - col * ldg;
-            Gt[q] = (col < n && r < k) ? G[col * ldg + r] : 0.0;
-        }
+        // The initial point (src/solver.jl:68-104, W = I) is the same factor + solve as a loop iteration with
+        // u = h, dx = -c, dy = b, k2 = h: then cx = x, cy = y and u = G x - h = z0.
+        for (int col = warp; col < npad; col += NW)
+            for (int r = lane; r < kpad; r += 32) Gt[col * ldt + r] = (col < n && r < k) ? G[col * ldg + r] : 0.0;
         for (int i = tid; i < k; i += T) { u[i] = hv[i]; k2[i] = hv[i]; }
         for (int i = tid; i < n; i += T) dx[i] = -cv[i];
         for (int i = tid; i < p; i += T) dy[i] = bv[i];
         tsync<NW>();
         PT2_MARK(P2_LOAD);
-        gemv_cols<NW, false>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + dx[c]; });
-        if (!factor()) status = ST_NUMERICAL;
-        PT2_MARK(P2_EQ);
-        if (status == ST_RUNNING) {
-            const double* cxv = solve_middle(1.0);
-            for (int i = tid; i < n; i += T) x[i] = cxv[i];
-            for (int i = tid; i < p; i += T) y[i] = cy[i];
-            // max_step(-z0), max_step(z0), src/mats.jl:1-28, then the shift of src/solver.jl:91-101
-            double mp = -INFINITY, md = -INFINITY, z4 = 0.0;
-            int fl = 0;
-            for (int i = tid; i < kpoc; i += T) { const double v = u[i]; mp = fmax(mp, v); md = fmax(md, -v); }
-            for_each_slot([&](const SocLane& L, int) {
-                double zv[4];
-                load_tail(L, u, zv);
-                double sq = 0.0;
-                F2_FOR_E sq = fma(zv[e], zv[e], sq);
-                const double nr = fast_sqrt(grp_sum(sq, lpc));
-                if (L.valid) {
-                    const double z0 = u[L.offs];
-                    mp = fmax(mp, nr + z0);          // ||-z1|| - (-z0)
-                    md = fmax(md, nr - z0);
-                }
-            });
-            team_reduce<NW>(z4, z4, z4, z4, mp, md, fl, scr + (scr_par ^= 1) * 64, lane, warp);
-            const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(md) < prm.init_eps);
-            for (int i = tid; i < k; i += T) {
-                const double z0 = u[i];
-                s[i] = -z0;
-                z[i] = z0;
-            }
-            tsync<NW>();
-            for (int i = tid; i < kpoc; i += T) {
-                if (shp) s[i] += 1.0 + mp;
-                if (shd) z[i] += 1.0 + md;
-            }
-            for (int c = tid; c < nsoc; c += T) {
-                const int o = P.soc_offs[c];
-                if (shp) s[o] += 1.0 + mp;
-                if (shd) z[o] += 1.0 + md;
-            }
-            tsync<NW>();
-        }
-        PT2_MARK(P2_INIT);
 
-        // ---- Mehrotra loop, src/solver.jl:105-151
-        while (status == ST_RUNNING && iters < prm.max_iter) {
-            // (P1) compute_scaling (:106) and the negated residuals (:110-118,:125) in one phase
-            double nx = 0.0, ny = 0.0, gap = 0.0, ll = 0.0, dm1 = -INFINITY, dm2 = -INFINITY;
-            int fl = 0;
-            for_each_slot([&](const SocLane& L, int slot) { fl |= soc_scaling(L, slot, gap, ll); });
-            for (int i = tid; i < kpoc; i += T) {                                   // src/scalings.jl:22-30
-                const double si = s[i], zi = z[i];
-                const double q = si * fast_rcp(zi), qi = zi * fast_rcp(si), pz = si * zi;
-                fl |= !(q >= 0.0) | !(pz >= 0.0);
-                const double lv = fast_sqrt(pz);
-                wb[i] = fast_sqrt(q);
-                iwb[i] = fast_sqrt(qi);
-                lam[i] = lv;
-                gap = fma(si, zi, gap);
-                ll = fma(lv, lv, ll);
-            }
-            gemv_cols<NW, false>(G, ldg, k, n, z, lane, warp, [&](int c, double acc) {
-                double v = -acc - cv[c];
-                for (int q = 0; q < p; ++q) v = fma(-A[c * p + q], y[q], v);
-                dx[c] = v;
-                nx = fma(v, v, nx);
-            });
-            gemv_rows<NW, false>(G, ldg, k, n, x, 1, P.split_k, lane, warp, [&](int r, double acc) { dz[r] = -acc - s[r] + hv[r]; });
-            if (p > 0)
-                gemv_rows<NW, false>(A, p, p, n, x, 1, P.split_p, lane, warp, [&](int r, double acc) {
-                    const double v = -acc + bv[r];
-                    dy[r] = v;
-                    ny = fma(v, v, ny);
-                });
-            team_reduce<NW>(nx, ny, gap, ll, dm1, dm2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
-            if (NW == 1) __syncwarp();
-            PT2_MARK(P2_RESID);
-            if (fl) { status = ST_NUMERICAL; break; }                              // compute_scaling threw
-            const double resid = sqrt(nx) + sqrt(ny) + gap;
-            if (resid < prm.tol) { status = ST_CONVERGED; break; }                  // :122-124
-
-            // (P2) affine right-hand side ds = -lam o lam (:120,:125), head of solve #1, Gt = W^-1 G (densesolver :41-43)
-            for_each_slot([&](const SocLane& L, int slot) {
-                const double* c = cs + slot * F2_CS;
-                double lv[4], wv[4], dsv[4];
-                load_tail(L, lam, lv);
-                load_tail(L, wb, wv);
-                const double l0 = c[CS_LAM0];
-                const double ds0 = -(c[CS_LLT] + l0 * l0);                          // src/vectors.jl:66-69
-                F2_FOR_E dsv[e] = -(l0 * lv[e] + l0 * lv[e]);                       // :73-75
-                F2_FOR_E if (L.tail(e)) ds[L.offs + L.idx(e)] = dsv[e];
-                if (L.head()) ds[L.offs] = ds0;
-                soc_head(L, slot, lv, wv, dsv, ds0, 1.0);
-            });
-            for (int i = tid; i < kpoc; i += T) {
-                const double lv = lam[i], w = wb[i], iw = iwb[i];
-                const double d = -(lv * lv);
-                const double kk = d * fast_rcp(lv);
-                const double kz = dz[i] - w * kk;
-                ds[i] = d; k0[i] = kk; k2[i] = kz; u[i] = iw * iw * kz;
-            }
-            {
-                // pad rows / pad columns of Gt (the region held H and X)
-                const int padr = kpad - k;
-                for (int q = tid; q < padr * n; q += T) Gt[(q / padr) * ldg + k + (q % padr)] = 0.0;
-                for (int q = tid; q < (npad - n) * kpad; q += T) Gt[(n + q / kpad) * ldg + (q % kpad)] = 0.0;
-                for (int col = warp; col < n; col += NW)
-                    for (int r = lane; r < kpoc; r += 32) Gt[col * ldg + r] = iwb[r] * G[col * ldg + r];
-                const int spw = 32 / lpc, npairs = n * nsoc;
-                for (int base = warp * spw; base < npairs; base += NW * spw) {
-                    const int pr = base + lane / lpc;
-                    SocLane L;
-                    L.valid = pr < npairs;
-                    const int col = L.valid ? pr / nsoc : 0;
-                    const int slot = L.valid ? pr - col * nsoc : 0;
-                    L.offs = L.valid ? P.soc_offs[slot] : 0;
-                    L.dim = L.valid ? P.soc_dim[slot] : 0;
-                    L.g = lane & (lpc - 1);
-                    L.lpc = lpc;
-                    const double* c = cs + slot * F2_CS;
-                    const double* gc = G + col * ldg;
-                    double wv[4], gv[4];
-                    load_tail(L, wb, wv);
-                    load_tail(L, gc, gv);
-                    const double dl = wdot(wv, gv);
-                    if (L.valid) {
-                        const double g0 = gc[L.offs], ie = c[CS_IE];
-                        const double cst = -g0 + dl * c[CS_R1W];                    // src/scalings.jl:151
-                        double* oc = Gt + col * ldg;
-                        F2_FOR_E if (L.tail(e)) oc[L.offs + L.idx(e)] = ie * (gv[e] + cst * wv[e]);   // :153-155
-                        if (L.g == 0) oc[L.offs] = ie * (c[CS_W0] * g0 - dl);       // :152
+        int phase = 0;              // 0: initial point, 1: affine direction (solve #1), 2: combined direction (solve #2)
+        double sc = 1.0;            // (1 - sigma) applied to dx, dy, dz in solve #2 (src/solver.jl:140)
+        double ll = 0.0;            // lambda'lambda of the current iteration
+        for (;;) {
+            // ---- n0 = G'u + sc*dx                                                   src/densesolver.jl:66-67
+            gemv_cols_v<NW>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + sc * dx[c]; });
+            if (phase != 2) {
+                // ---- KKT factor, src/densesolver.jl:41-52, from Gt (kpad x npad, pads zero)
+                f2_syrk<NW, MAXT>(Gt, ldt, kpad, n, nb, H, ldh, lane, warp);                 // :42-43
+                for (int q = tid; q < npad * ldh; q += T) X[q] = 0.0;
+                if (tid == 0) s_fail = 0;
+                tsync<NW>();
+                PT2_MARK(P2_SYRK);
+                int ok = f2_chol_inv<NW>(H, X, Dinv, nb, ldh, &s_fail, lane, warp);          // :47-48
+                PT2_MARK(P2_CHOL);
+                if (ok && p > 0) {
+                    for (int q = 0; q < p; ++q)          // B = X A'
+                        gemv_rows<NW, true>(X, ldh, n, n, A + q, p, D::split_n(P), lane, warp,
+                                            [&](int r, double acc) { Bm[q * n + r] = acc; });
+                    for (int q = tid; q < ppad * ldm; q += T) MX[q] = 0.0;
+                    tsync<NW>();
+                    for (int q = 0; q < p; ++q)          // HiAt = X' B = H^-1 A'                    :49
+                        gemv_cols<NW, true>(X, ldh, n, n, Bm + q * n, lane, warp, [&](int c, double acc) { HiAt[q * n + c] = acc; });
+                    tsync<NW>();
+                    for (int j = 0; j < p; ++j)          // M = A HiAt                              :50
+                        gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, D::split_p(P), lane, warp,
+                                             [&](int r, double acc) { Mm[j * ldm + r] = acc; });
+                    tsync<NW>();
+                    ok = f2_chol_inv<NW>(Mm, MX, Dinv, pb, ldm, &s_fail, lane, warp);        // :51
+                    if (ok) {
+                        for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
+                            const int i = q % p, j = q / p;
+                            double acc = 0.0;
+                            for (int m = max(i, j); m < p; ++m) acc = fma(MX[i * ldm + m], MX[j * ldm + m], acc);
+                            Minv[j * p + i] = acc;
+                        }
+                        tsync<NW>();
+                        for (int q = tid; q < n * p; q += T) {          // K = HiAt Minv
+                            const int i = q % n, j = q / n;
+                            double acc = 0.0;
+                            for (int r = 0; r < p; ++r) acc = fma(HiAt[r * n + i], Minv[j * p + r], acc);
+                            Km[j * n + i] = acc;
+                        }
                     }
                 }
+                PT2_MARK(P2_EQ);
+                if (!ok) { status = ST_NUMERICAL; break; }                                   // cholesky! threw
             }
+            // ---- middle of solve_kkt, src/densesolver.jl:66-85: out cx, cy, u = G cx - k2
             tsync<NW>();
-            PT2_MARK(P2_HEAD_GT);
-            gemv_cols<NW, false>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + dx[c]; });   // densesolver :66-67
-            if (!factor()) { status = ST_NUMERICAL; break; }                        // :126
-            PT2_MARK(P2_EQ);
-            solve_middle(1.0);                                                      // :127
+            gemv_rows<NW, true>(X, ldh, n, n, n0, 1, D::split_n(P), lane, warp, [&](int r, double acc) { t1[r] = acc; });
+            tsync<NW>();
+            gemv_cols<NW, true>(X, ldh, n, n, t1, lane, warp, [&](int c, double acc) { tt[c] = acc; });
+            if (p > 0)       // m0 = A H^-1 n0 - dy = B' t1 - dy                    :73-74
+                gemv_cols<NW, false>(Bm, n, n, p, t1, lane, warp, [&](int c, double acc) { m0[c] = acc - sc * dy[c]; });
+            tsync<NW>();
+            if (p > 0) {     // cy = M^-1 m0 (:75);  cx = H^-1 (n0 - A'cy) = t - K m0  (:76-83)
+                for (int i = tid; i < n; i += T) {
+                    double acc = tt[i];
+                    for (int q = 0; q < p; ++q) acc = fma(-Km[q * n + i], m0[q], acc);
+                    cx[i] = acc;
+                }
+                for (int i = tid; i < p; i += T) {
+                    double acc = 0.0;
+                    for (int q = 0; q < p; ++q) acc = fma(Minv[q * p + i], m0[q], acc);
+                    cy[i] = acc;
+                }
+                tsync<NW>();
+            }
+            const double* cxv = p > 0 ? cx : tt;
+            gemv_rows_v<NW>(G, ldg, k, n, cxv, D::split_k(P), lane, warp, [&](int r, double acc) { u[r] = acc - k2[r]; });   // :84-85
+            tsync<NW>();
             PT2_MARK(P2_SOLVE);
 
-            // (mid) tail of solve #1, centering parameter (:130-134), combined right-hand side (:136-140), head of solve #2
-            double mx = -INFINITY, dot = 0.0, z4 = 0.0;
-            fl = 0;
-            for_each_slot([&](const SocLane& L, int slot) {
-                const TailOut o = soc_tail(L, slot);
-                mx = fmax(mx, o.mx); dot += o.dot; fl |= o.fail;
-            });
-            poc_tail(mx, dot);
-            team_reduce<NW>(dot, z4, z4, z4, mx, dm2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
-            if (NW == 1) __syncwarp();
-            const double tstep = step_from_t(mx);                                   // :130
-            const double rho = 1.0 - tstep - tstep * tstep * dot * fast_rcp(ll);    // :132 (minus: reference quirk)
-            const double cl = fmax(0.0, fmin(1.0, rho));
-            const double sig = cl * cl * cl;                                        // :133
-            const double mu = ll / (double)a.g.L.deg;                               // :134
-            const double scf = 1.0 - sig, sm_ = sig * mu;                           // :136
-            if (fl) { status = ST_NUMERICAL; break; }
-            for_each_slot([&](const SocLane& L, int slot) {
-                double lv[4], wv[4], dsv[4], pv[4];
-                load_tail(L, lam, lv);
-                load_tail(L, wb, wv);
-                load_tail(L, ds, dsv);
-                load_tail(L, k2, pv);
-                F2_FOR_E dsv[e] -= pv[e];                                           // :137-139 (e is 0 on the tail)
-                const double ds0 = L.valid ? ds[L.offs] + sm_ - k2[L.offs] : 0.0;
-                soc_head(L, slot, lv, wv, dsv, ds0, scf);
-            });
+            bool new_iter;
+            if (phase == 0) {
+                for (int i = tid; i < n; i += T) x[i] = cxv[i];
+                for (int i = tid; i < p; i += T) y[i] = cy[i];
+                // max_step(-z0), max_step(z0), src/mats.jl:1-28, then the shift of src/solver.jl:91-101
+                double r2[2] = {-INFINITY, -INFINITY};
+                int fl = 0;
+                for (int i = tid; i < kpoc; i += T) { const double v = u[i]; r2[0] = fmax(r2[0], v); r2[1] = fmax(r2[1], -v); }
+                for_each_slot([&](const SocLane& L, int) {
+                    double zv[4];
+                    load_tail(L, u, zv);
+                    double sq = 0.0;
+                    F2_FOR_E sq = fma(zv[e], zv[e], sq);
+                    const double nr = fast_sqrt(grp_sum(sq, lpc));
+                    if (L.valid) {
+                        const double z0 = u[L.offs];
+                        r2[0] = fmax(r2[0], nr + z0);          // ||-z1|| - (-z0)
+                        r2[1] = fmax(r2[1], nr - z0);
+                    }
+                });
+                team_reduce<NW, 0, 2>(r2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+                const double mp = r2[0], md = r2[1];
+                const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(md) < prm.init_eps);
+                for (int i = tid; i < k; i += T) {
+                    const double z0 = u[i];
+                    s[i] = -z0;
+                    z[i] = z0;
+                }
+                tsync<NW>();
+                for (int i = tid; i < kpoc; i += T) {
+                    if (shp) s[i] += 1.0 + mp;
+                    if (shd) z[i] += 1.0 + md;
+                }
+                for (int c = tid; c < nsoc; c += T) {
+                    const int o = D::soc_offs(P, c);
+                    if (shp) s[o] += 1.0 + mp;
+                    if (shd) z[o] += 1.0 + md;
+                }
+                tsync<NW>();
+                PT2_MARK(P2_INIT);
+                new_iter = true;
+            } else {
+                // ---- tail of solve_kkt + scale!/iscale! + scmax for every cone (both solves)
+                double r2[2] = {0.0, -INFINITY};       // kt2'kt3, max scmax
+                int fl = 0;
+                for_each_slot([&](const SocLane& L, int slot) { soc_tail(L, slot, r2[1], r2[0], fl, phase == 2); });
+                for (int i = tid; i < kpoc; i += T) {
+                    const double w = wb[i], iw = iwb[i], il = fast_rcp(lam[i]);
+                    const double cz = iw * iw * u[i];
+                    const double kt3 = w * cz;
+                    const double kk = k0[i] - kt3;
+                    const double csx = w * kk;
+                    const double kt2 = iw * csx;
+                    r2[1] = fmax(r2[1], fmax(-kt3 * il, -kt2 * il));                 // src/mats.jl:53-62
+                    r2[0] = fma(kt2, kt3, r2[0]);
+                    u[i] = cz;
+                    k0[i] = csx;
+                    k2[i] = kt2 * kt3;
+                }
+                if (phase == 2) {      // the reference would carry NaN/Inf into the next cholesky! and throw there
+                    for (int i = tid; i < n; i += T) fl |= !isfinite(cxv[i]);
+                    for (int i = tid; i < p; i += T) fl |= !isfinite(cy[i]);
+                    for (int i = tid; i < kpoc; i += T) fl |= !isfinite(u[i]) | !isfinite(k0[i]);
+                }
+                PT2_MARK(P2_TAIL);
+                team_reduce<NW, 1, 1>(r2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+                if (NW == 1) __syncwarp();
+                const double tstep = step_from_t(r2[1]);                             // src/solver.jl:130 / :145
+                if (phase == 1) {
+                    // centering parameter (:130-134), combined right-hand side (:136-140)
+                    const double rho = 1.0 - tstep - tstep * tstep * r2[0] * fast_rcp(ll);   // :132 (minus: reference quirk)
+                    const double cl = fmax(0.0, fmin(1.0, rho));
+                    const double sig = cl * cl * cl;                                 // :133
+                    const double mu = ll / (double)a.g.L.deg;                        // :134
+                    if (fl) { status = ST_NUMERICAL; break; }
+                    const double smu = sig * mu;
+                    sc = 1.0 - sig;                                                  // :136
+                    for (int i = tid; i < kpoc; i += T) ds[i] += smu - k2[i];        // :137-139
+                    for_each_slot([&](const SocLane& L, int) {
+                        F2_FOR_E if (L.tail(e)) ds[L.at(e)] -= k2[L.at(e)];
+                        if (L.head()) ds[L.offs] += smu - k2[L.offs];
+                    });
+                    phase = 2;
+                    new_iter = false;
+                } else {
+                    // step length (:143-146), iterate update (:147-150)
+                    const double step = tstep * prm.step_damp;
+                    fl |= !isfinite(step);
+                    if (fl) { status = ST_NUMERICAL; break; }
+                    for (int i = tid; i < n; i += T) x[i] = fma(cxv[i], step, x[i]);     // :147
+                    for (int i = tid; i < p; i += T) y[i] = fma(cy[i], step, y[i]);      // :148
+                    for (int i = tid; i < k; i += T) {
+                        z[i] = fma(u[i], step, z[i]);                                    // :149
+                        s[i] = fma(k0[i], step, s[i]);                                   // :150
+                    }
+                    ++iters;
+                    tsync<NW>();
+                    new_iter = true;
+                }
+                PT2_MARK(P2_MIDPOST);
+            }
+
+            if (new_iter) {
+                // ---- top of a Mehrotra iteration, src/solver.jl:105-126
+                if (iters >= prm.max_iter) break;
+                // compute_scaling (:106) and the negated residuals (:110-118,:125) in one phase
+                double r4[4] = {0.0, 0.0, 0.0, 0.0};        // |rx|^2, |ry|^2, z's, lambda'lambda
+                int fl = 0;
+                for_each_slot([&](const SocLane& L, int slot) { fl |= soc_scaling(L, slot, r4[2], r4[3]); });
+                for (int i = tid; i < kpoc; i += T) {                                   // src/scalings.jl:22-30
+                    const double si = s[i], zi = z[i];
+                    const double q = si * fast_rcp(zi), qi = zi * fast_rcp(si), pz = si * zi;
+                    fl |= !(q >= 0.0) | !(pz >= 0.0);
+                    const double lv = fast_sqrt(pz);
+                    wb[i] = fast_sqrt(q);
+                    iwb[i] = fast_sqrt(qi);
+                    lam[i] = lv;
+                    r4[2] = fma(si, zi, r4[2]);
+                    r4[3] = fma(lv, lv, r4[3]);
+                }
+                gemv_cols_v<NW>(G, ldg, k, n, z, lane, warp, [&](int c, double acc) {
+                    double v = -acc - cv[c];
+                    for (int q = 0; q < p; ++q) v = fma(-A[c * p + q], y[q], v);
+                    dx[c] = v;
+                    r4[0] = fma(v, v, r4[0]);
+                });
+                gemv_rows_v<NW>(G, ldg, k, n, x, D::split_k(P), lane, warp, [&](int r, double acc) { dz[r] = -acc - s[r] + hv[r]; });
+                if (p > 0)
+                    gemv_rows<NW, false>(A, p, p, n, x, 1, D::split_p(P), lane, warp, [&](int r, double acc) {
+                        const double v = -acc + bv[r];
+                        dy[r] = v;
+                        r4[1] = fma(v, v, r4[1]);
+                    });
+                team_reduce<NW, 4, 0>(r4, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+                if (NW == 1) __syncwarp();
+                PT2_MARK(P2_RESID);
+                if (fl) { status = ST_NUMERICAL; break; }                              // compute_scaling threw
+                const double resid = sqrt(r4[0]) + sqrt(r4[1]) + r4[2];
+                if (resid < prm.tol) { status = ST_CONVERGED; break; }                  // :122-124
+                ll = r4[3];
+                // affine right-hand side ds = -lam o lam (:120,:125)
+                for (int i = tid; i < kpoc; i += T) { const double lv = lam[i]; ds[i] = -(lv * lv); }
+                for_each_slot([&](const SocLane& L, int slot) {
+                    const double* c = cs + slot * F2_CS;
+                    const double l0 = c[CS_LAM0];
+                    F2_FOR_E if (L.tail(e)) { const double lv = lam[L.at(e)]; ds[L.at(e)] = -(l0 * lv + l0 * lv); }   // src/vectors.jl:73-75
+                    if (L.head()) ds[L.offs] = -(c[CS_LLT] + l0 * l0);                  // :66-69
+                });
+                // Gt = W^-1 G column by column (densesolver :41-43); the region held H and X: pads must be zero again
+                {
+                    const int padr = kpad - k;
+                    for (int q = tid; q < padr * n; q += T) Gt[(q / padr) * ldt + k + (q % padr)] = 0.0;
+                    for (int col = n + warp; col < npad; col += NW)
+                        for (int r = lane; r < kpad; r += 32) Gt[col * ldt + r] = 0.0;
+                    for (int col = warp; col < n; col += NW)
+                        for (int r = lane; r < kpoc; r += 32) Gt[col * ldt + r] = iwb[r] * G[col * ldg + r];
+                    const int spw = 32 / lpc, npairs = n * nsoc;
+                    for (int base = warp * spw; base < npairs; base += NW * spw) {
+                        const int pr = base + lane / lpc;
+                        const bool valid = pr < npairs;
+                        const int col = valid ? pr / nsoc : 0;
+                        const int slot = valid ? pr - col * nsoc : 0;
+                        const SocLane L = make_lane(slot, valid);
+                        const double* c = cs + slot * F2_CS;
+                        const double* gc = G + col * ldg;
+                        double wv[4], gv[4];
+                        load_tail(L, wb, wv);
+                        load_tail(L, gc, gv);
+                        const double dl = wdot(wv, gv);
+                        if (valid) {
+                            const double g0 = gc[L.offs], ie = c[CS_IE];
+                            const double cst = -g0 + dl * c[CS_R1W];                    // src/scalings.jl:151
+                            double* oc = Gt + col * ldt;
+                            F2_FOR_E if (L.tail(e)) oc[L.at(e)] = ie * (gv[e] + cst * wv[e]);   // :153-155
+                            if (L.g == 0) oc[L.offs] = ie * (c[CS_W0] * g0 - dl);       // :152
+                        }
+                    }
+                }
+                sc = 1.0;
+                phase = 1;
+            }
+            // ---- head of solve_kkt (src/densesolver.jl:61-66 + W^-2) from ds and sc*dz: k0, k2, u
+            for_each_slot([&](const SocLane& L, int slot) { soc_head(L, slot, sc); });
             for (int i = tid; i < kpoc; i += T) {
-                const double lv = lam[i], w = wb[i], iw = iwb[i];
-                const double d = ds[i] + sm_ - k2[i];
-                const double kk = d * fast_rcp(lv);
-                const double kz = scf * dz[i] - w * kk;
+                const double w = wb[i], iw = iwb[i];
+                const double kk = ds[i] * fast_rcp(lam[i]);
+                const double kz = sc * dz[i] - w * kk;
                 k0[i] = kk; k2[i] = kz; u[i] = iw * iw * kz;
             }
             tsync<NW>();
-            PT2_MARK(P2_MID);
-            gemv_cols<NW, false>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + scf * dx[c]; });
-            const double* cxv = solve_middle(scf);                                  // :141
-            PT2_MARK(P2_SOLVE);
-
-            // (post) tail of solve #2, step length (:143-146), iterate update (:147-150)
-            mx = -INFINITY; dot = 0.0; fl = 0;
-            for_each_slot([&](const SocLane& L, int slot) {
-                const TailOut o = soc_tail(L, slot);
-                mx = fmax(mx, o.mx); fl |= o.fail;
-            });
-            poc_tail(mx, dot);
-            // the reference would carry NaN/Inf into the next cholesky! and throw there
-            for (int i = tid; i < n; i += T) fl |= !isfinite(cxv[i]);
-            for (int i = tid; i < p; i += T) fl |= !isfinite(cy[i]);
-            for (int i = tid; i < k; i += T) fl |= !isfinite(u[i]) | !isfinite(k0[i]);
-            team_reduce<NW>(z4, z4, z4, z4, mx, dm2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
-            if (NW == 1) __syncwarp();
-            const double step = step_from_t(mx) * prm.step_damp;                    // :145-146
-            fl |= !isfinite(step);
-            if (fl) { status = ST_NUMERICAL; break; }
-            for (int i = tid; i < n; i += T) x[i] = fma(cxv[i], step, x[i]);        // :147
-            for (int i = tid; i < p; i += T) y[i] = fma(cy[i], step, y[i]);         // :148
-            for (int i = tid; i < k; i += T) {
-                z[i] = fma(u[i], step, z[i]);                                       // :149
-                s[i] = fma(k0[i], step, s[i]);                                      // :150
-            }
-            ++iters;
-            tsync<NW>();
-            PT2_MARK(P2_POST);
+            PT2_MARK(P2_HEAD_GT);
         }
         if (status == ST_RUNNING) status = ST_MAXITER;
         tsync<NW>();
 
         // ---- results: iterate and objectives (pobj = c'x, dobj = -b'y - h'z)
         {
-            const bool dead = (status == ST_NUMERICAL && iters == 0 && s_fail);
-            double po = 0.0, d = 0.0, z2 = 0.0, m1 = -INFINITY, m2 = -INFINITY;
+            const bool dead = (status == ST_NUMERICAL && phase == 0);      // the initial factorisation failed
+            double r2[2] = {0.0, 0.0};
             int fl = 0;
             for (int i = tid; i < n; i += T) {
                 const double xi = dead ? 0.0 : x[i];
                 a.g.x[(int64_t)b * n + i] = xi;
-                po = fma(cv[i], xi, po);
+                r2[0] = fma(cv[i], xi, r2[0]);
             }
             for (int i = tid; i < p; i += T) {
                 const double yi = dead ? 0.0 : y[i];
                 a.g.y[(int64_t)b * p + i] = yi;
-                d = fma(-bv[i], yi, d);
+                r2[1] = fma(-bv[i], yi, r2[1]);
             }
             for (int i = tid; i < k; i += T) {
                 const double zi = dead ? 0.0 : z[i];
                 a.g.z[(int64_t)b * k + i] = zi;
                 a.g.s[(int64_t)b * k + i] = dead ? 0.0 : s[i];
-                d = fma(-hv[i], zi, d);
+                r2[1] = fma(-hv[i], zi, r2[1]);
             }
-            team_reduce<NW>(po, d, z2, z2, m1, m2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
+            team_reduce<NW, 2, 0>(r2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
             if (tid == 0) {
-                a.g.sc[b].pobj = po;
-                a.g.sc[b].dobj = d;
+                a.g.sc[b].pobj = r2[0];
+                a.g.sc[b].dobj = r2[1];
                 a.g.status[b] = status;
                 a.g.iters[b] = iters;
                 a.g.active[b] = 0;
@@ -1008,14 +1132,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
     }
 }
 
-template <int NW, int MAXT, int MINB>
+// compile-time specialised layouts (BASELINE.json): C2 = portfolio n=50, p=1, POC 50 + SOC 51; C3 = n=12, 10 x SOC 4
+using DimsC2 = DimsStatic<8, 50, 1, 50, 1, 51>;
+using DimsC3 = DimsStatic<1, 12, 0, 0, 10, 4>;
+
+template <int NW, int MAXT, int MINB, class D>
 inline void fused2_launch(const F2Plan& plan, const F2Args& args, int grid, cudaStream_t stream) {
-    cudaFuncSetAttribute(k_fused2<NW, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    k_fused2<NW, MAXT, MINB><<<grid, NW * 32, plan.smem, stream>>>(args);
+    cudaFuncSetAttribute(k_fused2<NW, MAXT, MINB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    k_fused2<NW, MAXT, MINB, D><<<grid, NW * 32, plan.smem, stream>>>(args);
 }
 
 inline void solve_fused2(F2Plan& plan, const Ws& g, int batch, int max_iter, double tol, double step_damp,
-                         double init_eps, cudaStream_t stream) {
+                         double init_eps, cudaStream_t stream, bool allow_static = true) {
     cudaMemsetAsync(plan.d_counter, 0, sizeof(int), stream);
     F2Args args;
     args.g = g;
@@ -1024,11 +1152,13 @@ inline void solve_fused2(F2Plan& plan, const Ws& g, int batch, int max_iter, dou
     args.batch = batch;
     args.counter = plan.d_counter;
     const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
+    if (allow_static && DimsC2::matches(plan)) { fused2_launch<8, 4, 2, DimsC2>(plan, args, grid, stream); return; }
+    if (allow_static && DimsC3::matches(plan)) { fused2_launch<1, 3, 16, DimsC3>(plan, args, grid, stream); return; }
     switch (plan.variant) {
-        case 0: fused2_launch<1, 3, 16>(plan, args, grid, stream); break;     // n <= 16: one warp per problem
-        case 1: fused2_launch<4, 3, 4>(plan, args, grid, stream); break;      // n <= 32: 10 tiles over 4 warps
-        case 2: fused2_launch<8, 4, 2>(plan, args, grid, stream); break;      // n <= 56: 28 tiles over 8 warps
-        default: fused2_launch<8, 5, 2>(plan, args, grid, stream); break;     // n <= 64: 36 tiles over 8 warps
+        case 0: fused2_launch<1, 3, 16, DimsDyn>(plan, args, grid, stream); break;     // n <= 16: one warp per problem
+        case 1: fused2_launch<4, 3, 4, DimsDyn>(plan, args, grid, stream); break;      // n <= 32: 10 tiles over 4 warps
+        case 2: fused2_launch<8, 4, 2, DimsDyn>(plan, args, grid, stream); break;      // n <= 56: 28 tiles over 8 warps
+        default: fused2_launch<8, 5, 2, DimsDyn>(plan, args, grid, stream); break;     // n <= 64: 36 tiles over 8 warps
     }
 }
 

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -469,7 +470,8 @@ void run_solve(Shard& sh, const socp_params& prm) {
     const int path = choose_path(sh, prm);
     if (path == SOCP_PATH_FUSED || path == PATH_FUSED_V1) {
         if (path == SOCP_PATH_FUSED)
-            solve_fused2(sh.fused2, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
+            solve_fused2(sh.fused2, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream,
+                         /*allow_static=*/getenv("SOCP_B200_GENERIC_ONLY") == nullptr);
         else
             solve_fused(sh.fused, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
         CK(cudaGetLastError());
