@@ -47,14 +47,14 @@ struct F2Plan {
     int* d_counter = nullptr;
     // layout
     int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
-    int npad = 0, nb = 0, kpad = 0, ldg = 0, ldt = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
+    int npad = 0, nb = 0, kpad = 0, ldg = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
     int shape = 0;         // 0: generic kernel; > 0: index of a compile-time specialised layout (F2_SHAPES)
     int split_k = 1, split_n = 1, split_p = 1;    // lanes per output row of the row gemvs (k, n, p rows)
     int soc_offs[F2_MAX_SOC], soc_dim[F2_MAX_SOC];
     // offsets into the dynamic shared memory, in doubles
-    int oG, oR, oX, oA, oB, oHiAt, oK, oM, oMX, oMinv, oDinv;
+    int oG, oR, oX, oA, oAt, oHiAt, oK, oM, oMX, oMinv, oDinv;
     int oc, ob, oh, ox, oy, oz, os, olam, owb, oiwb, ocs, odx, ody, odz, ods, ok0, ok2, ou;
-    int on0, ot1, ot, ocx, om0, ocy, oscr;
+    int on0, ocx, ocy, okd, omd, odw, ohc, oscr;
     int total = 0;
 };
 
@@ -73,6 +73,11 @@ __host__ __device__ constexpr int f2_split(int units, int nw) {   // lanes per o
     while (split > 1 && (units + (32 / split) - 1) / (32 / split) > nw) split >>= 1;
     return split;
 }
+// The inverse factor X = L^-1 is lower triangular: it is stored as a trapezoid, column block cb (8 columns) holding
+// only the rows from 8*cb on, with its own leading dimension (== 4 mod 8).  For nbl block columns:
+__host__ __device__ constexpr int f2_xld(int nbl, int cb) { return (nbl - cb) * 8 + 4; }
+__host__ __device__ constexpr int f2_xbase(int nbl, int cb) { return 8 * cb * (nbl * 8 + 4) - 32 * cb * (cb - 1); }
+__host__ __device__ constexpr int f2_xsize(int nbl) { return f2_xbase(nbl, nbl); }
 __host__ __device__ constexpr int f2_lpc(int maxdim) {   // lanes per second-order cone: 4 elements per lane
     int l = 1;
     while (l * 4 < maxdim) l <<= 1;
@@ -104,8 +109,7 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     else { P.variant = 3; P.nw = 8; }
     P.npad = (n + 7) / 8 * 8; P.nb = P.npad / 8;
     P.kpad = (k + 3) / 4 * 4;
-    P.ldg = f2_ldv(P.kpad);
-    P.ldt = f2_ld(P.kpad);
+    P.ldg = f2_ld(P.kpad);
     P.ldh = f2_ld(P.npad);
     P.ppad = (std::max(p, 1) + 7) / 8 * 8; P.pb = P.ppad / 8;
     P.ldm = f2_ld(P.ppad);
@@ -114,15 +118,15 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     P.split_p = f2_split(std::max(p, 1), P.nw);
     int at = 0;
     auto take = [&](int cnt) { int r = at; at += (cnt + 1) / 2 * 2; return r; };
-    P.oG = take(P.ldg * n);
-    const int gt_sz = P.ldt * P.npad, hx_sz = 2 * P.ldh * P.npad;
-    P.oR = take(std::max(gt_sz, hx_sz));
+    P.oG = take(P.ldg * (n + 1));                 // pad rows and column n stay zero (pad columns of the SYRK read column n)
+    P.oR = take(P.ldh * P.npad + f2_xsize(P.nb)); // H (later H^-1, then the solve matrix) | X (trapezoid)
     P.oX = P.oR + P.ldh * P.npad;
-    P.oA = take(p * n); P.oB = take(n * p); P.oHiAt = take(n * p); P.oK = take(n * p);
-    P.oM = take(p ? P.ldm * P.ppad : 0); P.oMX = take(p ? P.ldm * P.ppad : 0); P.oMinv = take(p * p);
+    P.oA = take(p * n); P.oAt = take(p * P.npad); P.oHiAt = take(n * p); P.oK = take(n * p);
+    P.oM = take(p ? P.ldm * P.ppad : 0); P.oMX = take(p ? f2_xsize(P.pb) : 0); P.oMinv = take(p * p);
     P.oDinv = take(2 * 8 * 12);
-    P.oc = take(n); P.ox = take(n); P.odx = take(n); P.on0 = take(n); P.ot1 = take(n); P.ot = take(n); P.ocx = take(n);
-    P.ob = take(p); P.oy = take(p); P.ody = take(p); P.om0 = take(p); P.ocy = take(p);
+    P.oc = take(n); P.ox = take(n); P.odx = take(n); P.on0 = take(P.npad); P.ocx = take(n); P.okd = take(n);
+    P.ob = take(p); P.oy = take(p); P.ody = take(p); P.ocy = take(p); P.omd = take(p);
+    P.odw = take(P.kpad); P.ohc = take(std::max(P.nsoc, 1) * P.npad);
     P.oh = take(k); P.oz = take(k); P.os = take(k); P.olam = take(k); P.owb = take(k); P.oiwb = take(P.kpoc);
     P.odz = take(k); P.ods = take(k); P.ok0 = take(k); P.ok2 = take(k); P.ou = take(k);
     P.ocs = take(F2_CS * std::max(P.nsoc, 1));
@@ -190,29 +194,30 @@ __device__ __forceinline__ void team_reduce(double (&v)[NS + NM], int& flag, dou
     flag = f != 0.0;
 }
 
-// out(c) = sum_r M[c*ld + r] * x[r] over rows [0, rows): four lanes per column, each lane takes the row pairs
-// {2rl, 2rl+1} + 8m with 128-bit loads (ld == 8 mod 16: conflict free).  M rows and x must be zero / finite up to
-// the next even row.  epi(c, acc) runs on one lane per column.
+// out(c) = sum_r M[c*ld + r] * x[r] over rows [0, rows): eight lanes per column, lane rl takes the row pairs
+// {2rl, 2rl+1} + 16m with 128-bit loads (a quarter warp reads 128 contiguous bytes: conflict free for any even ld).
+// M rows and x must be zero / finite up to the next even row.  epi(c, acc) runs on one lane per column.
 template <int NW, class Epi>
 __device__ __forceinline__ void gemv_cols_v(const double* __restrict__ M, int ld, int rows, int cols,
                                             const double* __restrict__ x, int lane, int warp, Epi epi) {
-    const int cq = lane >> 2, rl = lane & 3;
-    const double2* xv = reinterpret_cast<const double2*>(x) + rl;
+    const int cq = lane >> 3, rl = lane & 7;
+    const double2* xv = reinterpret_cast<const double2*>(x);
     const int npair = (rows + 1) >> 1;
-    for (int c0 = warp * 8; c0 < cols; c0 += NW * 8) {
+    for (int c0 = warp * 4; c0 < cols; c0 += NW * 4) {
         const int c = c0 + cq;
         const bool ok = c < cols;
-        const double2* col = reinterpret_cast<const double2*>(M + (ok ? c : 0) * ld) + rl;
+        const double2* col = reinterpret_cast<const double2*>(M + (ok ? c : 0) * ld);
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll 4
-        for (int q = rl; q < npair; q += 4) {
-            const double2 g = col[q - rl], w = xv[q - rl];
+        for (int q = rl; q < npair; q += 8) {
+            const double2 g = col[q], w = xv[q];
             a0 = fma(g.x, w.x, a0);
             a1 = fma(g.y, w.y, a1);
         }
         double acc = a0 + a1;
         acc += __shfl_xor_sync(FULL_MASK, acc, 1);
         acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+        acc += __shfl_xor_sync(FULL_MASK, acc, 4);
         if (rl == 0 && ok) epi(c, acc);
     }
 }
@@ -305,11 +310,22 @@ __device__ __forceinline__ void gemv_rows(const double* __restrict__ M, int ld, 
 }
 
 // ------------------------------------------------------------------------------------------------ SYRK
-// H (lower 8x8 tiles, n x n padded to npad with a unit pad diagonal, ld ldh) = S' S for S = kpad x npad (ld ldg,
-// pad rows/columns zero).  Accumulates in registers; tsync; stores (H may alias S).  The caller syncs afterwards.
+// Tile t (row-major over the lower triangle) -> (ti, tj), ti >= tj.
+__device__ __forceinline__ void f2_tile(int t, int& ti, int& tj) {
+    int a = 0;
+    while ((a + 1) * (a + 2) / 2 <= t) ++a;
+    ti = a;
+    tj = t - a * (a + 1) / 2;
+}
+// H (lower 8x8 tiles incl. full diagonal tiles; n x n padded to npad with a unit pad diagonal; ld ldh)
+//   = G' diag(dw) G + sum_c hc[c] hc[c]'
+// which is G'W^-2 G of src/densesolver.jl:42-43 for W^-2 = blockdiag(iwb^2 | eta^-2 (2 q q' - J)) (SURVEY.md appendix
+// A.1): dw = iwb^2 on positive-orthant rows, eta^-2 on cone tails, -eta^-2 on cone heads, hc[c] = sqrt(2)/eta G_c'q.
+// G: kpad x (n+1), ld ldg (pad rows and column n zero).  mma.sync m8n8k4 f64 from shared memory; accumulators in
+// registers.  The caller syncs afterwards.
 template <int NW, int MAXT>
-__device__ __forceinline__ void f2_syrk(const double* S, int ldg, int kpad, int n, int nb, double* H, int ldh,
-                                        int lane, int warp) {
+__device__ __forceinline__ void f2_syrk_w(const double* G, int ldg, int kpad, int n, int nb, const double* dw,
+                                          const double* hc, int nsoc, int npad, double* H, int ldh, int lane, int warp) {
     const int ntl = nb * (nb + 1) / 2;
     const int fr = lane >> 2, fk = lane & 3;
     const double* pa[MAXT];
@@ -318,20 +334,55 @@ __device__ __forceinline__ void f2_syrk(const double* S, int ldg, int kpad, int 
     double acc[MAXT][2];
 #pragma unroll
     for (int q = 0; q < MAXT; ++q) {
-        int t = warp + q * NW;
-        if (t >= ntl) t = ntl - 1;                 // duplicates compute a valid tile and skip the store
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= t) ++a;
-        ti[q] = a;
-        tj[q] = t - a * (a + 1) / 2;
-        pa[q] = S + (ti[q] * 8 + fr) * ldg + fk;
-        pb[q] = S + (tj[q] * 8 + fr) * ldg + fk;
+        const int t = min(warp + q * NW, ntl - 1);
+        f2_tile(t, ti[q], tj[q]);
+        pa[q] = G + min(ti[q] * 8 + fr, n) * ldg + fk;      // column n is the zero column
+        pb[q] = G + min(tj[q] * 8 + fr, n) * ldg + fk;
         acc[q][0] = acc[q][1] = 0.0;
     }
+    const double* pw = dw + fk;
 #pragma unroll 4
     for (int kk = 0; kk < kpad; kk += 4) {
+        const double w = pw[kk];
 #pragma unroll
-        for (int q = 0; q < MAXT; ++q) dmma884(acc[q][0], acc[q][1], pa[q][kk], pb[q][kk]);
+        for (int q = 0; q < MAXT; ++q)
+            if (warp + q * NW < ntl) dmma884(acc[q][0], acc[q][1], pa[q][kk] * w, pb[q][kk]);
+    }
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        if (warp + q * NW < ntl) {
+            const int gi = ti[q] * 8 + fr;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = tj[q] * 8 + 2 * fk + e;
+                double v = acc[q][e];
+                for (int c = 0; c < nsoc; ++c) v = fma(hc[c * npad + gi], hc[c * npad + gj], v);
+                if (gi == gj && gi >= n) v = 1.0;
+                H[gj * ldh + gi] = v;
+            }
+        }
+    }
+}
+// Out (full symmetric, ld) = X' X for the lower-triangular X (trapezoid storage; the part of a diagonal tile above
+// the diagonal is zero): H^-1 = L^-T L^-1.  Accumulates in registers, team barrier, then
+// stores, so Out may alias anything but X.
+template <int NW, int MAXT>
+__device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* Out, int lane, int warp) {
+    const int ntl = nb * (nb + 1) / 2;
+    const int fr = lane >> 2, fk = lane & 3;
+    int ti[MAXT], tj[MAXT];
+    double acc[MAXT][2];
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        const int t = min(warp + q * NW, ntl - 1);
+        f2_tile(t, ti[q], tj[q]);
+        acc[q][0] = acc[q][1] = 0.0;
+        if (warp + q * NW < ntl) {
+            // rows kk of column block cb live at offset kk - 8*cb of that block
+            const double* pa = X + f2_xbase(nb, ti[q]) + fr * f2_xld(nb, ti[q]) + fk - ti[q] * 8;
+            const double* pb = X + f2_xbase(nb, tj[q]) + fr * f2_xld(nb, tj[q]) + fk - tj[q] * 8;
+            for (int kk = ti[q] * 8; kk < nb * 8; kk += 4) dmma884(acc[q][0], acc[q][1], pa[kk], pb[kk]);
+        }
     }
     tsync<NW>();
 #pragma unroll
@@ -341,9 +392,8 @@ __device__ __forceinline__ void f2_syrk(const double* S, int ldg, int kpad, int 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int gj = tj[q] * 8 + 2 * fk + e;
-                double v = acc[q][e];
-                if (gi == gj && gi >= n) v = 1.0;
-                H[gj * ldh + gi] = v;
+                Out[gj * ld + gi] = acc[q][e];
+                Out[gi * ld + gj] = acc[q][e];
             }
         }
     }
@@ -407,7 +457,7 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     Db[i * 12 + lane] = xc[i];
-                    X[(b0 + lane) * ld + b0 + i] = xc[i];
+                    X[f2_xbase(nbl, b) + lane * f2_xld(nbl, b) + i] = xc[i];
                 }
             }
         }
@@ -426,14 +476,14 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
                 T[(2 * fk) * ld + fr] = c0;
                 T[(2 * fk + 1) * ld + fr] = c1;
             } else {
-                const int cc0 = (t - (nbl - 1 - b)) * 8;
-                double* T = X + cc0 * ld + b0;
+                const int cb = t - (nbl - 1 - b), xl = f2_xld(nbl, cb);
+                double* T = X + f2_xbase(nbl, cb) + (b - cb) * 8;
                 const double d0 = Db[fr * 12 + fk], d1 = Db[fr * 12 + 4 + fk];
-                const double x0 = T[fr * ld + fk], x1 = T[fr * ld + 4 + fk];
+                const double x0 = T[fr * xl + fk], x1 = T[fr * xl + 4 + fk];
                 dmma884(c0, c1, d0, x0);
                 dmma884(c0, c1, d1, x1);
-                T[(2 * fk) * ld + fr] = c0;
-                T[(2 * fk + 1) * ld + fr] = c1;
+                T[(2 * fk) * xl + fr] = c0;
+                T[(2 * fk + 1) * xl + fr] = c1;
             }
         }
         tsync<NW>();                                   // (2) panel visible
@@ -458,22 +508,26 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
                 const double a0 = -Lp[fk * ld + fr], a1 = -Lp[(4 + fk) * ld + fr];
                 double c0, c1, q0, q1;
                 double* C;
+                int cl;                                  // leading dimension of the destination tile
                 if (j > b) {
                     C = H + j0 * ld + i0;
+                    cl = ld;
                     const double* Lj = H + b0 * ld + j0;
                     q0 = Lj[fk * ld + fr]; q1 = Lj[(4 + fk) * ld + fr];
                     c0 = C[(2 * fk) * ld + fr]; c1 = C[(2 * fk + 1) * ld + fr];
                 } else {
-                    C = X + j0 * ld + i0;
-                    const double* Xb = X + j0 * ld + b0;
-                    q0 = Xb[fr * ld + fk]; q1 = Xb[fr * ld + 4 + fk];
+                    cl = f2_xld(nbl, j);
+                    const double* Xj = X + f2_xbase(nbl, j);        // column block j, rows from j0 on
+                    C = const_cast<double*>(Xj) + (i0 - j0);
+                    const double* Xb = Xj + (b0 - j0);
+                    q0 = Xb[fr * cl + fk]; q1 = Xb[fr * cl + 4 + fk];
                     if (j == b) { c0 = 0.0; c1 = 0.0; }
-                    else { c0 = C[(2 * fk) * ld + fr]; c1 = C[(2 * fk + 1) * ld + fr]; }
+                    else { c0 = C[(2 * fk) * cl + fr]; c1 = C[(2 * fk + 1) * cl + fr]; }
                 }
                 dmma884(c0, c1, a0, q0);
                 dmma884(c0, c1, a1, q1);
-                C[(2 * fk) * ld + fr] = c0;
-                C[(2 * fk + 1) * ld + fr] = c1;
+                C[(2 * fk) * cl + fr] = c0;
+                C[(2 * fk + 1) * cl + fr] = c1;
             }
         }
     }
@@ -497,7 +551,6 @@ struct DimsDyn {
     __device__ __forceinline__ static int npad(const F2Plan& P) { return P.npad; }
     __device__ __forceinline__ static int kpad(const F2Plan& P) { return P.kpad; }
     __device__ __forceinline__ static int ldg(const F2Plan& P) { return P.ldg; }
-    __device__ __forceinline__ static int ldt(const F2Plan& P) { return P.ldt; }
     __device__ __forceinline__ static int ldh(const F2Plan& P) { return P.ldh; }
     __device__ __forceinline__ static int ppad(const F2Plan& P) { return P.ppad; }
     __device__ __forceinline__ static int ldm(const F2Plan& P) { return P.ldm; }
@@ -521,8 +574,7 @@ struct DimsStatic {
     __device__ __forceinline__ static constexpr int lpc(const F2Plan&) { return f2_lpc(SDIM); }
     __device__ __forceinline__ static constexpr int npad(const F2Plan&) { return NPAD; }
     __device__ __forceinline__ static constexpr int kpad(const F2Plan&) { return KPAD; }
-    __device__ __forceinline__ static constexpr int ldg(const F2Plan&) { return f2_ldv(KPAD); }
-    __device__ __forceinline__ static constexpr int ldt(const F2Plan&) { return f2_ld(KPAD); }
+    __device__ __forceinline__ static constexpr int ldg(const F2Plan&) { return f2_ld(KPAD); }
     __device__ __forceinline__ static constexpr int ldh(const F2Plan&) { return f2_ld(NPAD); }
     __device__ __forceinline__ static constexpr int ppad(const F2Plan&) { return PPAD; }
     __device__ __forceinline__ static constexpr int ldm(const F2Plan&) { return f2_ld(PPAD); }
@@ -590,14 +642,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int T = NW * 32;
     const int n = D::n(P), p = D::p(P), k = D::k(P), kpoc = D::kpoc(P), nsoc = D::nsoc(P), lpc = D::lpc(P);
-    const int ldg = D::ldg(P), ldt = D::ldt(P), ldh = D::ldh(P), npad = D::npad(P), nb = npad / 8, kpad = D::kpad(P);
+    const int ldg = D::ldg(P), ldh = D::ldh(P), npad = D::npad(P), nb = npad / 8, kpad = D::kpad(P);
     const int ppad = D::ppad(P), pb = ppad / 8, ldm = D::ldm(P);
     double* G = sm + P.oG;
-    double* Gt = sm + P.oR;
-    double* H = sm + P.oR;
+    double* H = sm + P.oR;           // G'W^-2 G, then H^-1, then the solve matrix Pm = H^-1 - K (H^-1 A')'
     double* X = sm + P.oR + ldh * npad;
     double* A = sm + P.oA;
-    double* Bm = sm + P.oB;          // X A'            (n x p)
+    double* At = sm + P.oAt;         // A' (rows of A contiguous, stride npad)
     double* HiAt = sm + P.oHiAt;     // H^-1 A'         (n x p)
     double* Km = sm + P.oK;          // H^-1 A' M^-1    (n x p)
     double* Mm = sm + P.oM;
@@ -611,8 +662,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
     double* lam = sm + P.olam; double* wb = sm + P.owb; double* iwb = sm + P.oiwb; double* cs = sm + P.ocs;
     double* dx = sm + P.odx; double* dy = sm + P.ody; double* dz = sm + P.odz; double* ds = sm + P.ods;
     double* k0 = sm + P.ok0; double* k2 = sm + P.ok2; double* u = sm + P.ou;
-    double* n0 = sm + P.on0; double* t1 = sm + P.ot1; double* tt = sm + P.ot; double* cx = sm + P.ocx;
-    double* m0 = sm + P.om0; double* cy = sm + P.ocy;
+    double* n0 = sm + P.on0; double* cx = sm + P.ocx; double* cy = sm + P.ocy;
+    double* kd = sm + P.okd;         // K dy            (n)
+    double* md = sm + P.omd;         // M^-1 dy         (p)
+    double* dw = sm + P.odw;         // row weights of the SYRK (kpad)
+    double* hc = sm + P.ohc;         // sqrt(2)/eta G_c'q per cone (nsoc x npad)
     double* scr = sm + P.oscr;
     int scr_par = 0;
     const LoopParams prm = a.prm;
@@ -672,6 +726,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
         const double rg = fast_rsqrt(g2);
         const double gamma = g2 * rg, ig = 0.5 * rg;                      // :57, :64
         const double eta = fast_sqrt(nrms * iz);                          // :68
+        const double ie = fast_rcp(eta), ie2 = ie * ie;
         const double tmv1 = fast_sqrt(nrms * nrmz);                       // :91
         const double mult = tmv1 * fast_rcp(zb0 + sb0 + 2.0 * gamma);     // :92
         const double csf = gamma + zb0, czf = gamma + sb0;                // :93-94
@@ -681,16 +736,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             const double lv = (sb * csf + zb * czf) * mult;               // :95-97
             wb[L.at(e)] = (sb - zb) * ig;                                 // :62,:64
             lam[L.at(e)] = lv;
+            dw[L.at(e)] = ie2;                                            // W^-2 = eta^-2 (2 q q' - J): tail weight
             llt = fma(lv, lv, llt);
         }
         llt = grp_sum(llt, lpc);
         if (L.head()) {
-            const double w0 = (sb0 + zb0) * ig, l0 = gamma * tmv1, ie = fast_rcp(eta);
+            const double w0 = (sb0 + zb0) * ig, l0 = gamma * tmv1;
             wb[L.offs] = w0;                                              // :60
             lam[L.offs] = l0;                                             // :98
             double* c = cs + slot * F2_CS;
-            c[CS_ETA] = eta; c[CS_IE] = ie; c[CS_IE2] = ie * ie; c[CS_R1W] = fast_rcp(1.0 + w0);
+            c[CS_ETA] = eta; c[CS_IE] = ie; c[CS_IE2] = ie2; c[CS_R1W] = fast_rcp(1.0 + w0);
             c[CS_W0] = w0; c[CS_LAM0] = l0; c[CS_A] = l0 * l0 - llt; c[CS_LLT] = llt;
+            dw[L.offs] = -ie2;                                            // head weight
             gap += s0 * z0 + sz;
             ll += l0 * l0 + llt;
         }
@@ -809,7 +866,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             for (int col = warp; col < n; col += NW)
                 for (int r = lane; r < k; r += 32) G[col * ldg + r] = Gg[(int64_t)col * k + r];
             const double* Ag = a.g.A + (int64_t)b * a.g.sA;
-            for (int q = tid; q < p * n; q += T) A[q] = Ag[q];
+            for (int q = tid; q < p * n; q += T) { const double v = Ag[q]; A[q] = v; At[(q % p) * npad + q / p] = v; }
             for (int i = tid; i < n; i += T) cv[i] = a.g.c[(int64_t)b * n + i];
             for (int i = tid; i < p; i += T) bv[i] = a.g.b[(int64_t)b * p + i];
             for (int i = tid; i < k; i += T) hv[i] = a.g.h[(int64_t)b * k + i];
@@ -819,9 +876,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
 
         // The initial point (src/solver.jl:68-104, W = I) is the same factor + solve as a loop iteration with
         // u = h, dx = -c, dy = b, k2 = h: then cx = x, cy = y and u = G x - h = z0.
-        for (int col = warp; col < npad; col += NW)
-            for (int r = lane; r < kpad; r += 32) Gt[col * ldt + r] = (col < n && r < k) ? G[col * ldg + r] : 0.0;
-        for (int i = tid; i < k; i += T) { u[i] = hv[i]; k2[i] = hv[i]; }
+        for (int i = tid; i < k; i += T) { u[i] = hv[i]; k2[i] = hv[i]; dw[i] = 1.0; }
+        for (int q = tid; q < nsoc * npad; q += T) hc[q] = 0.0;
         for (int i = tid; i < n; i += T) dx[i] = -cv[i];
         for (int i = tid; i < p; i += T) dy[i] = bv[i];
         tsync<NW>();
@@ -834,22 +890,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             // ---- n0 = G'u + sc*dx                                                   src/densesolver.jl:66-67
             gemv_cols_v<NW>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + sc * dx[c]; });
             if (phase != 2) {
-                // ---- KKT factor, src/densesolver.jl:41-52, from Gt (kpad x npad, pads zero)
-                f2_syrk<NW, MAXT>(Gt, ldt, kpad, n, nb, H, ldh, lane, warp);                 // :42-43
-                for (int q = tid; q < npad * ldh; q += T) X[q] = 0.0;
+                // ---- KKT factor, src/densesolver.jl:41-52
+                f2_syrk_w<NW, MAXT>(G, ldg, kpad, n, nb, dw, hc, nsoc, npad, H, ldh, lane, warp);   // :42-43
+                for (int q = tid; q < f2_xsize(nb); q += T) X[q] = 0.0;
                 if (tid == 0) s_fail = 0;
                 tsync<NW>();
                 PT2_MARK(P2_SYRK);
-                int ok = f2_chol_inv<NW>(H, X, Dinv, nb, ldh, &s_fail, lane, warp);          // :47-48
+                int ok = f2_chol_inv<NW>(H, X, Dinv, nb, ldh, &s_fail, lane, warp);          // :47
+                if (ok) f2_xtx<NW, MAXT>(X, ldh, nb, H, lane, warp);                         // :48  Li = H^-1 (explicit)
+                tsync<NW>();
                 PT2_MARK(P2_CHOL);
                 if (ok && p > 0) {
-                    for (int q = 0; q < p; ++q)          // B = X A'
-                        gemv_rows<NW, true>(X, ldh, n, n, A + q, p, D::split_n(P), lane, warp,
-                                            [&](int r, double acc) { Bm[q * n + r] = acc; });
-                    for (int q = tid; q < ppad * ldm; q += T) MX[q] = 0.0;
-                    tsync<NW>();
-                    for (int q = 0; q < p; ++q)          // HiAt = X' B = H^-1 A'                    :49
-                        gemv_cols<NW, true>(X, ldh, n, n, Bm + q * n, lane, warp, [&](int c, double acc) { HiAt[q * n + c] = acc; });
+                    for (int q = 0; q < p; ++q)          // HiAt = H^-1 A'                           :49
+                        gemv_cols_v<NW>(H, ldh, n, n, At + q * npad, lane, warp, [&](int c, double acc) { HiAt[q * n + c] = acc; });
+                    for (int q = tid; q < f2_xsize(pb); q += T) MX[q] = 0.0;
                     tsync<NW>();
                     for (int j = 0; j < p; ++j)          // M = A HiAt                              :50
                         gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, D::split_p(P), lane, warp,
@@ -860,7 +914,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                         for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
                             const int i = q % p, j = q / p;
                             double acc = 0.0;
-                            for (int m = max(i, j); m < p; ++m) acc = fma(MX[i * ldm + m], MX[j * ldm + m], acc);
+                            const double* xi = MX + f2_xbase(pb, i >> 3) + (i & 7) * f2_xld(pb, i >> 3) - (i & ~7);
+                            const double* xj = MX + f2_xbase(pb, j >> 3) + (j & 7) * f2_xld(pb, j >> 3) - (j & ~7);
+                            for (int m = max(i, j); m < p; ++m) acc = fma(xi[m], xj[m], acc);
                             Minv[j * p + i] = acc;
                         }
                         tsync<NW>();
@@ -870,6 +926,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                             for (int r = 0; r < p; ++r) acc = fma(HiAt[r * n + i], Minv[j * p + r], acc);
                             Km[j * n + i] = acc;
                         }
+                        for (int i = tid; i < p; i += T) {              // md = Minv dy
+                            double acc = 0.0;
+                            for (int r = 0; r < p; ++r) acc = fma(Minv[r * p + i], dy[r], acc);
+                            md[i] = acc;
+                        }
+                        tsync<NW>();
+                        // Pm = H^-1 - K HiAt' (in place) and kd = K dy: then cx = Pm n0 + kd, cy = K'n0 - md, which is
+                        // src/densesolver.jl:73-83 (m0 = A H^-1 n0 - dy, cy = M^-1 m0, cx = H^-1 (n0 - A'cy)) in one pass
+                        for (int col = warp; col < n; col += NW)
+                            for (int r = lane; r < n; r += 32) {
+                                double acc = H[col * ldh + r];
+                                for (int q = 0; q < p; ++q) acc = fma(-Km[q * n + r], HiAt[q * n + col], acc);
+                                H[col * ldh + r] = acc;
+                            }
+                        for (int i = tid; i < n; i += T) {
+                            double acc = 0.0;
+                            for (int q = 0; q < p; ++q) acc = fma(Km[q * n + i], dy[q], acc);
+                            kd[i] = acc;
+                        }
                     }
                 }
                 PT2_MARK(P2_EQ);
@@ -877,26 +952,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             }
             // ---- middle of solve_kkt, src/densesolver.jl:66-85: out cx, cy, u = G cx - k2
             tsync<NW>();
-            gemv_rows<NW, true>(X, ldh, n, n, n0, 1, D::split_n(P), lane, warp, [&](int r, double acc) { t1[r] = acc; });
+            gemv_cols_v<NW>(H, ldh, n, n, n0, lane, warp, [&](int c, double acc) { cx[c] = p > 0 ? acc + sc * kd[c] : acc; });
+            if (p > 0)
+                gemv_cols<NW, false>(Km, n, n, p, n0, lane, warp, [&](int c, double acc) { cy[c] = acc - sc * md[c]; });
             tsync<NW>();
-            gemv_cols<NW, true>(X, ldh, n, n, t1, lane, warp, [&](int c, double acc) { tt[c] = acc; });
-            if (p > 0)       // m0 = A H^-1 n0 - dy = B' t1 - dy                    :73-74
-                gemv_cols<NW, false>(Bm, n, n, p, t1, lane, warp, [&](int c, double acc) { m0[c] = acc - sc * dy[c]; });
-            tsync<NW>();
-            if (p > 0) {     // cy = M^-1 m0 (:75);  cx = H^-1 (n0 - A'cy) = t - K m0  (:76-83)
-                for (int i = tid; i < n; i += T) {
-                    double acc = tt[i];
-                    for (int q = 0; q < p; ++q) acc = fma(-Km[q * n + i], m0[q], acc);
-                    cx[i] = acc;
-                }
-                for (int i = tid; i < p; i += T) {
-                    double acc = 0.0;
-                    for (int q = 0; q < p; ++q) acc = fma(Minv[q * p + i], m0[q], acc);
-                    cy[i] = acc;
-                }
-                tsync<NW>();
-            }
-            const double* cxv = p > 0 ? cx : tt;
+            const double* cxv = cx;
             gemv_rows_v<NW>(G, ldg, k, n, cxv, D::split_k(P), lane, warp, [&](int r, double acc) { u[r] = acc - k2[r]; });   // :84-85
             tsync<NW>();
             PT2_MARK(P2_SOLVE);
@@ -1015,8 +1075,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                     const double q = si * fast_rcp(zi), qi = zi * fast_rcp(si), pz = si * zi;
                     fl |= !(q >= 0.0) | !(pz >= 0.0);
                     const double lv = fast_sqrt(pz);
+                    const double iw = fast_sqrt(qi);
                     wb[i] = fast_sqrt(q);
-                    iwb[i] = fast_sqrt(qi);
+                    iwb[i] = iw;
+                    dw[i] = iw * iw;
                     lam[i] = lv;
                     r4[2] = fma(si, zi, r4[2]);
                     r4[3] = fma(lv, lv, r4[3]);
@@ -1049,14 +1111,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                     F2_FOR_E if (L.tail(e)) { const double lv = lam[L.at(e)]; ds[L.at(e)] = -(l0 * lv + l0 * lv); }   // src/vectors.jl:73-75
                     if (L.head()) ds[L.offs] = -(c[CS_LLT] + l0 * l0);                  // :66-69
                 });
-                // Gt = W^-1 G column by column (densesolver :41-43); the region held H and X: pads must be zero again
+                // hc[c] = sqrt(2)/eta G_c'q, q = J wbar: the rank-one part of G'W^-2 G per cone (densesolver :41-43)
                 {
-                    const int padr = kpad - k;
-                    for (int q = tid; q < padr * n; q += T) Gt[(q / padr) * ldt + k + (q % padr)] = 0.0;
-                    for (int col = n + warp; col < npad; col += NW)
-                        for (int r = lane; r < kpad; r += 32) Gt[col * ldt + r] = 0.0;
-                    for (int col = warp; col < n; col += NW)
-                        for (int r = lane; r < kpoc; r += 32) Gt[col * ldt + r] = iwb[r] * G[col * ldg + r];
                     const int spw = 32 / lpc, npairs = n * nsoc;
                     for (int base = warp * spw; base < npairs; base += NW * spw) {
                         const int pr = base + lane / lpc;
@@ -1070,13 +1126,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                         load_tail(L, wb, wv);
                         load_tail(L, gc, gv);
                         const double dl = wdot(wv, gv);
-                        if (valid) {
-                            const double g0 = gc[L.offs], ie = c[CS_IE];
-                            const double cst = -g0 + dl * c[CS_R1W];                    // src/scalings.jl:151
-                            double* oc = Gt + col * ldt;
-                            F2_FOR_E if (L.tail(e)) oc[L.at(e)] = ie * (gv[e] + cst * wv[e]);   // :153-155
-                            if (L.g == 0) oc[L.offs] = ie * (c[CS_W0] * g0 - dl);       // :152
-                        }
+                        if (L.head()) hc[slot * npad + col] = 1.4142135623730951 * c[CS_IE] * (c[CS_W0] * gc[L.offs] - dl);
                     }
                 }
                 sc = 1.0;

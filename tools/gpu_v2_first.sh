@@ -4,5 +4,4 @@ python -m pytest tests -m gpu -x -q > gpurun_out/tests_v2.log 2>&1; echo "pytest
 SOCP_B200_GENERIC_ONLY=1 python -m pytest tests -m gpu -x -q -k "batch or c2 or c3" > gpurun_out/tests_v2_generic.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests_v2_generic.log
 python tools/phase_timing.py C2 --batch 2960 > gpurun_out/phase_c2_v2.txt 2>&1
 python tools/phase_timing.py C3 --batch 17760 > gpurun_out/phase_c3_v2.txt 2>&1
-SOCP_B200_GENERIC_ONLY=1 python tools/phase_timing.py C2 --batch 2960 > gpurun_out/phase_c2_v2_generic.txt 2>&1
-SOCP_B200_GENERIC_ONLY=1 python tools/phase_timing.py C3 --batch 17760 > gpurun_out/phase_c3_v2_generic.txt 2>&1
+python tools/phase_timing.py C2 --batch 148 > gpurun_out/phase_c2_v2_148.txt 2>&1
