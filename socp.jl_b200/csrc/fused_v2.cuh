@@ -54,7 +54,7 @@ struct F2Plan {
     // offsets into the dynamic shared memory, in doubles
     int oG, oR, oX, oA, oAt, oHiAt, oK, oM, oMX, oMinv, oDinv;
     int oc, ob, oh, ox, oy, oz, os, olam, owb, oiwb, ocs, odx, ody, odz, ods, ok0, ok2, ou;
-    int on0, ocx, ocy, okd, omd, odw, ohc, oscr;
+    int on0, ocx, ocy, okd, omd, odw, ohc, oscr, odesc, odescm;
     int total = 0;
 };
 
@@ -78,6 +78,9 @@ __host__ __device__ constexpr int f2_split(int units, int nw) {   // lanes per o
 __host__ __device__ constexpr int f2_xld(int nbl, int cb) { return (nbl - cb) * 8 + 4; }
 __host__ __device__ constexpr int f2_xbase(int nbl, int cb) { return 8 * cb * (nbl * 8 + 4) - 32 * cb * (cb - 1); }
 __host__ __device__ constexpr int f2_xsize(int nbl) { return f2_xbase(nbl, nbl); }
+// number of trailing-update tiles of block column b, and where its descriptors start (see f2_trail_desc)
+__host__ __device__ constexpr int f2_ntrail(int nbl, int b) { return (nbl * (nbl + 1) - (b + 1) * (b + 2)) / 2; }
+__host__ __device__ constexpr int f2_trail_base(int nbl, int b) { return b * (nbl * (nbl + 1) / 2) - b * (b + 1) * (b + 2) / 6; }
 __host__ __device__ constexpr int f2_lpc(int maxdim) {   // lanes per second-order cone: 4 elements per lane
     int l = 1;
     while (l * 4 < maxdim) l <<= 1;
@@ -131,6 +134,7 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     P.odz = take(k); P.ods = take(k); P.ok0 = take(k); P.ok2 = take(k); P.ou = take(k);
     P.ocs = take(F2_CS * std::max(P.nsoc, 1));
     P.oscr = take(2 * 8 * 8);
+    P.odesc = take(f2_trail_base(P.nb, P.nb)); P.odescm = take(p ? f2_trail_base(P.pb, P.pb) : 0);   // uint2 = 8 bytes each
     P.total = at;
     P.smem = (size_t)at * sizeof(double);
     int dev_smem = 0, sms = 148;
@@ -324,8 +328,19 @@ __device__ __forceinline__ void f2_tile(int t, int& ti, int& tj) {
 // G: kpad x (n+1), ld ldg (pad rows and column n zero).  mma.sync m8n8k4 f64 from shared memory; accumulators in
 // registers.  The caller syncs afterwards.
 template <int NW, int MAXT>
+__device__ __forceinline__ void f2_my_tiles(int nb, int warp, int (&tl)[MAXT]) {
+    const int ntl = nb * (nb + 1) / 2;
+#pragma unroll
+    for (int q = 0; q < MAXT; ++q) {
+        int ti, tj;
+        f2_tile(min(warp + q * NW, ntl - 1), ti, tj);
+        tl[q] = ti | (tj << 8);
+    }
+}
+template <int NW, int MAXT>
 __device__ __forceinline__ void f2_syrk_w(const double* G, int ldg, int kpad, int n, int nb, const double* dw,
-                                          const double* hc, int nsoc, int npad, double* H, int ldh, int lane, int warp) {
+                                          const double* hc, int nsoc, int npad, double* H, int ldh, const int (&tl)[MAXT],
+                                          int lane, int warp) {
     const int ntl = nb * (nb + 1) / 2;
     const int fr = lane >> 2, fk = lane & 3;
     const double* pa[MAXT];
@@ -334,8 +349,7 @@ __device__ __forceinline__ void f2_syrk_w(const double* G, int ldg, int kpad, in
     double acc[MAXT][2];
 #pragma unroll
     for (int q = 0; q < MAXT; ++q) {
-        const int t = min(warp + q * NW, ntl - 1);
-        f2_tile(t, ti[q], tj[q]);
+        ti[q] = tl[q] & 255; tj[q] = tl[q] >> 8;
         pa[q] = G + min(ti[q] * 8 + fr, n) * ldg + fk;      // column n is the zero column
         pb[q] = G + min(tj[q] * 8 + fr, n) * ldg + fk;
         acc[q][0] = acc[q][1] = 0.0;
@@ -367,15 +381,15 @@ __device__ __forceinline__ void f2_syrk_w(const double* G, int ldg, int kpad, in
 // the diagonal is zero): H^-1 = L^-T L^-1.  Accumulates in registers, team barrier, then
 // stores, so Out may alias anything but X.
 template <int NW, int MAXT>
-__device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* Out, int lane, int warp) {
+__device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* Out, const int (&tl)[MAXT], int lane,
+                                       int warp) {
     const int ntl = nb * (nb + 1) / 2;
     const int fr = lane >> 2, fk = lane & 3;
     int ti[MAXT], tj[MAXT];
     double acc[MAXT][2];
 #pragma unroll
     for (int q = 0; q < MAXT; ++q) {
-        const int t = min(warp + q * NW, ntl - 1);
-        f2_tile(t, ti[q], tj[q]);
+        ti[q] = tl[q] & 255; tj[q] = tl[q] >> 8;
         acc[q][0] = acc[q][1] = 0.0;
         if (warp + q * NW < ntl) {
             // rows kk of column block cb live at offset kk - 8*cb of that block
@@ -437,13 +451,46 @@ __device__ __forceinline__ int f2_diag_factor(const double* T, int ld, int lane,
     return ok;
 }
 
-// H: nbl x nbl lower tiles (column-major, ld), unit pad diagonal.  On exit X (same shape, zero-initialised by
-// the caller in its lower tiles) holds L^-1; H is destroyed.  Dinv: 2 x (8 x 12) scratch, zero above the diagonal.
-// *fail is set (and 0 returned) on a non-positive pivot: cholesky!'s PosDefException, src/densesolver.jl:47,51.
+// Trailing-update tile descriptors of the blocked factorisation: for block column b, tile (i, j), i > b, j <= i
+// (flat index over rows i = b+1.. with i+1 tiles each), packed offsets (in doubles, relative to H) of the three
+// operands -- the same table serves every factorisation of the kernel's lifetime.
+//   x: aoff | boff << 16      a = H[aoff + (kk+fk)*ld + fr]        (L_ib, negated)
+//   y: coff | cl << 16 | flags << 24
+//        flags bit 0: b operand in X form  b = H[boff + fr*cl + kk + fk]   (else H form, like a)
+//        flags bit 1: destination starts from zero (X(i,b) = -L_ib X(b,b))
+//      C[fr][2fk+e] = H[coff + (2fk+e)*cl + fr]
+__device__ __forceinline__ uint2 f2_trail_desc(int nbl, int ld, int xoff, int b, int tf) {
+    int i = b + 1, j = tf;
+    while (j > i) { j -= i + 1; ++i; }
+    const int b0 = b * 8, i0 = i * 8, j0 = j * 8;
+    const int aoff = b0 * ld + i0;
+    int boff, coff, cl, flags;
+    if (j > b) {
+        boff = b0 * ld + j0; coff = j0 * ld + i0; cl = ld; flags = 0;
+    } else {
+        const int xj = xoff + f2_xbase(nbl, j);
+        cl = f2_xld(nbl, j);
+        boff = xj + (b0 - j0); coff = xj + (i0 - j0); flags = 1 | (j == b ? 2 : 0);
+    }
+    return make_uint2((unsigned)aoff | ((unsigned)boff << 16), (unsigned)coff | ((unsigned)cl << 16) | ((unsigned)flags << 24));
+}
+// fills desc[0 .. f2_trail_base(nbl, nbl)) -- call once, by the whole team, before the first factorisation
+__device__ __forceinline__ void f2_build_trail(uint2* desc, int nbl, int ld, int xoff, int tid, int nthreads) {
+    for (int b = 0; b < nbl; ++b) {
+        const int nt = f2_ntrail(nbl, b), base = f2_trail_base(nbl, b);
+        for (int t = tid; t < nt; t += nthreads) desc[base + t] = f2_trail_desc(nbl, ld, xoff, b, t);
+    }
+}
+
+// H: nbl x nbl lower tiles (column-major, ld), unit pad diagonal.  On exit X (trapezoid storage, zero-initialised by
+// the caller) holds L^-1; H is destroyed.  Dinv: 2 x (8 x 12) scratch, zero above the diagonal.  desc: the table of
+// f2_build_trail for (nbl, ld, X - H).  *fail is set (and 0 returned) on a non-positive pivot: cholesky!'s
+// PosDefException, src/densesolver.jl:47,51.
 template <int NW>
-__device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, int nbl, int ld, int* fail,
-                                           int lane, int warp) {
+__device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, const uint2* desc, int nbl, int ld,
+                                           int* fail, int lane, int warp) {
     const int fr = lane >> 2, fk = lane & 3;
+    const int la = fk * ld + fr;
     for (int b = 0; b < nbl; ++b) {
         const int b0 = b * 8;
         double* Db = Dinv + (b & 1) * 96;
@@ -466,11 +513,10 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
         // ---- panel: H(i,b) <- H(i,b) Dinv_b'  (i > b);   X(b,c) <- Dinv_b X(b,c)  (c < b)
         for (int t = warp; t < nbl - 1; t += NW) {
             double c0 = 0.0, c1 = 0.0;
+            const double d0 = Db[fr * 12 + fk], d1 = Db[fr * 12 + 4 + fk];
             if (t < nbl - 1 - b) {
-                const int i0 = (b + 1 + t) * 8;
-                double* T = H + b0 * ld + i0;
-                const double a0 = T[fk * ld + fr], a1 = T[(4 + fk) * ld + fr];
-                const double d0 = Db[fr * 12 + fk], d1 = Db[fr * 12 + 4 + fk];
+                double* T = H + b0 * ld + (b + 1 + t) * 8;
+                const double a0 = T[la], a1 = T[la + 4 * ld];
                 dmma884(c0, c1, a0, d0);
                 dmma884(c0, c1, a1, d1);
                 T[(2 * fk) * ld + fr] = c0;
@@ -478,7 +524,6 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
             } else {
                 const int cb = t - (nbl - 1 - b), xl = f2_xld(nbl, cb);
                 double* T = X + f2_xbase(nbl, cb) + (b - cb) * 8;
-                const double d0 = Db[fr * 12 + fk], d1 = Db[fr * 12 + 4 + fk];
                 const double x0 = T[fr * xl + fk], x1 = T[fr * xl + 4 + fk];
                 dmma884(c0, c1, d0, x0);
                 dmma884(c0, c1, d1, x1);
@@ -486,12 +531,18 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
                 T[(2 * fk + 1) * xl + fr] = c1;
             }
         }
-        tsync<NW>();                                   // (2) panel visible
+        // (2) panel visible.  Warp 0 only needs the panel tile it wrote itself (row b+1) for the one trailing tile it
+        // owns, so it merely arrives (named barrier 1) and runs ahead into the next diagonal factorisation.
+        if (NW > 1) {
+            if (warp == 0) { asm volatile("bar.arrive 1, %0;" ::"n"(NW * 32) : "memory"); __syncwarp(); }
+            else asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+        } else __syncwarp();
         // ---- trailing update: rows i > b, tiles j = 0..i:  j > b: H(i,j) -= L_ib L_jb';  j <= b: X(i,j) -= L_ib X(b,j)
-        // Warp 0 takes the next diagonal tile only (then goes on to factor it); the others share the rest.
-        // Flat tile index over rows i = b+1.. (row i has i+1 tiles, j = 0..i); the next diagonal tile is index b+1.
+        // Warp 0 takes the next diagonal tile only (flat index b+1; it then goes on to factor it); the others share
+        // the rest.
         {
-            const int ntile = (nbl * (nbl + 1) - (b + 1) * (b + 2)) / 2;
+            const int ntile = f2_ntrail(nbl, b);
+            const uint2* dtab = desc + f2_trail_base(nbl, b);
             const int stride = (NW > 1) ? NW - 1 : 1;
             for (int t = (NW > 1) ? warp - 1 : 0;; t += stride) {
                 int tf;
@@ -500,34 +551,18 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, i
                     else { tf = t + (t >= b + 1); }
                 } else tf = t;
                 if (tf >= ntile) break;
-                int i = b + 1, j = tf;
-                while (j > i) { j -= i + 1; ++i; }
-                const int i0 = i * 8;
-                const int j0 = j * 8;
-                const double* Lp = H + b0 * ld + i0;
-                const double a0 = -Lp[fk * ld + fr], a1 = -Lp[(4 + fk) * ld + fr];
-                double c0, c1, q0, q1;
-                double* C;
-                int cl;                                  // leading dimension of the destination tile
-                if (j > b) {
-                    C = H + j0 * ld + i0;
-                    cl = ld;
-                    const double* Lj = H + b0 * ld + j0;
-                    q0 = Lj[fk * ld + fr]; q1 = Lj[(4 + fk) * ld + fr];
-                    c0 = C[(2 * fk) * ld + fr]; c1 = C[(2 * fk + 1) * ld + fr];
-                } else {
-                    cl = f2_xld(nbl, j);
-                    const double* Xj = X + f2_xbase(nbl, j);        // column block j, rows from j0 on
-                    C = const_cast<double*>(Xj) + (i0 - j0);
-                    const double* Xb = Xj + (b0 - j0);
-                    q0 = Xb[fr * cl + fk]; q1 = Xb[fr * cl + 4 + fk];
-                    if (j == b) { c0 = 0.0; c1 = 0.0; }
-                    else { c0 = C[(2 * fk) * cl + fr]; c1 = C[(2 * fk + 1) * cl + fr]; }
-                }
+                const uint2 d = dtab[tf];
+                const int aoff = d.x & 0xffff, boff = d.x >> 16, coff = d.y & 0xffff, cl = (d.y >> 16) & 0xff;
+                const bool xform = (d.y >> 24) & 1, zero = (d.y >> 25) & 1;
+                const double a0 = -H[aoff + la], a1 = -H[aoff + la + 4 * ld];
+                const int lb = xform ? fr * cl + fk : la, sb = xform ? 4 : 4 * ld;
+                const double q0 = H[boff + lb], q1 = H[boff + lb + sb];
+                double* C = H + coff + (2 * fk) * cl + fr;
+                double c0 = zero ? 0.0 : C[0], c1 = zero ? 0.0 : C[cl];
                 dmma884(c0, c1, a0, q0);
                 dmma884(c0, c1, a1, q1);
-                C[(2 * fk) * cl + fr] = c0;
-                C[(2 * fk + 1) * cl + fr] = c1;
+                C[0] = c0;
+                C[cl] = c1;
             }
         }
     }
@@ -674,6 +709,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
 
     for (int q = tid; q < P.total; q += T) sm[q] = 0.0;
     tsync<NW>();
+    // tables that serve every factorisation of this kernel: trailing-update tile descriptors, SYRK tile lists
+    uint2* desc = reinterpret_cast<uint2*>(sm + P.odesc);
+    uint2* descm = reinterpret_cast<uint2*>(sm + P.odescm);
+    f2_build_trail(desc, nb, ldh, ldh * npad, tid, T);
+    if (p > 0) f2_build_trail(descm, pb, ldm, P.oMX - P.oM, tid, T);
+    int tl[MAXT];
+    f2_my_tiles<NW, MAXT>(nb, warp, tl);
     for (int i = p + tid; i < ppad; i += T) Mm[i * ldm + i] = 1.0;       // unit pad diagonal of M (never overwritten)
 
     // ------------------------------------------------------------------ building blocks (lambdas over the work set)
@@ -891,13 +933,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             gemv_cols_v<NW>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + sc * dx[c]; });
             if (phase != 2) {
                 // ---- KKT factor, src/densesolver.jl:41-52
-                f2_syrk_w<NW, MAXT>(G, ldg, kpad, n, nb, dw, hc, nsoc, npad, H, ldh, lane, warp);   // :42-43
+                f2_syrk_w<NW, MAXT>(G, ldg, kpad, n, nb, dw, hc, nsoc, npad, H, ldh, tl, lane, warp);   // :42-43
                 for (int q = tid; q < f2_xsize(nb); q += T) X[q] = 0.0;
                 if (tid == 0) s_fail = 0;
                 tsync<NW>();
                 PT2_MARK(P2_SYRK);
-                int ok = f2_chol_inv<NW>(H, X, Dinv, nb, ldh, &s_fail, lane, warp);          // :47
-                if (ok) f2_xtx<NW, MAXT>(X, ldh, nb, H, lane, warp);                         // :48  Li = H^-1 (explicit)
+                int ok = f2_chol_inv<NW>(H, X, Dinv, desc, nb, ldh, &s_fail, lane, warp);          // :47
+                if (ok) f2_xtx<NW, MAXT>(X, ldh, nb, H, tl, lane, warp);                         // :48  Li = H^-1 (explicit)
                 tsync<NW>();
                 PT2_MARK(P2_CHOL);
                 if (ok && p > 0) {
@@ -909,7 +951,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                         gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, D::split_p(P), lane, warp,
                                              [&](int r, double acc) { Mm[j * ldm + r] = acc; });
                     tsync<NW>();
-                    ok = f2_chol_inv<NW>(Mm, MX, Dinv, pb, ldm, &s_fail, lane, warp);        // :51
+                    ok = f2_chol_inv<NW>(Mm, MX, Dinv, descm, pb, ldm, &s_fail, lane, warp);        // :51
                     if (ok) {
                         for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
                             const int i = q % p, j = q / p;
