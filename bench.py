@@ -215,7 +215,9 @@ def main():
     n, p, k, batch_cfg, desc = workload_meta(args.config)
     B = args.batch or batch_cfg
     # every rank generates its own shard: problems [rank*B, (rank+1)*B) of the seeded sequence
-    prob = gen.make_config(args.config, batch=B, first=rank * B)
+    from socp_b200 import sharding
+    first, _last = sharding.weak_shard(B, rank)
+    prob = gen.make_config(args.config, batch=B, first=first)
 
     # pinned host staging for the e2e leg (inputs) and outputs
     def pin(a):
@@ -254,6 +256,12 @@ def main():
         h.check(lib.socp_b200_get_results(h.ptr, dptr(ox), None, None, None, iptr(ostatus), iptr(oiters), dptr(opobj),
                                           dptr(odobj)), "get_results")
 
+    def solve_host():
+        # the reference-facing call: Problem(c,A,b,G,h,cones) + solve_socp(prob, ss) from HOST data to HOST results
+        h.check(lib.socp_b200_solve_host(h.ptr, C.byref(prm), dptr(hc), dptr(hA), dptr(hb), dptr(hG), dptr(hh), sing_ptr,
+                                         flags, dptr(ox), None, None, None, iptr(ostatus), iptr(oiters), dptr(opobj),
+                                         dptr(odobj)), "solve_host")
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -289,15 +297,15 @@ def main():
 
     # ---- end-to-end leg (`e2e`): H2D of the step's inputs + solve + D2H of its results, every step
     for _ in range(2):
-        upload(); solve_dev(); download()
+        solve_host()
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        upload()
-        solve_dev()
-        download()
+        solve_host()
     barrier()
     wall_e2e = time.perf_counter() - t1
+    status_e2e = ostatus.numpy().copy()
+    assert np.array_equal(status_e2e, status), "e2e leg and device-resident leg disagree on status"
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -340,8 +348,8 @@ def main():
                        "timing": "CUDA events on the library's launch stream, summed over the timed steps, max over ranks",
                        "wall_s_device_leg": t_wall_dev},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
-                    "how": "pinned host buffers -> socp_b200_set_data -> socp_b200_solve_dev -> socp_b200_get_results, wall clock "
-                           "between barriers, max over ranks"},
+                    "how": "socp_b200_solve_host: pinned host buffers -> chunked H2D / solve / D2H (overlapped on three "
+                           "streams) -> pinned host results; wall clock between barriers, max over ranks"},
             "gpu_launches": int(total_launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,

@@ -126,6 +126,19 @@ int  socp_b200_solve(socp_handle* h, const socp_params* params,
                      double* x, double* y, double* z, double* s,
                      int32_t* status, int32_t* iters, double* pobj, double* dobj);
 
+/* Problem(c, A, b, G, h, cones) followed by solve_socp(prob, ss) -- reference
+ * src/Socp.jl:40-59 + src/solver.jl:40-152 -- as ONE call from host data to host
+ * results: what a caller of the reference's solve_socp pays end to end.  Same
+ * arguments as _set_data followed by _solve.  On the fused path (sing given, no
+ * sing problem) the batch is cut into chunks whose upload, solve and download
+ * overlap; otherwise it is exactly _set_data + _solve.  Pinned host buffers make
+ * the copies asynchronous; pageable ones work but serialise. */
+int  socp_b200_solve_host(socp_handle* h, const socp_params* params,
+                          const double* c, const double* A, const double* b, const double* G,
+                          const double* hvec, const uint8_t* sing, int32_t flags,
+                          double* x, double* y, double* z, double* s,
+                          int32_t* status, int32_t* iters, double* pobj, double* dobj);
+
 /* Same, but results stay on the device (inputs already resident after
  * set_data): the region bench.py times for `value`.  Fetch with _get_results. */
 int  socp_b200_solve_dev(socp_handle* h, const socp_params* params);

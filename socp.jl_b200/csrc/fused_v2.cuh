@@ -631,7 +631,7 @@ struct F2Args {
     Ws g;                 // global arrays of the shard
     F2Plan P;
     LoopParams prm;
-    int batch;
+    int first, batch;     // this launch solves problems [first, first + batch) of the shard
     int* counter;
 };
 
@@ -897,9 +897,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
     for (;;) {
         if (tid == 0) s_prob = atomicAdd(a.counter, 1);
         tsync<NW>();
-        const int b = s_prob;
+        const int b = s_prob + a.first;
         tsync<NW>();
-        if (b >= a.batch) break;
+        if (b >= a.first + a.batch) break;
         PT2_INIT();
 
         // ---- load the problem (global -> shared)
@@ -1211,8 +1211,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             }
             team_reduce<NW, 2, 0>(r2, fl, scr + (scr_par ^= 1) * 64, lane, warp);
             if (tid == 0) {
-                a.g.sc[b].pobj = r2[0];
-                a.g.sc[b].dobj = r2[1];
+                a.g.pobj[b] = r2[0];
+                a.g.dobj[b] = r2[1];
                 a.g.status[b] = status;
                 a.g.iters[b] = iters;
                 a.g.active[b] = 0;
@@ -1234,13 +1234,15 @@ inline void fused2_launch(const F2Plan& plan, const F2Args& args, int grid, cuda
     k_fused2<NW, MAXT, MINB, D><<<grid, NW * 32, plan.smem, stream>>>(args);
 }
 
-inline void solve_fused2(F2Plan& plan, const Ws& g, int batch, int max_iter, double tol, double step_damp,
+// Solves problems [first, first + batch) of the shard.
+inline void solve_fused2(F2Plan& plan, const Ws& g, int first, int batch, int max_iter, double tol, double step_damp,
                          double init_eps, cudaStream_t stream, bool allow_static = true) {
     cudaMemsetAsync(plan.d_counter, 0, sizeof(int), stream);
     F2Args args;
     args.g = g;
     args.P = plan;
     args.prm = LoopParams{max_iter, tol, step_damp, init_eps};
+    args.first = first;
     args.batch = batch;
     args.counter = plan.d_counter;
     const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);

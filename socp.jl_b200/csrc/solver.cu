@@ -4,7 +4,6 @@
 #include "../../include/socp_b200.h"
 #include "linalg.cuh"
 #include "tiled_kernels.cuh"
-#include "fused_small.cuh"
 #include "fused_v2.cuh"
 
 #include <algorithm>
@@ -50,6 +49,8 @@ struct Shard {
     int64_t first = 0;     // first problem of the shard in the caller's batch
     int batch = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;     // H2D / D2H legs of the pipelined one-shot solve
+    std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> allocs;
     Ws w{};
@@ -65,7 +66,6 @@ struct Shard {
     bool sharedA = false, sharedG = false;
     int threads = 256;     // CTA size of the per-problem cone kernels
     socp_timings tim{};
-    FusedPlan fused{};
     F2Plan fused2{};
 
     template <class T>
@@ -84,6 +84,9 @@ struct Shard {
         if (h_nactive) cudaFreeHost(h_nactive);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : pipe_ev) cudaEventDestroy(e);
+        if (up_stream) cudaStreamDestroy(up_stream);
+        if (down_stream) cudaStreamDestroy(down_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -333,6 +336,7 @@ void build_shard(socp_handle* h, Shard& sh) {
     w.u = sh.alloc<double>((size_t)B * k);
     w.kt2 = sh.alloc<double>((size_t)B * k); w.kt3 = sh.alloc<double>((size_t)B * k);
     w.sc = sh.alloc<ProbScalars>(B);
+    w.pobj = sh.alloc<double>(B); w.dobj = sh.alloc<double>(B);
     w.status = sh.alloc<int>(B); w.iters = sh.alloc<int>(B);
     w.active = sh.alloc<int>(B); w.fail = sh.alloc<int>(B);
     w.nactive = sh.alloc<int>(4096);
@@ -340,10 +344,8 @@ void build_shard(socp_handle* h, Shard& sh) {
     // tiled-path factor workspaces are allocated lazily (ensure_tiled): the fused
     // path does not need them and they dominate the footprint
     sh.threads = std::min(256, std::max(32, 32 * nc));
-    fused_plan(sh.fused, n, p, k, h->wkind, h->woffs, h->wdim, sh.device);
-    sh.fused.d_counter = sh.alloc<int>(1);
     f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
-    sh.fused2.d_counter = sh.fused.d_counter;
+    sh.fused2.d_counter = sh.alloc<int>(1);
     CK(cudaStreamSynchronize(sh.stream));
 }
 
@@ -447,14 +449,8 @@ void need(bool cond, int code, const char* msg) {
     if (!cond) throw UsageErr{code, msg};
 }
 
-constexpr int PATH_FUSED_V1 = 3;   // first-generation fused kernel (A/B comparisons only; not in the public header)
-
 int choose_path(const Shard& sh, const socp_params& prm) {
     if (prm.path == SOCP_PATH_TILED) return SOCP_PATH_TILED;
-    if (prm.path == PATH_FUSED_V1) {
-        need(sh.fused.fits && !sh.any_sing, SOCP_ERR_SIZE, "fused v1 does not fit");
-        return PATH_FUSED_V1;
-    }
     const bool ok = sh.fused2.fits && !sh.any_sing;
     if (prm.path == SOCP_PATH_FUSED) {
         need(ok, SOCP_ERR_SIZE, "the fused shared-memory kernel needs a layout that fits and no sing problems");
@@ -468,12 +464,9 @@ void run_solve(Shard& sh, const socp_params& prm) {
     sh.launches = 0;
     CK(cudaEventRecord(sh.ev[0], sh.stream));
     const int path = choose_path(sh, prm);
-    if (path == SOCP_PATH_FUSED || path == PATH_FUSED_V1) {
-        if (path == SOCP_PATH_FUSED)
-            solve_fused2(sh.fused2, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream,
-                         /*allow_static=*/getenv("SOCP_B200_GENERIC_ONLY") == nullptr);
-        else
-            solve_fused(sh.fused, sh.w, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream);
+    if (path == SOCP_PATH_FUSED) {
+        solve_fused2(sh.fused2, sh.w, 0, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream,
+                     /*allow_static=*/getenv("SOCP_B200_GENERIC_ONLY") == nullptr);
         CK(cudaGetLastError());
         sh.launches += 1;
         sh.tim.path_used = SOCP_PATH_FUSED;
@@ -502,20 +495,102 @@ void fetch_results(socp_handle* h, Shard& sh, double* x, double* y, double* z, d
     if (s) d2h(sh, s + f * k, sh.w.s, sizeof(double) * B * k);
     if (status) d2h(sh, status + f, sh.w.status, sizeof(int) * B);
     if (iters) d2h(sh, iters + f, sh.w.iters, sizeof(int) * B);
-    std::vector<ProbScalars> sc;
-    if (pobj || dobj) {
-        sc.resize(B);
-        d2h(sh, sc.data(), sh.w.sc, sizeof(ProbScalars) * B);
-    }
+    if (pobj) d2h(sh, pobj + f, sh.w.pobj, sizeof(double) * B);
+    if (dobj) d2h(sh, dobj + f, sh.w.dobj, sizeof(double) * B);
     CK(cudaEventRecord(sh.ev[3], sh.stream));
     CK(cudaStreamSynchronize(sh.stream));
-    for (int b = 0; b < (int)sc.size(); ++b) {
-        if (pobj) pobj[f + b] = sc[b].pobj;
-        if (dobj) dobj[f + b] = sc[b].dobj;
-    }
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, sh.ev[2], sh.ev[3]));
     sh.tim.d2h_ms = ms;
+}
+
+
+// Problem(c, A, b, G, h, cones) + solve_socp(prob, ss) in one pass over host data (fused path only): the batch is
+// cut into chunks; chunk i+1 uploads (copy engine) while chunk i solves and chunk i-1 downloads.
+bool can_pipeline(const Shard& sh, const socp_params& prm, const uint8_t* sing, int64_t first) {
+    if (!sh.fused2.fits || prm.path == SOCP_PATH_TILED || !sing) return false;
+    for (int64_t q = 0; q < sh.batch; ++q)
+        if (sing[first + q]) return false;
+    return true;
+}
+
+void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const double* c, const double* A, const double* b,
+                   const double* G, const double* hvec, const uint8_t* sing, int flags, double* x, double* y, double* z,
+                   double* s, int32_t* status, int32_t* iters, double* pobj, double* dobj) {
+    const int n = h->n, p = h->p, k = h->k, B = sh.batch;
+    const int64_t f = sh.first;
+    if (!sh.up_stream) {
+        CK(cudaStreamCreateWithFlags(&sh.up_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&sh.down_stream, cudaStreamNonBlocking));
+    }
+    sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
+    sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
+    sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
+    sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
+    sh.any_sing = false;
+    // chunks of at least 8 waves of resident CTAs, at most 8 chunks
+    const int slots = sh.fused2.num_sms * sh.fused2.ctas_per_sm;
+    int nchunk = std::max(1, std::min(8, B / std::max(1, 8 * slots)));
+    const int per = (B + nchunk - 1) / nchunk;
+    nchunk = (B + per - 1) / per;
+    while ((int)sh.pipe_ev.size() < 2 * nchunk) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        sh.pipe_ev.push_back(e);
+    }
+    const bool allow_static = getenv("SOCP_B200_GENERIC_ONLY") == nullptr;
+    auto up = [&](void* dst, const void* src, size_t bytes) {
+        if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sh.up_stream));
+    };
+    auto down = [&](void* dst, const void* src, size_t bytes) {
+        if (bytes && dst) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sh.down_stream));
+    };
+    CK(cudaEventRecord(sh.ev[0], sh.stream));
+    CK(cudaStreamWaitEvent(sh.up_stream, sh.ev[0], 0));
+    sh.launches = 0;
+    for (int ci = 0; ci < nchunk; ++ci) {
+        const int lo = ci * per, cb = std::min(per, B - lo);
+        const int64_t g0 = f + lo;
+        up(sh.d_c + (size_t)lo * n, c + g0 * n, sizeof(double) * cb * n);
+        up(sh.d_h + (size_t)lo * k, hvec + g0 * k, sizeof(double) * cb * k);
+        if (p > 0) {
+            up(sh.d_b + (size_t)lo * p, b + g0 * p, sizeof(double) * cb * p);
+            if (sh.sharedA) { if (ci == 0) up(sh.d_A, A, sizeof(double) * p * n); }
+            else up(sh.d_A + (size_t)lo * p * n, A + g0 * p * n, sizeof(double) * cb * p * n);
+        }
+        if (sh.sharedG) { if (ci == 0) up(sh.d_G, G, sizeof(double) * k * n); }
+        else up(sh.d_G + (size_t)lo * k * n, G + g0 * (int64_t)k * n, sizeof(double) * cb * k * n);
+        up(sh.d_sing + lo, sing + g0, cb);
+        CK(cudaEventRecord(sh.pipe_ev[2 * ci], sh.up_stream));
+        CK(cudaStreamWaitEvent(sh.stream, sh.pipe_ev[2 * ci], 0));
+        solve_fused2(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream, allow_static);
+        CK(cudaGetLastError());
+        sh.launches += 1;
+        CK(cudaEventRecord(sh.pipe_ev[2 * ci + 1], sh.stream));
+        CK(cudaStreamWaitEvent(sh.down_stream, sh.pipe_ev[2 * ci + 1], 0));
+        if (x) down(x + g0 * n, sh.w.x + (size_t)lo * n, sizeof(double) * cb * n);
+        if (y) down(y + g0 * p, sh.w.y + (size_t)lo * p, sizeof(double) * cb * p);
+        if (z) down(z + g0 * k, sh.w.z + (size_t)lo * k, sizeof(double) * cb * k);
+        if (s) down(s + g0 * k, sh.w.s + (size_t)lo * k, sizeof(double) * cb * k);
+        if (status) down(status + g0, sh.w.status + lo, sizeof(int) * cb);
+        if (iters) down(iters + g0, sh.w.iters + lo, sizeof(int) * cb);
+        if (pobj) down(pobj + g0, sh.w.pobj + lo, sizeof(double) * cb);
+        if (dobj) down(dobj + g0, sh.w.dobj + lo, sizeof(double) * cb);
+    }
+    CK(cudaEventRecord(sh.ev[1], sh.stream));
+    CK(cudaStreamSynchronize(sh.up_stream));
+    CK(cudaStreamSynchronize(sh.stream));
+    CK(cudaStreamSynchronize(sh.down_stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
+    sh.tim.h2d_ms = 0;
+    sh.tim.solve_ms = ms;          // upload + solve, overlapped
+    sh.tim.d2h_ms = 0;
+    sh.tim.kernel_launches = sh.launches;
+    sh.tim.path_used = SOCP_PATH_FUSED;
+    sh.tim.iterations_max = -1;
+    sh.have_data = true;
+    sh.have_scaling = sh.have_factor = false;
 }
 
 }  // namespace
@@ -651,10 +726,14 @@ int socp_b200_set_data(socp_handle* h, const double* c, const double* A, const d
             CK(cudaEventRecord(sh.ev[1], sh.stream));
             // sing / A'A are only needed when there are equalities or the caller
             // asks for the test; with p == 0 and sing given the tiled buffers stay unallocated
-            if (sing && p == 0) {
-                std::vector<uint8_t> hs(sing + f, sing + f + B);
-                sh.any_sing = false;
-                for (uint8_t v : hs) sh.any_sing |= (v != 0);
+            bool given_none = false;
+            if (sing) {
+                given_none = true;
+                for (int64_t q = 0; q < B; ++q) given_none &= (sing[f + q] == 0);
+            }
+            if (given_none || (sing && p == 0)) {
+                // A'A (src/densesolver.jl:32) is only used by `sing` problems: nothing to prepare
+                sh.any_sing = !given_none;
                 CK(cudaStreamSynchronize(sh.stream));
             } else {
                 prepare_problem(sh, sing != nullptr);
@@ -700,6 +779,30 @@ int socp_b200_solve(socp_handle* h, const socp_params* params, double* x, double
             fetch_results(h, sh, x, y, z, s, status, iters, pobj, dobj);
         });
     });
+}
+
+int socp_b200_solve_host(socp_handle* h, const socp_params* params, const double* c, const double* A, const double* b,
+                         const double* G, const double* hvec, const uint8_t* sing, int32_t flags, double* x, double* y,
+                         double* z, double* s, int32_t* status, int32_t* iters, double* pobj, double* dobj) {
+    if (!h) return SOCP_ERR_NULL;
+    socp_params prm;
+    socp_b200_default_params(&prm);
+    if (params) prm = *params;
+    bool pipelined = true;
+    int rc = guarded(h, [&]() {
+        need(c && G && hvec, SOCP_ERR_NULL, "c, G, h must not be null");
+        need(h->p == 0 || (A && b), SOCP_ERR_NULL, "A, b must not be null when p > 0");
+        need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
+        for (auto& sh : h->shards) pipelined &= can_pipeline(sh, prm, sing, sh.first);
+        if (!pipelined) return;
+        for_each_shard(h, [&](Shard& sh) {
+            run_pipelined(h, sh, prm, c, A, b, G, hvec, sing, flags, x, y, z, s, status, iters, pobj, dobj);
+        });
+    });
+    if (rc != 0 || pipelined) return rc;
+    rc = socp_b200_set_data(h, c, A, b, G, hvec, sing, flags);
+    if (rc != 0) return rc;
+    return socp_b200_solve(h, &prm, x, y, z, s, status, iters, pobj, dobj);
 }
 
 int socp_b200_get_sing(socp_handle* h, uint8_t* sing) {
@@ -896,14 +999,6 @@ int socp_b200_get_H(socp_handle* h, double* out) {
 
 #ifdef SOCP_PHASE_TIMING
 // profiling build only (not declared in include/socp_b200.h)
-int socp_b200_debug_phase_clocks(unsigned long long* out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, socp::g_phase_clk, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(socp::g_phase_clk, z, sizeof z);
-    }
-    return 0;
-}
 int socp_b200_debug_phase_clocks2(unsigned long long* out16, int reset) {
     if (out16) cudaMemcpyFromSymbol(out16, socp::g_phase_clk2, sizeof(unsigned long long) * 16);
     if (reset) {

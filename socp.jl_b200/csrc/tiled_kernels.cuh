@@ -33,6 +33,7 @@ struct Ws {
     // factor workspaces
     double *Gt, *H, *HiAt, *M, *AA, *Ap;
     ProbScalars* sc;
+    double *pobj, *dobj;   // [batch] objectives of the returned iterate
     int *status, *iters, *active, *fail;
     int* nactive;          // [max_iter+2] counters
 };
@@ -455,7 +456,7 @@ __global__ void k_finalize(Ws w, int phase) {
     for (int i = threadIdx.x; i < L.k; i += blockDim.x) d = fma(-h[i], z[i], d);
     po = block_sum(po, scratch);
     d = block_sum(d, scratch);
-    if (threadIdx.x == 0) { w.sc[b].pobj = po; w.sc[b].dobj = d; }
+    if (threadIdx.x == 0) { w.sc[b].pobj = po; w.sc[b].dobj = d; w.pobj[b] = po; w.dobj[b] = d; }
 }
 
 // reset of the per-problem state at the start of a solve

@@ -39,6 +39,9 @@ SYMBOLS = {
     "socp_b200_set_data": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p, C.c_int32]),
     "socp_b200_solve": (C.c_int, [H, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_int32_p, c_int32_p, c_double_p, c_double_p]),
+    "socp_b200_solve_host": (C.c_int, [H, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                       c_uint8_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
+                                       c_int32_p, c_int32_p, c_double_p, c_double_p]),
     "socp_b200_solve_dev": (C.c_int, [H, C.POINTER(Params)]),
     "socp_b200_get_results": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p,
                                         c_int32_p, c_int32_p, c_double_p, c_double_p]),

@@ -316,7 +316,6 @@ def solve_socp_batch(prob: BatchProblem, ss: BatchSolverState, params: Optional[
     """solve_socp over the batch: upload (unless already resident), initial
     point + Mehrotra loop on the device, download."""
     h = ss.handle
-    ss.load(prob, force=reload)
     B, n, p, k = h.batch, h.n, h.p, h.k
     x = np.empty((B, n)) if want_iterates else None
     y = np.empty((B, p)) if want_iterates else None
@@ -327,9 +326,21 @@ def solve_socp_batch(prob: BatchProblem, ss: BatchSolverState, params: Optional[
     pobj = np.empty(B)
     dobj = np.empty(B)
     prm = params if params is not None else default_params()
-    rc = h.lib.socp_b200_solve(h.ptr, C.byref(prm), _dp(x), _dp(y) if p else None, _dp(z), _dp(s),
-                               _ip(status), _ip(iters), _dp(pobj), _dp(dobj))
-    h.check(rc, "socp_b200_solve")
+    if reload or ss._loaded_id != id(prob):
+        # Problem(...) + solve_socp(prob, ss) in one call: upload, solve and download overlap on the fused path
+        assert (prob.n, prob.p, prob.B) == (h.n, h.p, h.batch) and prob.cones == h.cones
+        flags = (1 if prob.shared_A else 0) | (2 if prob.shared_G else 0)
+        sing = None if prob.sing is None else prob.sing.ctypes.data_as(L.c_uint8_p)
+        rc = h.lib.socp_b200_solve_host(h.ptr, C.byref(prm), _dp(prob.c), _dp(prob.A_cm) if p else None,
+                                        _dp(prob.b) if p else None, _dp(prob.G_cm), _dp(prob.h), sing, flags,
+                                        _dp(x), _dp(y) if p else None, _dp(z), _dp(s),
+                                        _ip(status), _ip(iters), _dp(pobj), _dp(dobj))
+        h.check(rc, "socp_b200_solve_host")
+        ss._loaded_id = id(prob)
+    else:
+        rc = h.lib.socp_b200_solve(h.ptr, C.byref(prm), _dp(x), _dp(y) if p else None, _dp(z), _dp(s),
+                                   _ip(status), _ip(iters), _dp(pobj), _dp(dobj))
+        h.check(rc, "socp_b200_solve")
     return BatchResult(x, y, z, s, status, iters, pobj, dobj, h.timings())
 
 

@@ -289,3 +289,18 @@ def test_shared_G_batch():
     ra = sb.solve_socp_batch(shared, sb.SolverState(shared), sb.default_params(path=sb.PATH_TILED))
     rb = sb.solve_socp_batch(full, sb.SolverState(full), sb.default_params(path=sb.PATH_TILED))
     assert np.array_equal(ra.status, rb.status) and np.array_equal(ra.x, rb.x)
+
+
+def test_solve_host_pipelined_matches_two_step():
+    """socp_b200_solve_host (chunked upload / solve / download on three streams) must return exactly what
+    set_data + solve return: same kernel, same data, only the schedule differs."""
+    prob = gen.make_config("C2", batch=5000)          # 2 chunks on a 148-SM part (8 waves of 296 CTAs each)
+    ss = sb.SolverState(prob)
+    one = sb.solve_socp_batch(prob, ss)                # reload=True -> socp_b200_solve_host
+    assert one.timings["path_used"] == sb.PATH_FUSED and one.timings["kernel_launches"] >= 2
+    ss2 = sb.SolverState(prob)
+    ss2.load(prob)
+    two = sb.solve_socp_batch(prob, ss2, reload=False) # socp_b200_set_data + socp_b200_solve
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+        assert np.array_equal(getattr(one, f), getattr(two, f)), f
+    assert (one.status == sb.STATUS_CONVERGED).all()

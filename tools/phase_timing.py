@@ -12,20 +12,19 @@ import numpy as np
 import socp_b200 as sb
 from socp_b200 import generators as gen, _lib
 ap = argparse.ArgumentParser(); ap.add_argument("config"); ap.add_argument("--batch", type=int, default=2960)
-ap.add_argument("--v1", action="store_true", help="first-generation fused kernel (path 3)")
 a = ap.parse_args()
 prob = gen.make_config(a.config, batch=a.batch)
 ss = sb.SolverState(prob)
+ss.load(prob)
 lib = _lib.load()
-prm = sb.default_params(path=3 if a.v1 else 2)
-r = sb.solve_socp_batch(prob, ss, prm, want_iterates=False)      # warm
+prm = sb.default_params(path=2)
+r = sb.solve_socp_batch(prob, ss, prm, reload=False, want_iterates=False)      # warm
 buf = (C.c_ulonglong * 16)()
-fn = lib.socp_b200_debug_phase_clocks if a.v1 else lib.socp_b200_debug_phase_clocks2
+fn = lib.socp_b200_debug_phase_clocks2
 fn(buf, 1)
-r = sb.solve_socp_batch(prob, ss, prm, want_iterates=False)
+r = sb.solve_socp_batch(prob, ss, prm, reload=False, want_iterates=False)
 fn(buf, 0)
-names = (["load", "syrk", "chol_inv", "eq(HiAt,M)", "solve_mid", "init_shift", "mid", "post", "scaling+resid", "pre", "build_gt", "out"]
-         if a.v1 else ["load", "scaling+resid", "head+build_gt", "n0+syrk", "chol_inv", "eq", "solve_mid", "init", "mid", "post", "out", "-"])
+names = ["load", "scaling+resid", "hc+head", "n0+syrk", "chol+inverse", "eq", "solve_mid", "init", "tail", "mid/post", "out", "-"]
 tot = sum(buf[i] for i in range(12))
 print(a.config, "batch", a.batch, "solve_ms %.3f" % r.timings["solve_ms"], "mean iters %.2f" % r.iters.mean())
 for i, nm in enumerate(names):

@@ -20,8 +20,9 @@ ap.add_argument("--max-iter", type=int, default=40)
 a = ap.parse_args()
 prob = gen.make_config(a.config, batch=a.batch)
 ss = sb.SolverState(prob)
+ss.load(prob)
 prm = sb.default_params(path={"auto": 0, "tiled": 1, "fused": 2}[a.path], max_iter=a.max_iter)
 for _ in range(a.reps):
-    r = sb.solve_socp_batch(prob, ss, prm, want_iterates=False)
+    r = sb.solve_socp_batch(prob, ss, prm, reload=False, want_iterates=False)
 print(a.config, "batch", prob.B, "status counts", np.bincount(r.status, minlength=3).tolist(), "mean iters %.2f" % r.iters.mean(),
       "timings", r.timings)
