@@ -185,6 +185,13 @@ int  socp_b200_compute_step(socp_handle* h, const double* lambda, const double* 
 int  socp_b200_get_H(socp_handle* h, double* out);
 int  socp_b200_get_L(socp_handle* h, double* out);
 
+/* Measurement utility (no reference counterpart): mean CUDA-event time, in ms, of
+ * the device kernels behind one step-level call over `reps` repetitions on the data
+ * resident after _set_data + _compute_scaling.  which: 0 compute_scaling, 1 scale!,
+ * 2 iscale!, 3 vprod!, 4 iprod!, 5 compute_step, 6 W^-1 G, 7 SYRK G'W^-2 G,
+ * 8 Cholesky, 9 L L' solve (1 rhs), 10 G'v, 11 G v.  Single-device handles only. */
+int  socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* ms_per_call);
+
 #ifdef __cplusplus
 }
 #endif

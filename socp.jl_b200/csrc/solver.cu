@@ -5,6 +5,7 @@
 #include "linalg.cuh"
 #include "tiled_kernels.cuh"
 #include "fused_v2.cuh"
+#include "cone_batch.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -56,6 +57,10 @@ struct Shard {
     Ws w{};
     // layout (device copies)
     int *d_kind = nullptr, *d_offs = nullptr, *d_dim = nullptr;
+    BLayout bl{};          // batch-wide lane-group view of the cones (cone_batch.cuh)
+    bool bl_ok = false;    // every second-order cone has dimension <= 128
+    bool bl_warp = false;  // ... and the cones of one problem fit in one warp (nsoc * lpc <= 32)
+    int bl_sw = 32;        // lanes per problem in the per-problem reductions (power of two >= nsoc * lpc)
     // owned copies of the problem data
     double *d_c = nullptr, *d_A = nullptr, *d_b = nullptr, *d_G = nullptr, *d_h = nullptr;
     uint8_t* d_sing = nullptr;
@@ -180,17 +185,79 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, int* fail, const in
         }
     }
 }
-// X <- (L L')^-1 X, X is nn x nrhs (ld ldx)
+// X <- (L L')^-1 X, X is nn x nrhs (ld ldx).  Up to 1024 rows one CTA per (rhs, problem) walks the whole factor;
+// beyond that the factor is cut into diagonal blocks of 512 solved the same way, with the off-diagonal panels
+// applied by the batch-wide gemv kernels (many CTAs) in between -- a single CTA streaming a 4096^2 factor would be
+// ~40x slower than the gemvs.
 void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, double* X, int64_t sX, int ldx, int nrhs,
            const int* active) {
     if (nn == 0 || nrhs == 0) return;
+    constexpr int BS = 512;
+    if (nn <= 2 * BS) {
+        dim3 grid(nrhs, sh.batch);
+        const size_t smem = (size_t)nn * sizeof(double);
+        LAUNCH(sh, k_trsv_fwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
+        LAUNCH(sh, k_trsv_bwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
+        return;
+    }
     dim3 grid(nrhs, sh.batch);
-    const size_t smem = (size_t)nn * sizeof(double);
-    LAUNCH(sh, k_trsv_fwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
-    LAUNCH(sh, k_trsv_bwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
+    for (int jb = 0; jb < nn; jb += BS) {                       // forward: L y = x
+        const int bs = std::min(BS, nn - jb), below = nn - jb - bs;
+        LAUNCH(sh, k_trsv_fwd, grid, 256, (size_t)bs * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, X + jb, sX, ldx, active);
+        for (int q = 0; q < nrhs && below > 0; ++q)
+            gemv_n(sh, L + (int64_t)jb * ld + jb + bs, sL, ld, below, bs, X + (int64_t)q * ldx + jb, sX,
+                   X + (int64_t)q * ldx + jb + bs, sX, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
+    }
+    for (int jb = (nn - 1) / BS * BS; jb >= 0; jb -= BS) {       // backward: L' x = y
+        const int bs = std::min(BS, nn - jb), below = nn - jb - bs;
+        for (int q = 0; q < nrhs && below > 0; ++q)
+            gemv_t(sh, L + (int64_t)jb * ld + jb + bs, sL, ld, below, bs, X + (int64_t)q * ldx + jb + bs, sX,
+                   X + (int64_t)q * ldx + jb, sX, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
+        LAUNCH(sh, k_trsv_bwd, grid, 256, (size_t)bs * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, X + jb, sX, ldx, active);
+    }
 }
 
-ConeLayout& LY(Shard& sh) { return sh.w.L; }
+// grid of the batch-wide cone kernels: enough 256-thread CTAs for one lane group per cone / one thread per
+// positive-orthant row, capped at 16 CTAs per SM (grid-stride beyond that)
+int cone_grid(const Shard& sh) {
+    const long long thr = std::max((long long)sh.batch * sh.bl.nsoc * sh.bl.lpc, (long long)sh.batch * sh.bl.kpoc);
+    return (int)std::max(1LL, std::min((thr + 255) / 256, 148LL * 16));
+}
+void launch_scaling(Shard& sh, const int* active) {
+    Ws& w = sh.w;
+    if (sh.bl_ok) LAUNCH(sh, bk_scaling, cone_grid(sh), 256, 0, sh.bl, sh.batch, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, active);
+    else LAUNCH(sh, k_scaling, sh.batch, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, active);
+}
+void launch_apply(Shard& sh, int mode, const double* v, double* out) {
+    Ws& w = sh.w;
+    const int B = sh.batch;
+    if (sh.bl_ok) {
+        const int g = cone_grid(sh);
+        if (mode == 0) LAUNCH(sh, bk_apply<APPLY_W>, g, 256, 0, sh.bl, B, w.wb, w.iwb, w.eta, v, out);
+        else if (mode == 1) LAUNCH(sh, bk_apply<APPLY_WINV>, g, 256, 0, sh.bl, B, w.wb, w.iwb, w.eta, v, out);
+        else LAUNCH(sh, bk_apply<APPLY_WINV2>, g, 256, 0, sh.bl, B, w.wb, w.iwb, w.eta, v, out);
+    } else {
+        if (mode == 0) LAUNCH(sh, k_apply<APPLY_W>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, v, out);
+        else if (mode == 1) LAUNCH(sh, k_apply<APPLY_WINV>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, v, out);
+        else LAUNCH(sh, k_apply<APPLY_WINV2>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, v, out);
+    }
+}
+void launch_vprod(Shard& sh, const double* u, const double* v, double* t) {
+    if (sh.bl_ok) LAUNCH(sh, bk_vprod, cone_grid(sh), 256, 0, sh.bl, sh.batch, u, v, t);
+    else LAUNCH(sh, k_vprod, sh.batch, sh.threads, 0, sh.w.L, u, v, t);
+}
+void launch_iprod(Shard& sh, const double* lam, const double* v, double* t) {
+    if (sh.bl_ok) LAUNCH(sh, bk_iprod, cone_grid(sh), 256, 0, sh.bl, sh.batch, lam, v, t);
+    else LAUNCH(sh, k_iprod, sh.batch, sh.threads, 0, sh.w.L, lam, v, t);
+}
+void launch_max_step(Shard& sh, const double* x, double* out) {
+    if (sh.bl_warp) LAUNCH(sh, bk_max_step, (sh.batch + 8 * (32 / sh.bl_sw) - 1) / (8 * (32 / sh.bl_sw)), 256, 0, sh.bl, sh.batch, sh.bl_sw, x, out);
+    else LAUNCH(sh, k_max_step, sh.batch, sh.threads, 0, sh.w.L, x, out);
+}
+void launch_compute_step(Shard& sh, const double* lam, const double* ds, const double* dz, double* out) {
+    if (sh.bl_warp) LAUNCH(sh, bk_compute_step, (sh.batch + 8 * (32 / sh.bl_sw) - 1) / (8 * (32 / sh.bl_sw)), 256, 0, sh.bl, sh.batch, sh.bl_sw, lam, ds, dz, out);
+    else LAUNCH(sh, k_compute_step, sh.batch, sh.threads, 0, sh.w.L, lam, ds, dz, out);
+}
 
 // KKT factor, reference src/densesolver.jl:41-52.  identity: W = I (initial point, sing test).
 void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
@@ -271,7 +338,7 @@ void solve_tiled(Shard& sh, const socp_params& prm) {
     initial_point(sh, P);
     int itmax = 0;
     for (int it = 0; it < prm.max_iter; ++it) {
-        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, w.active);   // :106
+        launch_scaling(sh, w.active);                                                   // :106
         // negated residuals                                                           :110-118,:125
         gemv_t(sh, w.G, w.sG, k, k, n, w.z, k, w.dx, n, -1.0, epi(w.c, -1.0, n), w.active);
         if (p > 0) {
@@ -344,6 +411,27 @@ void build_shard(socp_handle* h, Shard& sh) {
     // tiled-path factor workspaces are allocated lazily (ensure_tiled): the fused
     // path does not need them and they dominate the footprint
     sh.threads = std::min(256, std::max(32, 32 * nc));
+    {
+        std::vector<int> so, sd, sw;
+        int kpoc = 0, maxd = 1;
+        for (size_t i = 0; i < h->kind.size(); ++i) {
+            if (h->kind[i] == SOCP_CONE_POC) kpoc += h->dim[i];
+            else { so.push_back(h->offs[i]); sd.push_back(h->dim[i]); sw.push_back(h->first_work[i]); maxd = std::max(maxd, h->dim[i]); }
+        }
+        const int ns = (int)so.size();
+        int* d = sh.alloc<int>(3 * std::max(ns, 1));
+        if (ns) {
+            CK(cudaMemcpyAsync(d, so.data(), ns * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+            CK(cudaMemcpyAsync(d + ns, sd.data(), ns * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+            CK(cudaMemcpyAsync(d + 2 * ns, sw.data(), ns * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
+        }
+        sh.bl = BLayout{k, kpoc, ns, f2_lpc(maxd), nc, d, d + ns, d + 2 * ns};
+        sh.bl_ok = maxd <= 128;
+        sh.bl_warp = sh.bl_ok && ns * sh.bl.lpc <= 32;
+        sh.bl_sw = 1;
+        while (sh.bl_sw < std::max(1, ns * sh.bl.lpc)) sh.bl_sw <<= 1;
+        sh.bl_sw = std::min(sh.bl_sw, 32);
+    }
     f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
     sh.fused2.d_counter = sh.alloc<int>(1);
     CK(cudaStreamSynchronize(sh.stream));
@@ -856,7 +944,7 @@ int socp_b200_compute_scaling(socp_handle* h, const double* s, const double* z, 
         h2d(sh, w.s, s + f * k, sizeof(double) * B * k);
         h2d(sh, w.z, z + f * k, sizeof(double) * B * k);
         CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
-        LAUNCH(sh, k_scaling, B, sh.threads, 0, w.L, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, (const int*)nullptr);
+        launch_scaling(sh, nullptr);
         if (lambda) d2h(sh, lambda + f * k, w.lam, sizeof(double) * B * k);
         if (wbs) d2h(sh, wbs + f * k, w.wb, sizeof(double) * B * k);
         if (fail) d2h(sh, fail + f, w.fail, sizeof(int) * B);
@@ -907,9 +995,7 @@ static int apply_common(socp_handle* h, const double* in, double* out, int mode)
     if (h && (!in || !out)) return SOCP_ERR_NULL;
     STEP_PROLOGUE(sh.have_scaling, "needs compute_scaling first")
         h2d(sh, w.kt2, in + f * k, sizeof(double) * B * k);
-        if (mode == 0) LAUNCH(sh, k_apply<APPLY_W>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, w.kt2, w.kt3);
-        else if (mode == 1) LAUNCH(sh, k_apply<APPLY_WINV>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, w.kt2, w.kt3);
-        else LAUNCH(sh, k_apply<APPLY_WINV2>, B, sh.threads, 0, w.L, w.wb, w.iwb, w.eta, w.kt2, w.kt3);
+        launch_apply(sh, mode, w.kt2, w.kt3);
         d2h(sh, out + f * k, w.kt3, sizeof(double) * B * k);
     STEP_EPILOGUE
 }
@@ -929,7 +1015,7 @@ int socp_b200_vprod(socp_handle* h, const double* u, const double* v, double* ou
     STEP_PROLOGUE(true, "")
         h2d(sh, w.kt2, u + f * k, sizeof(double) * B * k);
         h2d(sh, w.kt3, v + f * k, sizeof(double) * B * k);
-        LAUNCH(sh, k_vprod, B, sh.threads, 0, w.L, w.kt2, w.kt3, w.k0);
+        launch_vprod(sh, w.kt2, w.kt3, w.k0);
         d2h(sh, out + f * k, w.k0, sizeof(double) * B * k);
     STEP_EPILOGUE
 }
@@ -938,7 +1024,7 @@ int socp_b200_iprod(socp_handle* h, const double* lambda, const double* v, doubl
     STEP_PROLOGUE(true, "")
         h2d(sh, w.kt2, lambda + f * k, sizeof(double) * B * k);
         h2d(sh, w.kt3, v + f * k, sizeof(double) * B * k);
-        LAUNCH(sh, k_iprod, B, sh.threads, 0, w.L, w.kt2, w.kt3, w.k0);
+        launch_iprod(sh, w.kt2, w.kt3, w.k0);
         d2h(sh, out + f * k, w.k0, sizeof(double) * B * k);
     STEP_EPILOGUE
 }
@@ -946,7 +1032,7 @@ int socp_b200_max_step(socp_handle* h, const double* x, double* out) {
     if (h && (!x || !out)) return SOCP_ERR_NULL;
     STEP_PROLOGUE(true, "")
         h2d(sh, w.kt2, x + f * k, sizeof(double) * B * k);
-        LAUNCH(sh, k_max_step, B, sh.threads, 0, w.L, w.kt2, w.k0);
+        launch_max_step(sh, w.kt2, w.k0);
         d2h(sh, out + f, w.k0, sizeof(double) * B);
     STEP_EPILOGUE
 }
@@ -956,7 +1042,7 @@ int socp_b200_compute_step(socp_handle* h, const double* lambda, const double* d
         h2d(sh, w.k2, lambda + f * k, sizeof(double) * B * k);
         h2d(sh, w.kt2, ds + f * k, sizeof(double) * B * k);
         h2d(sh, w.kt3, dz + f * k, sizeof(double) * B * k);
-        LAUNCH(sh, k_compute_step, B, sh.threads, 0, w.L, w.k2, w.kt2, w.kt3, w.k0);
+        launch_compute_step(sh, w.k2, w.kt2, w.kt3, w.k0);
         d2h(sh, out + f, w.k0, sizeof(double) * B);
     STEP_EPILOGUE
 }
@@ -995,6 +1081,77 @@ int socp_b200_get_H(socp_handle* h, double* out) {
             }
     }
     return 0;
+}
+
+// Measurement utility (not a reference interface): runs the device kernels of one step-level call `reps` times on
+// the data already resident after compute_scaling / setup_iter and returns the mean CUDA-event time per call.
+//   0 compute_scaling   1 scale! (W v)   2 iscale! (W^-1 v)   3 vprod!   4 iprod!   5 compute_step
+//   6 Gt = W^-1 G       7 SYRK H = Gt'Gt 8 Cholesky of H (H restored from a copy before every repetition)
+//   9 L L' solve, one right-hand side    10 G'v gemv          11 G v gemv
+int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* ms_per_call) {
+    if (!h || !ms_per_call) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        need(h->shards.size() == 1, SOCP_ERR_STATE, "profile_step works on a single-device handle");
+        need(reps > 0 && which >= 0 && which <= 11, SOCP_ERR_SIZE, "bad arguments");
+        Shard& sh = h->shards[0];
+        CK(cudaSetDevice(sh.device));
+        need(sh.have_data && sh.have_scaling, SOCP_ERR_STATE, "profile_step needs set_data and compute_scaling first");
+        Ws& w = sh.w;
+        const int n = w.L.n, k = w.L.k, B = sh.batch;
+        ensure_tiled(sh);
+        double* Hcopy = nullptr;
+        const size_t hbytes = sizeof(double) * (size_t)B * w.ldh * n;
+        if (which == 7 || which == 8 || which == 9) {
+            const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
+            dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
+            LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 0, cols_per_cta, (const int*)nullptr);
+            syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0, 0, nullptr, nullptr);
+            if (which == 8) {
+                CK(cudaMalloc((void**)&Hcopy, hbytes));
+                CK(cudaMemcpyAsync(Hcopy, w.H, hbytes, cudaMemcpyDeviceToDevice, sh.stream));
+            }
+            if (which == 9) {
+                CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
+                potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr);
+            }
+        }
+        double total = 0.0;
+        for (int r = 0; r < reps + 1; ++r) {          // repetition 0 warms up
+            if (which == 8) {
+                CK(cudaMemcpyAsync(w.H, Hcopy, hbytes, cudaMemcpyDeviceToDevice, sh.stream));
+                CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
+            }
+            CK(cudaEventRecord(sh.ev[0], sh.stream));
+            switch (which) {
+                case 0: launch_scaling(sh, nullptr); break;
+                case 1: launch_apply(sh, 0, w.s, w.kt3); break;
+                case 2: launch_apply(sh, 1, w.s, w.kt3); break;
+                case 3: launch_vprod(sh, w.s, w.z, w.k0); break;
+                case 4: launch_iprod(sh, w.lam, w.z, w.k0); break;
+                case 5: launch_compute_step(sh, w.lam, w.s, w.z, w.k0); break;
+                case 6: {
+                    const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
+                    dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
+                    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 0, cols_per_cta, (const int*)nullptr);
+                    break;
+                }
+                case 7: syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0, 0, nullptr, nullptr); break;
+                case 8: potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr); break;
+                case 9: potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.rx, n, n, 1, nullptr); break;
+                case 10: gemv_t(sh, w.G, w.sG, k, k, n, w.z, k, w.dx, n, 1.0, epi(), nullptr); break;
+                default: gemv_n(sh, w.G, w.sG, k, k, n, w.x, n, w.dz, k, 1.0, epi(), nullptr); break;
+            }
+            CK(cudaEventRecord(sh.ev[1], sh.stream));
+            CK(cudaStreamSynchronize(sh.stream));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
+            if (r > 0) total += ms;
+        }
+        if (Hcopy) cudaFree(Hcopy);
+        CK(cudaGetLastError());
+        *ms_per_call = total / reps;
+        sh.have_factor = false;
+    });
 }
 
 #ifdef SOCP_PHASE_TIMING
