@@ -151,16 +151,26 @@ function load!(ss::SolverState, pr::BatchProblem)
     check(ss, rc, "socp_b200_set_data")
 end
 
-"solve_socp_batch(prob, ss) -- solve_socp (src/solver.jl:40-152) for every problem of the batch on the GPU."
-function solve_socp_batch(pr::BatchProblem, ss::SolverState; params = default_params())
-    load!(ss, pr)
+"""
+    solve_socp_batch(prob, ss; params, sing)
+
+solve_socp (src/solver.jl:40-152) for every problem of the batch on the GPU, as ONE library call from host data
+to host results (`socp_b200_solve_host`: upload, solve and download of chunks overlap).  `sing` is the reference's
+5th type parameter per problem (src/Socp.jl:49-56); pass `nothing` to have it computed on the device.
+"""
+function solve_socp_batch(pr::BatchProblem, ss::SolverState; params = default_params(),
+                          sing::Union{Nothing,Vector{UInt8}} = zeros(UInt8, pr.B))
     x = zeros(pr.n, pr.B); y = zeros(pr.m, pr.B); z = zeros(pr.k, pr.B); s = zeros(pr.k, pr.B)
     status = zeros(Int32, pr.B); iters = zeros(Int32, pr.B); pobj = zeros(pr.B); dobj = zeros(pr.B)
-    rc = ccall((:socp_b200_solve, libsocp), Cint,
-        (Ptr{Cvoid}, Ref{CParams}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+    flags = Int32((ndims(pr.A) == 2 && pr.m > 0 ? 1 : 0) | (ndims(pr.G) == 2 ? 2 : 0))
+    rc = GC.@preserve pr sing ccall((:socp_b200_solve_host, libsocp), Cint,
+        (Ptr{Cvoid}, Ref{CParams}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{UInt8}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
-        ss.solver.handle, params, x, pr.m > 0 ? pointer(y) : C_NULL, z, s, status, iters, pobj, dobj)
-    check(ss, rc, "socp_b200_solve")
+        ss.solver.handle, params, pr.c, pr.m > 0 ? pointer(pr.A) : C_NULL, pr.m > 0 ? pointer(pr.b) : C_NULL,
+        pr.G, pr.h, sing === nothing ? Ptr{UInt8}(C_NULL) : pointer(sing), flags,
+        x, pr.m > 0 ? pointer(y) : C_NULL, z, s, status, iters, pobj, dobj)
+    check(ss, rc, "socp_b200_solve_host")
     return (x = x, y = y, z = z, s = s, status = status, iters = iters, pobj = pobj, dobj = dobj)
 end
 
