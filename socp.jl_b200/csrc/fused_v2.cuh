@@ -417,7 +417,8 @@ __device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* 
 // Factor of one 8x8 diagonal tile by one warp.  The Cholesky factor is computed by all lanes redundantly in
 // registers (no shuffles); lane c (mod 8) then computes column c of its inverse by forward substitution, so that
 // on exit xc[i] = (L^-1)[i][c], c = lane & 7 (zero above the diagonal).  Returns 0 on a pivot that is not > 0.
-__device__ __forceinline__ int f2_diag_factor(const double* T, int ld, int lane, double (&xc)[8]) {
+template <bool WRITE_L>
+__device__ __forceinline__ int f2_diag_factor(double* T, int ld, int lane, double (&xc)[8]) {
     double a[36];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -439,8 +440,17 @@ __device__ __forceinline__ int f2_diag_factor(const double* T, int ld, int lane,
             for (int c = j + 1; c <= i; ++c)
                 a[i * (i + 1) / 2 + c] = fma(-a[i * (i + 1) / 2 + j], a[c * (c + 1) / 2 + j], a[i * (i + 1) / 2 + c]);
     }
-    // column c of the inverse: x_i = 0 (i < c), r_c (i == c), -r_i sum_{m<i} l_im x_m (i > c)
     const int c = lane & 7;
+    if (WRITE_L) {      // the tiled path needs the factor itself: lane c < 8 writes column c of L (rows i >= c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = a[i * (i + 1) / 2];
+#pragma unroll
+            for (int cc = 1; cc <= i; ++cc) v = (c == cc) ? a[i * (i + 1) / 2 + cc] : v;
+            if (lane < 8 && i >= c) T[c * ld + i] = (i == c) ? v * r[i] : v;      // l_ii = d_i / sqrt(d_i)
+        }
+    }
+    // column c of the inverse: x_i = 0 (i < c), r_c (i == c), -r_i sum_{m<i} l_im x_m (i > c)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         double sacc = 0.0;
@@ -486,7 +496,7 @@ __device__ __forceinline__ void f2_build_trail(uint2* desc, int nbl, int ld, int
 // the caller) holds L^-1; H is destroyed.  Dinv: 2 x (8 x 12) scratch, zero above the diagonal.  desc: the table of
 // f2_build_trail for (nbl, ld, X - H).  *fail is set (and 0 returned) on a non-positive pivot: cholesky!'s
 // PosDefException, src/densesolver.jl:47,51.
-template <int NW>
+template <int NW, bool WRITE_L = false>
 __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, const uint2* desc, int nbl, int ld,
                                            int* fail, int lane, int warp) {
     const int fr = lane >> 2, fk = lane & 3;
@@ -497,7 +507,7 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, c
         if (warp == 0) {
             __syncwarp();
             double xc[8];
-            const int ok = f2_diag_factor(H + b0 * ld + b0, ld, lane, xc);
+            const int ok = f2_diag_factor<WRITE_L>(H + b0 * ld + b0, ld, lane, xc);
             if (!ok && lane == 0) *fail = 1;
             // publish column c = lane of the tile's inverse: Dinv (row-major, ld 12) and the diagonal tile of X
             if (lane < 8) {

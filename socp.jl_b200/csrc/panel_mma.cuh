@@ -1,0 +1,112 @@
+// panel_mma.cuh -- DMMA panel kernels of the tiled path's blocked Cholesky (n > what fits the fused kernel).
+// Reuses the tile algorithm of fused_v2.cuh (f2_chol_inv).  Replaces LAPACK dpotrf's panel work behind
+// cholesky! (reference src/densesolver.jl:47,51).
+#pragma once
+#include "fused_v2.cuh"
+
+namespace socp {
+
+// ---------------------------------------------------------------------------
+// DMMA panel of the blocked Cholesky (replaces k_potrf_diag + k_trsm_panel when the
+// panel is a full 64 columns wide):
+//   k_potrf_diag_mma : one CTA (8 warps) per problem factors the 64 x 64 diagonal block
+//                      with the tile algorithm of the fused kernel (f2_chol_inv: 8x8
+//                      tiles, mma.sync f64, the inverse carried along), writes L11 back
+//                      and X11 = L11^-1 (dense 64 x 64, zero above the diagonal) to Xd.
+//   k_trsm_mma       : L21 = A21 X11' as a DMMA product; CTA x owns 128 rows of the
+//                      sub-panel.                grid (ceil((n-j-64)/128), batch)
+// ---------------------------------------------------------------------------
+constexpr int PANEL_LDH = 68;                                   // 64 + 4: conflict-free fragment loads
+constexpr size_t POTRF_MMA_SMEM = sizeof(double) * (64 * PANEL_LDH + f2_xsize(8) + 192) + sizeof(uint2) * f2_trail_base(8, 8);
+
+__global__ void __launch_bounds__(256)
+k_potrf_diag_mma(double* __restrict__ H, int64_t strideH, int ldh, int j, double* __restrict__ Xd,
+                 int* __restrict__ fail, const int* __restrict__ active) {
+    const int b = blockIdx.x;
+    if (active && !active[b]) return;
+    extern __shared__ __align__(16) double psm[];
+    __shared__ int sfail;
+    double* Hs = psm;
+    double* Xs = Hs + 64 * PANEL_LDH;
+    double* Dinv = Xs + f2_xsize(8);
+    uint2* desc = reinterpret_cast<uint2*>(Dinv + 192);
+    double* Hb = H + (int64_t)b * strideH + (int64_t)j * ldh + j;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sfail = 0;
+    for (int q = tid; q < 64 * 64; q += 256) {
+        const int c = q >> 6, r = q & 63;
+        Hs[c * PANEL_LDH + r] = (r >= c) ? Hb[(int64_t)c * ldh + r] : 0.0;
+    }
+    for (int q = tid; q < f2_xsize(8) + 192; q += 256) Xs[q] = 0.0;
+    f2_build_trail(desc, 8, PANEL_LDH, 64 * PANEL_LDH, tid, 256);
+    __syncthreads();
+    const int ok = f2_chol_inv<8, true>(Hs, Xs, Dinv, desc, 8, PANEL_LDH, &sfail, lane, warp);
+    if (!ok) {
+        if (tid == 0) fail[b] = 1;
+        return;
+    }
+    double* Xb = Xd + (int64_t)b * 64 * 64;
+    for (int q = tid; q < 64 * 64; q += 256) {
+        const int c = q >> 6, r = q & 63;
+        if (r >= c) Hb[(int64_t)c * ldh + r] = Hs[c * PANEL_LDH + r];
+        const int cb = c >> 3;
+        Xb[q] = (r >= cb * 8) ? Xs[f2_xbase(8, cb) + (c & 7) * f2_xld(8, cb) + r - cb * 8] : 0.0;
+    }
+}
+
+constexpr int TRSM_LDA = 132;                                   // 128 + 4
+constexpr size_t TRSM_MMA_SMEM = sizeof(double) * (64 * PANEL_LDH + 64 * TRSM_LDA);
+
+__global__ void __launch_bounds__(256)
+k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const double* __restrict__ Xd,
+           const int* __restrict__ fail, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    if (fail[b]) return;
+    extern __shared__ __align__(16) double psm[];
+    double* Xs = psm;                       // X11, 64 x 64, ld PANEL_LDH
+    double* As = psm + 64 * PANEL_LDH;      // 128 rows x 64 columns of A21, ld TRSM_LDA
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row0 = j + 64 + blockIdx.x * 128;
+    const int nrow = min(128, n - row0);
+    double* Hb = H + (int64_t)b * strideH;
+    const double* Xb = Xd + (int64_t)b * 64 * 64;
+    for (int q = tid; q < 64 * 64; q += 256) Xs[(q >> 6) * PANEL_LDH + (q & 63)] = Xb[q];
+    for (int q = tid; q < 64 * 128; q += 256) {
+        const int c = q >> 7, r = q & 127;
+        As[c * TRSM_LDA + r] = (r < nrow) ? Hb[(int64_t)(j + c) * ldh + row0 + r] : 0.0;
+    }
+    __syncthreads();
+    // warp w: rows [16w, 16w+16), all 64 columns: C[r][c] = sum_{m <= c} A[r][m] X[c][m]
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[2][8][2];
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) acc[rt][ct][0] = acc[rt][ct][1] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < 64; kk += 4) {
+        const double a0 = As[(kk + fk) * TRSM_LDA + warp * 16 + fr];
+        const double a1 = As[(kk + fk) * TRSM_LDA + warp * 16 + 8 + fr];
+#pragma unroll
+        for (int ct = 0; ct < 8; ++ct) {
+            if (kk < (ct + 1) * 8) {        // X is lower triangular: X[c][m] = 0 for m > c
+                const double xb = Xs[(kk + fk) * PANEL_LDH + ct * 8 + fr];
+                dmma884(acc[0][ct][0], acc[0][ct][1], a0, xb);
+                dmma884(acc[1][ct][0], acc[1][ct][1], a1, xb);
+            }
+        }
+    }
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt) {
+        const int r = warp * 16 + rt * 8 + fr;
+        if (r < nrow) {
+#pragma unroll
+            for (int ct = 0; ct < 8; ++ct)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) Hb[(int64_t)(j + ct * 8 + 2 * fk + e) * ldh + row0 + r] = acc[rt][ct][e];
+        }
+    }
+}
+
+}  // namespace socp

@@ -6,6 +6,7 @@
 #include "tiled_kernels.cuh"
 #include "fused_v2.cuh"
 #include "cone_batch.cuh"
+#include "panel_mma.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -171,14 +172,28 @@ void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, i
     }
 }
 
-// blocked Cholesky of `nn x nn` matrices (ld, stride), lower, in place
+// blocked Cholesky of `nn x nn` matrices (ld, stride), lower, in place.  Full 64-column panels go through the DMMA
+// panel kernels (panel_mma.cuh); a narrower last panel through the scalar ones.
 void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, int* fail, const int* active) {
+    static bool configured[64] = {};
+    if (!configured[sh.device]) {
+        CK(cudaFuncSetAttribute(k_potrf_diag_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_MMA_SMEM));
+        CK(cudaFuncSetAttribute(k_trsm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_MMA_SMEM));
+        configured[sh.device] = true;
+    }
     for (int j = 0; j < nn; j += CHOL_NB) {
         const int below = nn - j - CHOL_NB;
-        LAUNCH(sh, k_potrf_diag, sh.batch, 128, 0, H, sH, ld, nn, j, fail, active);
+        const bool mma = (nn - j >= CHOL_NB) && sh.w.Xd != nullptr;
+        if (mma) LAUNCH(sh, k_potrf_diag_mma, sh.batch, 256, POTRF_MMA_SMEM, H, sH, ld, j, sh.w.Xd, fail, active);
+        else LAUNCH(sh, k_potrf_diag, sh.batch, 128, 0, H, sH, ld, nn, j, fail, active);
         if (below > 0) {
-            dim3 grid((below + 127) / 128, sh.batch);
-            LAUNCH(sh, k_trsm_panel, grid, 128, 0, H, sH, ld, nn, j, (const int*)fail, active);
+            if (mma) {
+                dim3 grid((below + 127) / 128, sh.batch);
+                LAUNCH(sh, k_trsm_mma, grid, 256, TRSM_MMA_SMEM, H, sH, ld, nn, j, (const double*)sh.w.Xd, (const int*)fail, active);
+            } else {
+                dim3 grid((below + 127) / 128, sh.batch);
+                LAUNCH(sh, k_trsm_panel, grid, 128, 0, H, sH, ld, nn, j, (const int*)fail, active);
+            }
             const double* P = H + (int64_t)j * ld + (j + CHOL_NB);
             double* T = H + (int64_t)(j + CHOL_NB) * ld + (j + CHOL_NB);
             syrk(sh, false, P, sH, ld, below, CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active);
@@ -447,6 +462,7 @@ void ensure_tiled(Shard& sh) {
     w.M = sh.alloc<double>((size_t)B * w.ldm * p);
     w.AA = sh.alloc<double>((size_t)B * w.ldh * n * (p > 0 ? 1 : 0));
     w.Ap = sh.alloc<double>((size_t)B * w.ldap * n * (p > 0 ? 1 : 0));
+    w.Xd = sh.alloc<double>((size_t)B * 64 * 64, false);
 }
 
 // AA = A'A (reference src/densesolver.jl:32) and, when the caller gave no
