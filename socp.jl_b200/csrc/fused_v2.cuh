@@ -378,8 +378,7 @@ __device__ __forceinline__ void f2_syrk_w(const double* G, int ldg, int kpad, in
     }
 }
 // Out (full symmetric, ld) = X' X for the lower-triangular X (trapezoid storage; the part of a diagonal tile above
-// the diagonal is zero): H^-1 = L^-T L^-1.  Accumulates in registers, team barrier, then
-// stores, so Out may alias anything but X.
+// the diagonal is zero): H^-1 = L^-T L^-1.  Out must not alias X nor anything another warp still reads.
 template <int NW, int MAXT>
 __device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* Out, const int (&tl)[MAXT], int lane,
                                        int warp) {
@@ -398,7 +397,6 @@ __device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* 
             for (int kk = ti[q] * 8; kk < nb * 8; kk += 4) dmma884(acc[q][0], acc[q][1], pa[kk], pb[kk]);
         }
     }
-    tsync<NW>();
 #pragma unroll
     for (int q = 0; q < MAXT; ++q) {
         if (warp + q * NW < ntl) {
@@ -955,47 +953,84 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                 if (ok && p > 0) {
                     for (int q = 0; q < p; ++q)          // HiAt = H^-1 A'                           :49
                         gemv_cols_v<NW>(H, ldh, n, n, At + q * npad, lane, warp, [&](int c, double acc) { HiAt[q * n + c] = acc; });
-                    for (int q = tid; q < f2_xsize(pb); q += T) MX[q] = 0.0;
+                    if (pb > 1) for (int q = tid; q < f2_xsize(pb); q += T) MX[q] = 0.0;
                     tsync<NW>();
-                    for (int j = 0; j < p; ++j)          // M = A HiAt                              :50
-                        gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, D::split_p(P), lane, warp,
-                                             [&](int r, double acc) { Mm[j * ldm + r] = acc; });
-                    tsync<NW>();
-                    ok = f2_chol_inv<NW>(Mm, MX, Dinv, descm, pb, ldm, &s_fail, lane, warp);        // :51
-                    if (ok) {
-                        for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
-                            const int i = q % p, j = q / p;
-                            double acc = 0.0;
-                            const double* xi = MX + f2_xbase(pb, i >> 3) + (i & 7) * f2_xld(pb, i >> 3) - (i & ~7);
-                            const double* xj = MX + f2_xbase(pb, j >> 3) + (j & 7) * f2_xld(pb, j >> 3) - (j & ~7);
-                            for (int m = max(i, j); m < p; ++m) acc = fma(xi[m], xj[m], acc);
-                            Minv[j * p + i] = acc;
+                    if (pb == 1) {
+                        // p <= 8: warp 0 alone forms M = A HiAt (:50), factors it (:51) and inverts it -- no team barrier
+                        if (warp == 0) {
+                            for (int e = 0; e < p * p; ++e) {
+                                const int i = e % p, j = e / p;
+                                double acc = 0.0;
+                                for (int c = lane; c < n; c += 32) acc = fma(A[c * p + i], HiAt[j * n + c], acc);
+                                acc = warp_sum(acc);
+                                if (lane == 0) Mm[j * ldm + i] = acc;
+                            }
+                            __syncwarp();
+                            double xc[8];
+                            const int okm = f2_diag_factor<false>(Mm, ldm, lane, xc);
+                            if (!okm && lane == 0) s_fail = 1;
+                            if (lane < 8) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) Dinv[i * 12 + lane] = xc[i];      // X = chol(M)^-1, row-major
+                            }
+                            __syncwarp();
+                            for (int e = lane; e < p * p; e += 32) {                        // Minv = X'X
+                                const int i = e % p, j = e / p;
+                                double acc = 0.0;
+                                for (int m = max(i, j); m < p; ++m) acc = fma(Dinv[m * 12 + i], Dinv[m * 12 + j], acc);
+                                Minv[j * p + i] = acc;
+                            }
                         }
                         tsync<NW>();
-                        for (int q = tid; q < n * p; q += T) {          // K = HiAt Minv
-                            const int i = q % n, j = q / n;
-                            double acc = 0.0;
-                            for (int r = 0; r < p; ++r) acc = fma(HiAt[r * n + i], Minv[j * p + r], acc);
-                            Km[j * n + i] = acc;
+                        ok = !s_fail;
+                    } else {
+                        for (int j = 0; j < p; ++j)          // M = A HiAt                              :50
+                            gemv_rows<NW, false>(A, p, p, n, HiAt + j * n, 1, D::split_p(P), lane, warp,
+                                                 [&](int r, double acc) { Mm[j * ldm + r] = acc; });
+                        tsync<NW>();
+                        ok = f2_chol_inv<NW>(Mm, MX, Dinv, descm, pb, ldm, &s_fail, lane, warp);        // :51
+                        if (ok) {
+                            for (int q = tid; q < p * p; q += T) {          // Minv = MX' MX
+                                const int i = q % p, j = q / p;
+                                double acc = 0.0;
+                                const double* xi = MX + f2_xbase(pb, i >> 3) + (i & 7) * f2_xld(pb, i >> 3) - (i & ~7);
+                                const double* xj = MX + f2_xbase(pb, j >> 3) + (j & 7) * f2_xld(pb, j >> 3) - (j & ~7);
+                                for (int m = max(i, j); m < p; ++m) acc = fma(xi[m], xj[m], acc);
+                                Minv[j * p + i] = acc;
+                            }
+                            tsync<NW>();
+                        }
+                    }
+                    if (ok) {
+                        // K = HiAt Minv, md = Minv dy, kd = K dy and Pm = H^-1 - K HiAt' (in place): then cx = Pm n0 + kd,
+                        // cy = K'n0 - md, which is src/densesolver.jl:73-83 (m0 = A H^-1 n0 - dy, cy = M^-1 m0,
+                        // cx = H^-1 (n0 - A'cy)) in one pass.  Every lane keeps the rows of K it needs in registers.
+                        for (int r0 = 0; r0 < n; r0 += 32) {
+                            const int r = r0 + lane;
+                            for (int q = 0; q < p; ++q) {
+                                double kq = 0.0;
+                                if (r < n)
+                                    for (int t = 0; t < p; ++t) kq = fma(HiAt[t * n + r], Minv[q * p + t], kq);
+                                for (int col = warp; col < n; col += NW)
+                                    if (r < n) H[col * ldh + r] = fma(-kq, HiAt[q * n + col], H[col * ldh + r]);
+                                if (warp == 0 && r < n) Km[q * n + r] = kq;
+                            }
                         }
                         for (int i = tid; i < p; i += T) {              // md = Minv dy
                             double acc = 0.0;
                             for (int r = 0; r < p; ++r) acc = fma(Minv[r * p + i], dy[r], acc);
                             md[i] = acc;
                         }
-                        tsync<NW>();
-                        // Pm = H^-1 - K HiAt' (in place) and kd = K dy: then cx = Pm n0 + kd, cy = K'n0 - md, which is
-                        // src/densesolver.jl:73-83 (m0 = A H^-1 n0 - dy, cy = M^-1 m0, cx = H^-1 (n0 - A'cy)) in one pass
-                        for (int col = warp; col < n; col += NW)
-                            for (int r = lane; r < n; r += 32) {
-                                double acc = H[col * ldh + r];
-                                for (int q = 0; q < p; ++q) acc = fma(-Km[q * n + r], HiAt[q * n + col], acc);
-                                H[col * ldh + r] = acc;
+                        if (warp == NW - 1) {                           // kd = K dy = HiAt (Minv dy)
+                            for (int i = lane; i < n; i += 32) {
+                                double acc = 0.0;
+                                for (int q = 0; q < p; ++q) {
+                                    double mq = 0.0;
+                                    for (int r = 0; r < p; ++r) mq = fma(Minv[r * p + q], dy[r], mq);
+                                    acc = fma(HiAt[q * n + i], mq, acc);
+                                }
+                                kd[i] = acc;
                             }
-                        for (int i = tid; i < n; i += T) {
-                            double acc = 0.0;
-                            for (int q = 0; q < p; ++q) acc = fma(Km[q * n + i], dy[q], acc);
-                            kd[i] = acc;
                         }
                     }
                 }
