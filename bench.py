@@ -329,6 +329,12 @@ def main():
         achieved = flops_step * args.steps / (dev_ms * 1e-3) / 1e12
         bytes_step = B * (8.0 * (k * n + p * n + n + p + k) + 8.0 * (n + p + 2 * k) + 24.0)
         hbm_ach = bytes_step * args.steps / (dev_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(args.config)
+            if t and t.get("problems_per_launch") == B and path_used == 2:
+                traffic = t["dram_bytes"]
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -352,7 +358,7 @@ def main():
                            "streams) -> pinned host results; wall clock between barriers, max over ranks"},
             "gpu_launches": int(total_launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
+                         "frac": achieved / fp64_peak, "traffic": traffic,
                          "peak_source": "FP64: cuBLAS DGEMM 4096^3 through torch.matmul, best of 10, measured in this run "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_step": flops_step, "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak,

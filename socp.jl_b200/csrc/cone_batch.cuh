@@ -87,7 +87,7 @@ __device__ __forceinline__ void b_for_each_poc(const BLayout& L, int batch, F f)
 
 // ---------------------------------------------------------------------------------------------- compute_scaling
 // reference src/scalings.jl:22-30 (POC), :32-99 (SOC).  eta: [batch][4][nwork] = eta, 1/eta, 1/eta^2, 1/(1+wbar0).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bk_scaling(BLayout L, int batch, const double* __restrict__ s, const double* __restrict__ z, double* __restrict__ lam,
            double* __restrict__ wb, double* __restrict__ iwb, double* __restrict__ eta, int* __restrict__ fail,
            const int* __restrict__ active) {
@@ -148,7 +148,7 @@ bk_scaling(BLayout L, int batch, const double* __restrict__ s, const double* __r
 // ---------------------------------------------------------------------------------------------- scale! / iscale! / W^-2
 // reference src/scalings.jl:112-156, src/densesolver.jl:86.  MODE as ApplyMode of cone_ops.cuh.
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bk_apply(BLayout L, int batch, const double* __restrict__ wb, const double* __restrict__ iwb,
          const double* __restrict__ eta, const double* __restrict__ v, double* __restrict__ out) {
     b_for_each_poc(L, batch, [&](int b, int i) {
@@ -188,7 +188,7 @@ bk_apply(BLayout L, int batch, const double* __restrict__ wb, const double* __re
 
 // ---------------------------------------------------------------------------------------------- vprod! / iprod!
 // reference src/vectors.jl:58-81, :99-131
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bk_vprod(BLayout L, int batch, const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ t) {
     b_for_each_poc(L, batch, [&](int b, int i) {
         const size_t o = (size_t)b * L.k + i;
@@ -206,7 +206,7 @@ bk_vprod(BLayout L, int batch, const double* __restrict__ u, const double* __res
         if (l.g == 0) t[o + l.offs] = acc + u0 * v0;                       // :66-69
     });
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bk_iprod(BLayout L, int batch, const double* __restrict__ lam, const double* __restrict__ v, double* __restrict__ t) {
     b_for_each_poc(L, batch, [&](int b, int i) {
         const size_t o = (size_t)b * L.k + i;
@@ -240,7 +240,7 @@ __device__ __forceinline__ BLane b_lane_seg(const BLayout& L, int b, bool bvalid
     const int grp = sl / L.lpc;
     return b_lane(L, (long long)b * L.nsoc + grp, bvalid && grp < L.nsoc ? (long long)(b + 1) * L.nsoc : 0, sl);
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bk_max_step(BLayout L, int batch, int sw, const double* __restrict__ x, double* __restrict__ out) {
     const int lane = threadIdx.x & 31, sl = lane & (sw - 1);
     const int b = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / sw) + lane / sw;
@@ -272,7 +272,7 @@ __device__ __forceinline__ double b_scmax(const BLayout& L, const BLane& l, cons
     q = b_gsum(q, L.lpc);
     return l.valid ? fast_sqrt(q) - a * r1 : -INFINITY;     // :85
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bk_compute_step(BLayout L, int batch, int sw, const double* __restrict__ lam, const double* __restrict__ ds,
                 const double* __restrict__ dz, double* __restrict__ out) {
     const int lane = threadIdx.x & 31, sl = lane & (sw - 1);

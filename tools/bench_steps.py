@@ -28,7 +28,7 @@ sb.compute_scaling(prob.cones, ss.scaling, s, z)
 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 fp64 = float(os.environ.get("FP64_PEAK_TFLOPS", "35.3"))     # cuBLAS DGEMM measured by bench.py on this pool
 spec = {  # which: (name, bytes per problem, flops per problem)   SURVEY.md section 8(d)
-    0: ("compute_scaling", 32 * k + 8 * N + 8 * k, 0), 1: ("scale!", 24 * k, 0), 2: ("iscale!", 24 * k, 0), 3: ("vprod!", 24 * k, 0),
+    0: ("compute_scaling", 32 * k + 8 * N, 0), 1: ("scale!", 24 * k, 0), 2: ("iscale!", 24 * k, 0), 3: ("vprod!", 24 * k, 0),
     4: ("iprod!", 24 * k, 0), 5: ("compute_step", 24 * k, 0), 6: ("Gt = W^-1 G", 16 * k * n, 0),
     7: ("SYRK Gt'Gt", 8 * k * n + 4 * n * (n + 1), n * (n + 1) * k), 8: ("Cholesky", 8 * n * n, n ** 3 / 3.0),
     9: ("L L' solve (1 rhs)", 8 * n * n, 2 * n * n), 10: ("G'v", 8 * k * n, 2 * k * n), 11: ("G v", 8 * k * n, 2 * k * n)}
