@@ -1,7 +1,8 @@
 // linalg.cuh -- batched dense FP64 kernels of the tiled (global-memory) path:
-// gemv, SYRK on the DMMA tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4),
-// blocked right-looking Cholesky (panel kernel + DMMA trailing update) and
-// blocked triangular solves.  Column-major everywhere, batch = slowest index.
+// gemv and SYRK on the DMMA tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4); the
+// SYRK is also the trailing update of the blocked right-looking Cholesky whose panel
+// kernels and triangular solves live in panel_mma.cuh.  Column-major everywhere,
+// batch = slowest index.
 //
 // They replace the LAPACK/BLAS calls of the reference's dense back end:
 // mul! (src/densesolver.jl:42-43,49-50,66,73,83-86), cholesky! (:47,:51) and
@@ -271,199 +272,6 @@ k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
         }
 }
 
-// ---------------------------------------------------------------------------
-// Blocked Cholesky, panel step (lower, in place, column-major, ld = ldh), for the
-// panel starting at column j (width jb = min(NB, n-j)), as TWO kernels so that no
-// CTA reads the diagonal block while another one overwrites it:
-//   k_potrf_diag : one CTA per problem factors the jb x jb diagonal block in shared
-//                  memory and writes L11 back; fail[b] |= 1 on a pivot that is not
-//                  > 0 (LAPACK dpotrf's info > 0, Julia's PosDefException, reference
-//                  src/densesolver.jl:47,51).            grid (batch), block 128
-//   k_trsm_panel : CTA x owns rows j+NB+128x .. +128 of the sub-panel and solves
-//                  L21 = A21 L11^-T, one thread per row (row in registers).
-//                                          grid (ceil((n-j-NB)/128), batch), block 128
-// ---------------------------------------------------------------------------
-constexpr int CHOL_NB = 64;
-
-__global__ void __launch_bounds__(128)
-k_potrf_diag(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, int* __restrict__ fail,
-             const int* __restrict__ active) {
-    constexpr int NB = CHOL_NB;
-    const int b = blockIdx.x;
-    if (active && !active[b]) return;
-    __shared__ double D[NB][NB + 1];
-    __shared__ int sfail;
-    double* Hb = H + (int64_t)b * strideH;
-    const int jb = min(NB, n - j);
-    const int tid = threadIdx.x;
-    if (tid == 0) sfail = 0;
-    for (int c = tid >> 6; c < jb; c += 2) {
-        const int r = tid & 63;
-        if (r < jb) D[r][c] = (r >= c) ? Hb[(int64_t)(j + c) * ldh + j + r] : 0.0;
-    }
-    __syncthreads();
-    for (int c = 0; c < jb; ++c) {
-        const double piv = D[c][c];
-        if (!(piv > 0.0)) {            // uniform across the CTA
-            if (tid == 0) sfail = 1;
-            break;
-        }
-        const double rdiag = sqrt(piv);
-        const double idiag = 1.0 / rdiag;
-        __syncthreads();               // everyone has read D[c][c]
-        for (int r = c + tid; r < jb; r += 128) D[r][c] = (r == c) ? rdiag : D[r][c] * idiag;
-        __syncthreads();
-        // trailing update of the lower triangle: (r, cc) with c < cc <= r < jb; lane -> row, thread group -> column
-        {
-            const int r = c + 1 + (tid & 63);
-            if (r < jb) {
-                const double lr = D[r][c];
-                for (int cc = c + 1 + (tid >> 6); cc <= r; cc += 2) D[r][cc] = fma(-lr, D[cc][c], D[r][cc]);
-            }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    if (sfail) {
-        if (tid == 0) fail[b] = 1;
-        return;
-    }
-    for (int c = tid >> 6; c < jb; c += 2) {
-        const int r = tid & 63;
-        if (r < jb && r >= c) Hb[(int64_t)(j + c) * ldh + j + r] = D[r][c];
-    }
-}
-
-__global__ void __launch_bounds__(128)
-k_trsm_panel(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const int* __restrict__ fail,
-             const int* __restrict__ active) {
-    constexpr int NB = CHOL_NB;
-    const int b = blockIdx.y;
-    if (active && !active[b]) return;
-    if (fail[b]) return;               // the factorisation already failed: leave the rest alone
-    __shared__ double D[NB][NB + 1];
-    double* Hb = H + (int64_t)b * strideH;
-    const int tid = threadIdx.x;
-    for (int c = tid >> 6; c < NB; c += 2) {
-        const int r = tid & 63;
-        D[r][c] = (r >= c) ? Hb[(int64_t)(j + c) * ldh + j + r] : 0.0;
-    }
-    __syncthreads();
-    const int row = j + NB + blockIdx.x * 128 + tid;
-    if (row >= n) return;
-    double a[NB];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) a[c] = Hb[(int64_t)(j + c) * ldh + row];
-#pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        double v = a[c];
-#pragma unroll
-        for (int q = 0; q < c; ++q) v = fma(-a[q], D[c][q], v);
-        a[c] = v / D[c][c];
-    }
-#pragma unroll
-    for (int c = 0; c < NB; ++c) Hb[(int64_t)(j + c) * ldh + row] = a[c];
-}
-
-// ---------------------------------------------------------------------------
-// Triangular solves with the Cholesky factor, in place on X (n x nrhs, ld = ldx):
-//   k_trsv_fwd:  X <- L^-1 X        k_trsv_bwd:  X <- L^-T X
-// One CTA (256 threads) per (rhs, problem); the right-hand side lives in shared
-// memory (n doubles, dynamic).  Blocks of 32: the diagonal block is solved by
-// warp 0 with shuffles; the off-diagonal part is a coalesced gemv.
-// grid (nrhs, batch), dynamic smem = n * 8.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_trsv_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n,
-           double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
-    const int b = blockIdx.y;
-    if (active && !active[b]) return;
-    extern __shared__ double xs[];
-    const double* Lb = L + (int64_t)b * strideL;
-    double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
-    __syncthreads();
-    for (int jb = 0; jb < n; jb += 32) {
-        const int w = min(32, n - jb);
-        if (warp == 0) {
-            // lane i owns row jb+i of the diagonal block
-            double lrow[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                lrow[c] = (lane < w && c <= lane && c < w) ? Lb[(int64_t)(jb + c) * ldl + jb + lane] : 0.0;
-            double x = (lane < w) ? xs[jb + lane] : 0.0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                if (lane == c && c < w) x = x / lrow[c];
-                const double xc = __shfl_sync(FULL_MASK, x, c);
-                if (lane > c && lane < w) x = fma(-lrow[c], xc, x);
-            }
-            if (lane < w) xs[jb + lane] = x;
-        }
-        __syncthreads();
-        // rows below the block: xs[r] -= sum_c L[r, jb+c] xs[jb+c]
-        for (int r = jb + 32 + tid; r < n; r += 256) {
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < 32; c += 2) {
-                acc0 = fma(Lb[(int64_t)(jb + c) * ldl + r], xs[jb + c], acc0);
-                acc1 = fma(Lb[(int64_t)(jb + c + 1) * ldl + r], xs[jb + c + 1], acc1);
-            }
-            xs[r] -= acc0 + acc1;
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
-}
-
-__global__ void __launch_bounds__(256)
-k_trsv_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n,
-           double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
-    const int b = blockIdx.y;
-    if (active && !active[b]) return;
-    extern __shared__ double xs[];
-    const double* Lb = L + (int64_t)b * strideL;
-    double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
-    __syncthreads();
-    const int nblk = (n + 31) / 32;
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        const int jb = blk * 32;
-        const int w = min(32, n - jb);
-        // left-looking: xs[jb+i] -= sum_{r >= jb+32} L[r, jb+i] xs[r]; warp per column
-        for (int i = warp; i < w; i += 8) {
-            const double* col = Lb + (int64_t)(jb + i) * ldl;
-            double acc0 = 0.0, acc1 = 0.0;
-            int r = jb + 32 + lane;
-            for (; r + 32 < n; r += 64) {
-                acc0 = fma(col[r], xs[r], acc0);
-                acc1 = fma(col[r + 32], xs[r + 32], acc1);
-            }
-            for (; r < n; r += 32) acc0 = fma(col[r], xs[r], acc0);
-            const double acc = warp_sum(acc0 + acc1);
-            if (lane == 0) xs[jb + i] -= acc;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // diagonal block, transposed: lane i needs L[jb+c, jb+i] for c >= i
-            double lcol[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-                lcol[c] = (lane < w && c >= lane && c < w) ? Lb[(int64_t)(jb + lane) * ldl + jb + c] : 0.0;
-            double x = (lane < w) ? xs[jb + lane] : 0.0;
-#pragma unroll
-            for (int c = 31; c >= 0; --c) {
-                if (lane == c && c < w) x = x / lcol[c];
-                const double xc = __shfl_sync(FULL_MASK, x, c);
-                if (lane < c && c < w) x = fma(-lcol[c], xc, x);
-            }
-            if (lane < w) xs[jb + lane] = x;
-        }
-        __syncthreads();
-    }
-    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
-}
+constexpr int CHOL_NB = 64;      // panel width of the blocked Cholesky (panel kernels: panel_mma.cuh)
 
 }  // namespace socp

@@ -19,8 +19,10 @@ namespace socp {
 constexpr int PANEL_LDH = 68;                                   // 64 + 4: conflict-free fragment loads
 constexpr size_t POTRF_MMA_SMEM = sizeof(double) * (64 * PANEL_LDH + f2_xsize(8) + 192) + sizeof(uint2) * f2_trail_base(8, 8);
 
+// Xinv: [batch][nblk][64*64], block j/64 of problem b receives the inverse of its diagonal block (dense column-major,
+// zero above the diagonal; a partial last block is padded with the identity).
 __global__ void __launch_bounds__(256)
-k_potrf_diag_mma(double* __restrict__ H, int64_t strideH, int ldh, int j, double* __restrict__ Xd,
+k_potrf_diag_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, double* __restrict__ Xinv, int nblk,
                  int* __restrict__ fail, const int* __restrict__ active) {
     const int b = blockIdx.x;
     if (active && !active[b]) return;
@@ -32,10 +34,14 @@ k_potrf_diag_mma(double* __restrict__ H, int64_t strideH, int ldh, int j, double
     uint2* desc = reinterpret_cast<uint2*>(Dinv + 192);
     double* Hb = H + (int64_t)b * strideH + (int64_t)j * ldh + j;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jb = min(64, n - j);
     if (tid == 0) sfail = 0;
     for (int q = tid; q < 64 * 64; q += 256) {
         const int c = q >> 6, r = q & 63;
-        Hs[c * PANEL_LDH + r] = (r >= c) ? Hb[(int64_t)c * ldh + r] : 0.0;
+        double v = 0.0;
+        if (r < jb && c < jb) v = (r >= c) ? Hb[(int64_t)c * ldh + r] : 0.0;
+        else if (r == c) v = 1.0;
+        Hs[c * PANEL_LDH + r] = v;
     }
     for (int q = tid; q < f2_xsize(8) + 192; q += 256) Xs[q] = 0.0;
     f2_build_trail(desc, 8, PANEL_LDH, 64 * PANEL_LDH, tid, 256);
@@ -45,10 +51,10 @@ k_potrf_diag_mma(double* __restrict__ H, int64_t strideH, int ldh, int j, double
         if (tid == 0) fail[b] = 1;
         return;
     }
-    double* Xb = Xd + (int64_t)b * 64 * 64;
+    double* Xb = Xinv + ((int64_t)b * nblk + j / 64) * 64 * 64;
     for (int q = tid; q < 64 * 64; q += 256) {
         const int c = q >> 6, r = q & 63;
-        if (r >= c) Hb[(int64_t)c * ldh + r] = Hs[c * PANEL_LDH + r];
+        if (r >= c && r < jb) Hb[(int64_t)c * ldh + r] = Hs[c * PANEL_LDH + r];
         const int cb = c >> 3;
         Xb[q] = (r >= cb * 8) ? Xs[f2_xbase(8, cb) + (c & 7) * f2_xld(8, cb) + r - cb * 8] : 0.0;
     }
@@ -58,7 +64,7 @@ constexpr int TRSM_LDA = 132;                                   // 128 + 4
 constexpr size_t TRSM_MMA_SMEM = sizeof(double) * (64 * PANEL_LDH + 64 * TRSM_LDA);
 
 __global__ void __launch_bounds__(256)
-k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const double* __restrict__ Xd,
+k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const double* __restrict__ Xinv, int nblk,
            const int* __restrict__ fail, const int* __restrict__ active) {
     const int b = blockIdx.y;
     if (active && !active[b]) return;
@@ -70,7 +76,7 @@ k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const
     const int row0 = j + 64 + blockIdx.x * 128;
     const int nrow = min(128, n - row0);
     double* Hb = H + (int64_t)b * strideH;
-    const double* Xb = Xd + (int64_t)b * 64 * 64;
+    const double* Xb = Xinv + ((int64_t)b * nblk + j / 64) * 64 * 64;
     for (int q = tid; q < 64 * 64; q += 256) Xs[(q >> 6) * PANEL_LDH + (q & 63)] = Xb[q];
     for (int q = tid; q < 64 * 128; q += 256) {
         const int c = q >> 7, r = q & 127;
@@ -107,6 +113,107 @@ k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const
                 for (int e = 0; e < 2; ++e) Hb[(int64_t)(j + ct * 8 + 2 * fk + e) * ldh + row0 + r] = acc[rt][ct][e];
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Triangular solves with the factor and the inverted 64 x 64 diagonal blocks kept by k_potrf_diag_mma:
+//   k_trsv_blk_fwd:  X <- L^-1 X        k_trsv_blk_bwd:  X <- L^-T X        (in place, n x nrhs, ld = ldx)
+// One CTA (256 threads) per (rhs, problem), the right-hand side in shared memory.  Per 64-block: a 64 x 64 gemv
+// with the inverted block (no serial substitution chain) and a gemv with the panel below it.
+// grid (nrhs, batch), dynamic smem = (n + 64) * 8.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_trsv_blk_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, const double* __restrict__ Xinv,
+               int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    extern __shared__ double tsm[];
+    double* xs = tsm;
+    double* ys = tsm + n;
+    const double* Lb = L + (int64_t)b * strideL;
+    const double* Xi = Xinv + ((int64_t)b * nblk + blk0) * 4096;
+    double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
+    __syncthreads();
+    for (int jb = 0; jb < n; jb += 64) {
+        const int w = min(64, n - jb);
+        const double* Xb = Xi + (int64_t)(jb >> 6) * 4096;
+        {   // ys = Xbb xs[jb .. jb+w): 4 threads per row, 16 columns each
+            const int r = tid >> 2, q = tid & 3;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int c = q * 16; c < q * 16 + 16; ++c)
+                if (c <= r && c < w) acc = fma(Xb[c * 64 + r], xs[jb + c], acc);
+            acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+            acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+            if (q == 0) ys[r] = acc;
+        }
+        __syncthreads();
+        for (int r = jb + 64 + tid; r < n; r += 256) {      // rows below: xs[r] -= L[r, jb..jb+64) ys
+            const double* lp = Lb + (int64_t)jb * ldl + r;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < 64; c += 4) {
+                a0 = fma(lp[(int64_t)c * ldl], ys[c], a0);
+                a1 = fma(lp[(int64_t)(c + 1) * ldl], ys[c + 1], a1);
+                a2 = fma(lp[(int64_t)(c + 2) * ldl], ys[c + 2], a2);
+                a3 = fma(lp[(int64_t)(c + 3) * ldl], ys[c + 3], a3);
+            }
+            xs[r] -= (a0 + a1) + (a2 + a3);
+        }
+        if (tid < w) xs[jb + tid] = ys[tid];
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
+}
+
+__global__ void __launch_bounds__(256)
+k_trsv_blk_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, const double* __restrict__ Xinv,
+               int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
+    const int b = blockIdx.y;
+    if (active && !active[b]) return;
+    extern __shared__ double tsm[];
+    double* xs = tsm;
+    double* ts = tsm + n;
+    const double* Lb = L + (int64_t)b * strideL;
+    const double* Xi = Xinv + ((int64_t)b * nblk + blk0) * 4096;
+    double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
+    __syncthreads();
+    for (int jb = ((n - 1) >> 6) << 6; jb >= 0; jb -= 64) {
+        const int w = min(64, n - jb);
+        const double* Xb = Xi + (int64_t)(jb >> 6) * 4096;
+        // ts[c] = xs[jb+c] - sum_{r >= jb+64} L[r, jb+c] xs[r]: warp per column, lanes over the rows below
+        for (int c = warp; c < 64; c += 8) {
+            double a0 = 0.0, a1 = 0.0;
+            if (c < w) {
+                const double* col = Lb + (int64_t)(jb + c) * ldl;
+                int r = jb + 64 + lane;
+                for (; r + 32 < n; r += 64) {
+                    a0 = fma(col[r], xs[r], a0);
+                    a1 = fma(col[r + 32], xs[r + 32], a1);
+                }
+                if (r < n) a0 = fma(col[r], xs[r], a0);
+            }
+            const double acc = warp_sum(a0 + a1);
+            if (lane == 0) ts[c] = (c < w) ? xs[jb + c] - acc : 0.0;
+        }
+        __syncthreads();
+        {   // xs[jb+c] = sum_{r >= c} Xbb[r, c] ts[r]: 4 threads per column, 16 rows each
+            const int c = tid >> 2, q = tid & 3;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int r = q * 16; r < q * 16 + 16; ++r)
+                if (r >= c && r < w) acc = fma(Xb[c * 64 + r], ts[r], acc);
+            acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+            acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+            if (q == 0 && c < w) xs[jb + c] = acc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
 }
 
 }  // namespace socp

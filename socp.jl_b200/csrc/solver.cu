@@ -172,53 +172,50 @@ void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, i
     }
 }
 
-// blocked Cholesky of `nn x nn` matrices (ld, stride), lower, in place.  Full 64-column panels go through the DMMA
-// panel kernels (panel_mma.cuh); a narrower last panel through the scalar ones.
-void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, int* fail, const int* active) {
+// blocked Cholesky of `nn x nn` matrices (ld, stride), lower, in place, through the DMMA panel kernels
+// (panel_mma.cuh).  Xinv ([batch][ceil(nn/64)][64*64]) receives the inverted diagonal blocks for the solves.
+void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* fail, const int* active) {
     static bool configured[64] = {};
     if (!configured[sh.device]) {
         CK(cudaFuncSetAttribute(k_potrf_diag_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_MMA_SMEM));
         CK(cudaFuncSetAttribute(k_trsm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_MMA_SMEM));
+        CK(cudaFuncSetAttribute(k_trsv_blk_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_trsv_blk_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
         configured[sh.device] = true;
     }
+    const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
     for (int j = 0; j < nn; j += CHOL_NB) {
         const int below = nn - j - CHOL_NB;
-        const bool mma = (nn - j >= CHOL_NB) && sh.w.Xd != nullptr;
-        if (mma) LAUNCH(sh, k_potrf_diag_mma, sh.batch, 256, POTRF_MMA_SMEM, H, sH, ld, j, sh.w.Xd, fail, active);
-        else LAUNCH(sh, k_potrf_diag, sh.batch, 128, 0, H, sH, ld, nn, j, fail, active);
+        LAUNCH(sh, k_potrf_diag_mma, sh.batch, 256, POTRF_MMA_SMEM, H, sH, ld, nn, j, Xinv, nblk, fail, active);
         if (below > 0) {
-            if (mma) {
-                dim3 grid((below + 127) / 128, sh.batch);
-                LAUNCH(sh, k_trsm_mma, grid, 256, TRSM_MMA_SMEM, H, sH, ld, nn, j, (const double*)sh.w.Xd, (const int*)fail, active);
-            } else {
-                dim3 grid((below + 127) / 128, sh.batch);
-                LAUNCH(sh, k_trsm_panel, grid, 128, 0, H, sH, ld, nn, j, (const int*)fail, active);
-            }
+            dim3 grid((below + 127) / 128, sh.batch);
+            LAUNCH(sh, k_trsm_mma, grid, 256, TRSM_MMA_SMEM, H, sH, ld, nn, j, (const double*)Xinv, nblk, (const int*)fail, active);
             const double* P = H + (int64_t)j * ld + (j + CHOL_NB);
             double* T = H + (int64_t)(j + CHOL_NB) * ld + (j + CHOL_NB);
             syrk(sh, false, P, sH, ld, below, CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active);
         }
     }
 }
-// X <- (L L')^-1 X, X is nn x nrhs (ld ldx).  Up to 1024 rows one CTA per (rhs, problem) walks the whole factor;
-// beyond that the factor is cut into diagonal blocks of 512 solved the same way, with the off-diagonal panels
-// applied by the batch-wide gemv kernels (many CTAs) in between -- a single CTA streaming a 4096^2 factor would be
-// ~40x slower than the gemvs.
-void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, double* X, int64_t sX, int ldx, int nrhs,
-           const int* active) {
+// X <- (L L')^-1 X, X is nn x nrhs (ld ldx), with the inverted diagonal blocks of potrf.  Up to 1024 rows one CTA
+// per (rhs, problem) walks the whole factor; beyond that the factor is cut into diagonal blocks of 512 solved the
+// same way, with the off-diagonal panels applied by the batch-wide gemv kernels (many CTAs) in between -- a single
+// CTA streaming a 4096^2 factor would be far slower than the gemvs.
+void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, const double* Xinv, double* X, int64_t sX, int ldx,
+           int nrhs, const int* active) {
     if (nn == 0 || nrhs == 0) return;
     constexpr int BS = 512;
+    const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
+    dim3 grid(nrhs, sh.batch);
     if (nn <= 2 * BS) {
-        dim3 grid(nrhs, sh.batch);
-        const size_t smem = (size_t)nn * sizeof(double);
-        LAUNCH(sh, k_trsv_fwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
-        LAUNCH(sh, k_trsv_bwd, grid, 256, smem, L, sL, ld, nn, X, sX, ldx, active);
+        const size_t smem = (size_t)(nn + 64) * sizeof(double);
+        LAUNCH(sh, k_trsv_blk_fwd, grid, 256, smem, L, sL, ld, nn, Xinv, nblk, 0, X, sX, ldx, active);
+        LAUNCH(sh, k_trsv_blk_bwd, grid, 256, smem, L, sL, ld, nn, Xinv, nblk, 0, X, sX, ldx, active);
         return;
     }
-    dim3 grid(nrhs, sh.batch);
     for (int jb = 0; jb < nn; jb += BS) {                       // forward: L y = x
         const int bs = std::min(BS, nn - jb), below = nn - jb - bs;
-        LAUNCH(sh, k_trsv_fwd, grid, 256, (size_t)bs * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, X + jb, sX, ldx, active);
+        LAUNCH(sh, k_trsv_blk_fwd, grid, 256, (size_t)(bs + 64) * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, Xinv,
+               nblk, jb / CHOL_NB, X + jb, sX, ldx, active);
         for (int q = 0; q < nrhs && below > 0; ++q)
             gemv_n(sh, L + (int64_t)jb * ld + jb + bs, sL, ld, below, bs, X + (int64_t)q * ldx + jb, sX,
                    X + (int64_t)q * ldx + jb + bs, sX, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
@@ -228,7 +225,8 @@ void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, double* X, in
         for (int q = 0; q < nrhs && below > 0; ++q)
             gemv_t(sh, L + (int64_t)jb * ld + jb + bs, sL, ld, below, bs, X + (int64_t)q * ldx + jb + bs, sX,
                    X + (int64_t)q * ldx + jb, sX, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
-        LAUNCH(sh, k_trsv_bwd, grid, 256, (size_t)bs * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, X + jb, sX, ldx, active);
+        LAUNCH(sh, k_trsv_blk_bwd, grid, 256, (size_t)(bs + 64) * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, Xinv,
+               nblk, jb / CHOL_NB, X + jb, sX, ldx, active);
     }
 }
 
@@ -284,14 +282,14 @@ void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
     const bool aa = add_aa && p > 0 && sh.any_sing;
     syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0,
          aa ? w.AA : nullptr, (int64_t)w.ldh * n, w.ldh, w.sing, active);
-    potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, active);
+    potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, active);
     if (p > 0) {
         dim3 gt(std::max(1, std::min(64, (p * n + 255) / 256)), sh.batch);
         LAUNCH(sh, k_transpose_A, gt, 256, 0, w.A, w.sA, p, n, w.HiAt, active);
-        potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.HiAt, (int64_t)n * p, n, p, active);
+        potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.HiAt, (int64_t)n * p, n, p, active);
         dim3 gm(std::max(1, std::min(64, (p * p + 255) / 256)), sh.batch);
         LAUNCH(sh, k_small_gemm, gm, 256, 0, w.A, w.sA, p, n, w.HiAt, w.M, w.ldm, active);
-        potrf(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.fail, active);
+        potrf(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.XM, w.fail, active);
     }
 }
 
@@ -305,11 +303,11 @@ void kkt_middle(Shard& sh, const int* active) {
     if (p > 0 && sh.any_sing)
         gemv_t(sh, w.A, w.sA, p, p, n, w.dy, p, w.rx, n, 1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active, w.sing);
     // t = H^-1 n0
-    potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.rx, n, n, 1, active);
+    potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.rx, n, n, 1, active);
     if (p > 0) {
         // m0 = A t - dy; cy = M^-1 m0                                     :73-75
         gemv_n(sh, w.A, w.sA, p, p, n, w.rx, n, w.ry, p, 1.0, epi(w.dy, -1.0, p), active);
-        potrs(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.ry, p, p, 1, active);
+        potrs(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.XM, w.ry, p, p, 1, active);
         // cx = H^-1 (n0 + A'(sing ? dy - cy : -cy)) = t - HiAt cy (+ HiAt dy if sing)   :76-83
         gemv_n(sh, w.HiAt, (int64_t)n * p, n, n, p, w.ry, p, w.rx, n, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
         if (sh.any_sing)
@@ -333,10 +331,10 @@ void initial_point(Shard& sh, const LoopParams& P) {
     gemv_t(sh, w.G, w.sG, k, k, n, w.h, k, w.x, n, 1.0, epi(w.c, -1.0, n), w.active);
     if (p > 0 && sh.any_sing)
         gemv_t(sh, w.A, w.sA, p, p, n, w.b, p, w.x, n, 1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), w.active, w.sing);
-    potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.x, n, n, 1, w.active);          // t = H^-1 n0
+    potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.x, n, n, 1, w.active);          // t = H^-1 n0
     if (p > 0) {
         gemv_n(sh, w.A, w.sA, p, p, n, w.x, n, w.y, p, 1.0, epi(w.b, -1.0, p), w.active);   // A t - b
-        potrs(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.y, p, p, 1, w.active);       // y
+        potrs(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.XM, w.y, p, p, 1, w.active);       // y
         gemv_n(sh, w.HiAt, (int64_t)n * p, n, n, p, w.y, p, w.x, n, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), w.active);
     }
     gemv_n(sh, w.G, w.sG, k, k, n, w.x, n, w.z, k, 1.0, epi(w.h, -1.0, k), w.active);       // z0 = G x - h
@@ -462,7 +460,8 @@ void ensure_tiled(Shard& sh) {
     w.M = sh.alloc<double>((size_t)B * w.ldm * p);
     w.AA = sh.alloc<double>((size_t)B * w.ldh * n * (p > 0 ? 1 : 0));
     w.Ap = sh.alloc<double>((size_t)B * w.ldap * n * (p > 0 ? 1 : 0));
-    w.Xd = sh.alloc<double>((size_t)B * 64 * 64, false);
+    w.XH = sh.alloc<double>((size_t)B * ((n + 63) / 64) * 4096, false);
+    w.XM = sh.alloc<double>((size_t)B * ((p + 63) / 64) * 4096 * (p > 0 ? 1 : 0), false);
 }
 
 // AA = A'A (reference src/densesolver.jl:32) and, when the caller gave no
@@ -488,7 +487,7 @@ void prepare_problem(Shard& sh, bool have_sing) {
         LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 1, cols_per_cta, (const int*)nullptr);
         syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0,
              0, nullptr, nullptr);
-        potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr);
+        potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, nullptr);
         LAUNCH(sh, k_fail_to_sing, (B + 255) / 256, 256, 0, w.fail, sh.d_sing, B);
     }
     std::vector<uint8_t> hs(B);
@@ -1128,7 +1127,7 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
             }
             if (which == 9) {
                 CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
-                potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr);
+                potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, nullptr);
             }
         }
         double total = 0.0;
@@ -1152,8 +1151,8 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
                     break;
                 }
                 case 7: syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0, 0, nullptr, nullptr); break;
-                case 8: potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.fail, nullptr); break;
-                case 9: potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.rx, n, n, 1, nullptr); break;
+                case 8: potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, nullptr); break;
+                case 9: potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.rx, n, n, 1, nullptr); break;
                 case 10: gemv_t(sh, w.G, w.sG, k, k, n, w.z, k, w.dx, n, 1.0, epi(), nullptr); break;
                 default: gemv_n(sh, w.G, w.sG, k, k, n, w.x, n, w.dz, k, 1.0, epi(), nullptr); break;
             }

@@ -32,7 +32,7 @@ struct Ws {
     double *kt2, *kt3;
     // factor workspaces
     double *Gt, *H, *HiAt, *M, *AA, *Ap;
-    double* Xd;            // [batch][64][64] inverse of the current diagonal block of the blocked Cholesky
+    double *XH, *XM;       // [batch][ceil(n/64)][64*64] inverted diagonal blocks of the factors of H and M
     ProbScalars* sc;
     double *pobj, *dobj;   // [batch] objectives of the returned iterate
     int *status, *iters, *active, *fail;
