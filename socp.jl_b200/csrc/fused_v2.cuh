@@ -1280,16 +1280,17 @@ inline void fused2_launch(const F2Plan& plan, const F2Args& args, int grid, cuda
 }
 
 // Solves problems [first, first + batch) of the shard.
+// counter_slot: which of the plan's work counters this launch uses (launches that may overlap need different ones).
 inline void solve_fused2(F2Plan& plan, const Ws& g, int first, int batch, int max_iter, double tol, double step_damp,
-                         double init_eps, cudaStream_t stream, bool allow_static = true) {
-    cudaMemsetAsync(plan.d_counter, 0, sizeof(int), stream);
+                         double init_eps, cudaStream_t stream, bool allow_static = true, int counter_slot = 0) {
+    cudaMemsetAsync(plan.d_counter + counter_slot, 0, sizeof(int), stream);
     F2Args args;
     args.g = g;
     args.P = plan;
     args.prm = LoopParams{max_iter, tol, step_damp, init_eps};
     args.first = first;
     args.batch = batch;
-    args.counter = plan.d_counter;
+    args.counter = plan.d_counter + counter_slot;
     const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
     if (allow_static && DimsC2::matches(plan)) { fused2_launch<8, 4, 2, DimsC2>(plan, args, grid, stream); return; }
     if (allow_static && DimsC3::matches(plan)) { fused2_launch<1, 3, 16, DimsC3>(plan, args, grid, stream); return; }

@@ -52,6 +52,7 @@ struct Shard {
     int batch = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t up_stream = nullptr, down_stream = nullptr;     // H2D / D2H legs of the pipelined one-shot solve
+    cudaStream_t alt_stream = nullptr;                           // second compute stream: consecutive chunks backfill
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> allocs;
@@ -92,6 +93,7 @@ struct Shard {
             if (e) cudaEventDestroy(e);
         for (auto& e : pipe_ev) cudaEventDestroy(e);
         if (up_stream) cudaStreamDestroy(up_stream);
+        if (alt_stream) cudaStreamDestroy(alt_stream);
         if (down_stream) cudaStreamDestroy(down_stream);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -446,7 +448,7 @@ void build_shard(socp_handle* h, Shard& sh) {
         sh.bl_sw = std::min(sh.bl_sw, 32);
     }
     f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
-    sh.fused2.d_counter = sh.alloc<int>(1);
+    sh.fused2.d_counter = sh.alloc<int>(16);
     CK(cudaStreamSynchronize(sh.stream));
 }
 
@@ -625,15 +627,16 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     if (!sh.up_stream) {
         CK(cudaStreamCreateWithFlags(&sh.up_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&sh.down_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&sh.alt_stream, cudaStreamNonBlocking));
     }
     sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
     sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
     sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
     sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
     sh.any_sing = false;
-    // chunks of at least 8 waves of resident CTAs, at most 8 chunks
+    // chunks of at least 4 waves of resident CTAs, at most 8 chunks
     const int slots = sh.fused2.num_sms * sh.fused2.ctas_per_sm;
-    int nchunk = std::max(1, std::min(8, B / std::max(1, 8 * slots)));
+    int nchunk = std::max(1, std::min(8, B / std::max(1, 4 * slots)));
     const int per = (B + nchunk - 1) / nchunk;
     nchunk = (B + per - 1) / per;
     while ((int)sh.pipe_ev.size() < 2 * nchunk) {
@@ -650,8 +653,12 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     };
     CK(cudaEventRecord(sh.ev[0], sh.stream));
     CK(cudaStreamWaitEvent(sh.up_stream, sh.ev[0], 0));
+    CK(cudaStreamWaitEvent(sh.alt_stream, sh.ev[0], 0));
     sh.launches = 0;
+    // Consecutive chunks alternate between two compute streams: the persistent CTAs of chunk i+1 move in as those
+    // of chunk i run out of work, so there is no drain bubble between launches.
     for (int ci = 0; ci < nchunk; ++ci) {
+        cudaStream_t cs = (ci & 1) ? sh.alt_stream : sh.stream;
         const int lo = ci * per, cb = std::min(per, B - lo);
         const int64_t g0 = f + lo;
         up(sh.d_c + (size_t)lo * n, c + g0 * n, sizeof(double) * cb * n);
@@ -665,11 +672,11 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         else up(sh.d_G + (size_t)lo * k * n, G + g0 * (int64_t)k * n, sizeof(double) * cb * k * n);
         up(sh.d_sing + lo, sing + g0, cb);
         CK(cudaEventRecord(sh.pipe_ev[2 * ci], sh.up_stream));
-        CK(cudaStreamWaitEvent(sh.stream, sh.pipe_ev[2 * ci], 0));
-        solve_fused2(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream, allow_static);
+        CK(cudaStreamWaitEvent(cs, sh.pipe_ev[2 * ci], 0));
+        solve_fused2(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, cs, allow_static, ci & 15);
         CK(cudaGetLastError());
         sh.launches += 1;
-        CK(cudaEventRecord(sh.pipe_ev[2 * ci + 1], sh.stream));
+        CK(cudaEventRecord(sh.pipe_ev[2 * ci + 1], cs));
         CK(cudaStreamWaitEvent(sh.down_stream, sh.pipe_ev[2 * ci + 1], 0));
         if (x) down(x + g0 * n, sh.w.x + (size_t)lo * n, sizeof(double) * cb * n);
         if (y) down(y + g0 * p, sh.w.y + (size_t)lo * p, sizeof(double) * cb * p);
@@ -680,8 +687,10 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         if (pobj) down(pobj + g0, sh.w.pobj + lo, sizeof(double) * cb);
         if (dobj) down(dobj + g0, sh.w.dobj + lo, sizeof(double) * cb);
     }
+    if (nchunk > 1) CK(cudaStreamWaitEvent(sh.stream, sh.pipe_ev[2 * (nchunk - 1) + 1], 0));   // join the alternate stream
     CK(cudaEventRecord(sh.ev[1], sh.stream));
     CK(cudaStreamSynchronize(sh.up_stream));
+    CK(cudaStreamSynchronize(sh.alt_stream));
     CK(cudaStreamSynchronize(sh.stream));
     CK(cudaStreamSynchronize(sh.down_stream));
     float ms = 0;
