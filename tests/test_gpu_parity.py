@@ -304,3 +304,20 @@ def test_solve_host_pipelined_matches_two_step():
     for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
         assert np.array_equal(getattr(one, f), getattr(two, f)), f
     assert (one.status == sb.STATUS_CONVERGED).all()
+
+
+def test_multi_device_handle_matches_single_device():
+    """socp_b200_create(devices=[0, 1]) shards the batch contiguously over the devices of one process (no collective);
+    results must equal the single-device ones bit for bit (same kernels, same problems).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    prob = gen.make_config("C2", batch=301)           # odd split: 151 + 150
+    one = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0]))
+    two = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0, 1]))
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+        assert np.array_equal(getattr(one, f), getattr(two, f)), f
+    prob3 = gen.make_config("C3", batch=1000)
+    a = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[1]))
+    b = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[0, 1]))
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.x, b.x)
