@@ -145,6 +145,53 @@ bk_scaling(BLayout L, int batch, const double* __restrict__ s, const double* __r
     });
 }
 
+// ---------------------------------------------------------------------------------------------- Gt = W^-1 G
+// The scaled copy of G whose Gram matrix is the reduced KKT matrix (setup_iter, reference src/densesolver.jl:41-43):
+// iscale! (src/scalings.jl:119-124, :142-156) applied to every column of G.  One lane group per (problem, column,
+// cone); positive-orthant rows elementwise.  Gt: [batch][n][ldgt], rows >= k stay zero.
+__global__ void __launch_bounds__(256, 4)
+bk_build_gt(BLayout L, int batch, int n, const double* __restrict__ G, int64_t sG, const double* __restrict__ wb,
+            const double* __restrict__ iwb, const double* __restrict__ eta, double* __restrict__ Gt, int ldgt,
+            const int* __restrict__ active) {
+    {   // positive-orthant rows
+        const long long total = (long long)batch * n * L.kpoc;
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+            const int b = (int)(q / ((long long)n * L.kpoc));
+            const int rem = (int)(q - (long long)b * n * L.kpoc);
+            const int col = rem / L.kpoc, r = rem - col * L.kpoc;
+            if (active && !active[b]) continue;
+            Gt[((size_t)b * n + col) * ldgt + r] = iwb[(size_t)b * L.k + r] * G[(int64_t)b * sG + (int64_t)col * L.k + r];
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    const int spw = 32 / L.lpc;
+    const long long total = (long long)batch * n * L.nsoc;
+    const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long base = wglobal * spw; base < total; base += wstride * spw) {
+        const long long gid = base + lane / L.lpc;
+        const bool valid = gid < total;
+        const long long q = valid ? gid : 0;
+        const int b = (int)(q / ((long long)n * L.nsoc));
+        const int rem = (int)(q - (long long)b * n * L.nsoc);
+        const int col = rem / L.nsoc, slot = rem - col * L.nsoc;
+        const BLane l = b_lane(L, (long long)b * L.nsoc + slot, valid ? (long long)(b + 1) * L.nsoc : 0, lane);
+        const bool on = l.valid && !(active && !active[b]);
+        const double* gc = G + (int64_t)b * sG + (int64_t)col * L.k;
+        const double* wbb = wb + (size_t)b * L.k;
+        double wv[4], gv[4];
+        B_FOR_E { const bool t = on && l.tail(e); wv[e] = t ? wbb[l.at(e)] : 0.0; gv[e] = t ? gc[l.at(e)] : 0.0; }
+        const double dl = b_dot(wv, gv, L.lpc);                                      // src/scalings.jl:145-148
+        if (!on) continue;
+        const double* es = eta + (size_t)b * 4 * L.nwork + L.soc_work[slot];
+        const double ie = es[L.nwork], g0 = gc[l.offs], w0 = wbb[l.offs];
+        const double cst = -g0 + dl * es[3 * L.nwork];                               // :151
+        double* oc = Gt + ((size_t)b * n + col) * ldgt;
+        B_FOR_E if (l.tail(e)) oc[l.at(e)] = ie * (gv[e] + cst * wv[e]);             // :153-155
+        if (l.g == 0) oc[l.offs] = ie * (w0 * g0 - dl);                              // :152
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- scale! / iscale! / W^-2
 // reference src/scalings.jl:112-156, src/densesolver.jl:86.  MODE as ApplyMode of cone_ops.cuh.
 template <int MODE>

@@ -238,6 +238,20 @@ int cone_grid(const Shard& sh) {
     const long long thr = std::max((long long)sh.batch * sh.bl.nsoc * sh.bl.lpc, (long long)sh.batch * sh.bl.kpoc);
     return (int)std::max(1LL, std::min((thr + 255) / 256, 148LL * 16));
 }
+// Gt = W^-1 G (identity: Gt = G) for the whole shard
+void launch_build_gt(Shard& sh, bool identity, const int* active) {
+    Ws& w = sh.w;
+    const int n = w.L.n;
+    if (sh.bl_ok && !identity) {
+        const long long thr = std::max((long long)sh.batch * n * sh.bl.nsoc * sh.bl.lpc, (long long)sh.batch * n * sh.bl.kpoc);
+        const int grid = (int)std::max(1LL, std::min((thr + 255) / 256, 148LL * 16));
+        LAUNCH(sh, bk_build_gt, grid, 256, 0, sh.bl, sh.batch, n, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, active);
+        return;
+    }
+    const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
+    dim3 g((n + cols_per_cta - 1) / cols_per_cta, sh.batch);
+    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active);
+}
 void launch_scaling(Shard& sh, const int* active) {
     Ws& w = sh.w;
     if (sh.bl_ok) LAUNCH(sh, bk_scaling, cone_grid(sh), 256, 0, sh.bl, sh.batch, w.s, w.z, w.lam, w.wb, w.iwb, w.eta, w.fail, active);
@@ -278,9 +292,7 @@ void launch_compute_step(Shard& sh, const double* lam, const double* ds, const d
 void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
     Ws& w = sh.w;
     const int n = w.L.n, p = w.L.p;
-    const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)) );
-    dim3 g((n + cols_per_cta - 1) / cols_per_cta, sh.batch);
-    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active);
+    launch_build_gt(sh, identity, active);
     const bool aa = add_aa && p > 0 && sh.any_sing;
     syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0,
          aa ? w.AA : nullptr, (int64_t)w.ldh * n, w.ldh, w.sing, active);
@@ -1126,9 +1138,7 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
         double* Hcopy = nullptr;
         const size_t hbytes = sizeof(double) * (size_t)B * w.ldh * n;
         if (which == 7 || which == 8 || which == 9) {
-            const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
-            dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
-            LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 0, cols_per_cta, (const int*)nullptr);
+            launch_build_gt(sh, false, nullptr);
             syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0, 0, nullptr, nullptr);
             if (which == 8) {
                 CK(cudaMalloc((void**)&Hcopy, hbytes));
@@ -1153,12 +1163,7 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
                 case 3: launch_vprod(sh, w.s, w.z, w.k0); break;
                 case 4: launch_iprod(sh, w.lam, w.z, w.k0); break;
                 case 5: launch_compute_step(sh, w.lam, w.s, w.z, w.k0); break;
-                case 6: {
-                    const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
-                    dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
-                    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 0, cols_per_cta, (const int*)nullptr);
-                    break;
-                }
+                case 6: launch_build_gt(sh, false, nullptr); break;
                 case 7: syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0, 0, nullptr, nullptr); break;
                 case 8: potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, nullptr); break;
                 case 9: potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.rx, n, n, 1, nullptr); break;
