@@ -1,27 +1,31 @@
-// fused_v2.cuh -- whole-solve kernel for layouts that fit in shared memory (second generation).
+// fused_v2.cuh -- whole-solve kernel for layouts that fit in shared memory.
 //
 // One CTA ("team" of NW warps; a single warp for n <= 16) owns one problem from the initial point
-// to the last Mehrotra step (reference src/solver.jl:68-152).  G, Gt = W^-1 G, the reduced KKT
-// matrix H, the explicit inverse X = L^-1 of its Cholesky factor and every work vector live in
+// to the last Mehrotra step (reference src/solver.jl:68-152).  G, the reduced KKT matrix H (later
+// its explicit inverse), the inverse X = L^-1 of its Cholesky factor and every work vector live in
 // shared memory; global traffic is the problem in and the iterate out.  CTAs are persistent and
 // pull problems from an atomic counter.
 //
 // What bounds this kernel is the serial dependency chain of one interior-point iteration, so the
-// design minimises team barriers and reduction rounds:
+// design minimises team barriers, reduction rounds and instructions on the critical warp:
 //   * cone chains (compute_scaling; solve_kkt head: iprod -> W -> W^-2; tail: W^-2 -> W -> W ->
 //     W^-1 -> scmax) run register-resident on a group of LPC lanes per second-order cone (LPC = 1
 //     for SOC(4): one thread per cone, no shuffles; LPC = 16 for SOC(51)), reductions are xor
 //     shuffles inside the group; positive-orthant rows are elementwise over the whole team
-//   * H = Gt'Gt and every block operation of the factorisation are mma.sync m8n8k4 f64 (SASS
-//     DMMA.8x8x4) on shared-memory tiles with leading dimension == 4 (mod 8): conflict-free
-//     fragment loads
+//   * H = G'W^-2 G = G' diag(dw) G + sum_c hc hc' straight from G (the reference's product order,
+//     src/densesolver.jl:42-43, with the block-diagonal iWiW in closed form): mma.sync m8n8k4 f64
+//     (SASS DMMA.8x8x4) with the row weight folded into the A fragment; no scaled copy of G
 //   * blocked right-looking Cholesky on 8x8 tiles that carries the inverse along: one warp factors
 //     the diagonal tile redundantly in registers (no shuffles, no barriers), the panel and the
-//     trailing update (of H and of the partially built inverse) are DMMA tile products; two team
-//     barriers per block column instead of one per column
-//   * the solves are two triangular gemvs with X (the reference also applies an explicit inverse,
-//     src/densesolver.jl:48,83); the equality rows ride along (B = X A', K = H^-1 A' M^-1
-//     precomputed per factorisation), so p > 0 adds no barrier to a solve
+//     trailing update (of H and of the partially built inverse) are DMMA tile products driven by
+//     a descriptor table; two team barriers per block column, and the diagonal warp only arrives
+//     at the second one
+//   * explicit H^-1 = X'X by DMMA, as the reference does (Li, src/densesolver.jl:48,83); equality
+//     rows are folded into one solve matrix per factorisation (Pm = H^-1 - K (H^-1 A')', K = H^-1 A'
+//     M^-1), so a solve is three phases: n0 = G'u + dx, (cx, cy) = (Pm n0 + K dy, K'n0 - M^-1 dy),
+//     u = G cx - k2
+//   * one copy of factor / solve / head / tail for the initial point and both directions (state
+//     machine), compile-time specialised layouts for the BASELINE.json shapes (DimsStatic)
 //   * stop-test norms, sigma/mu and step-length reductions share one scratch exchange per phase
 //
 // Restrictions (the tiled path takes everything else): no `sing` problems, n <= 64, p <= 32,
