@@ -164,7 +164,9 @@ void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, i
           double alpha, double beta, const double* addC, int64_t sAdd, int ldadd, const uint8_t* addFlag,
           const int* active) {
     if (N <= 0) return;
-    const bool big = N > 256;
+    // 128 x 128 tiles when they fill the machine at least twice over, 64 x 64 tiles (3 CTAs per SM) otherwise
+    const long long t128 = (long long)((N + 127) / 128) * ((N + 127) / 128 + 1) / 2 * sh.batch;
+    const bool big = N > 256 && t128 >= 2 * 148;
     if (kmajor) {
         if (big) syrk_launch<128, 4, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
         else syrk_launch<64, 2, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
