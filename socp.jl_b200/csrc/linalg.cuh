@@ -117,7 +117,7 @@ k_gemv_n(const double* __restrict__ M, int64_t strideM, int ld, int rows, int co
 //   KMAJOR = false: A is N x K column-major,            C[i,j] = sum_c A[i,c] A[j,c]
 //                   (trailing update of the blocked Cholesky)
 //   C = beta*C + alpha*(...) (+ addC where addFlag[b]) on the lower-triangle TILES
-//   (diagonal tiles are written in full).
+//   (of a diagonal tile the warp sub-tiles on or below the diagonal are written).
 // Tile BT x BT per CTA, NW x NW warps each owning a (BT/NW)^2 sub-tile made of
 // m8n8k4 DMMAs; operands staged through shared memory with a 3-stage cp.async
 // ring.  Requirements: A 16-byte aligned, lda even; KMAJOR: K % KT == 0 with the
@@ -159,7 +159,21 @@ k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
     extern __shared__ __align__(16) double smem[];
     const double* Ab = A + (int64_t)b * strideA;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wr = warp / NW, wc = warp % NW;
+    // Warp (wr, wc) owns the (BT/NW)^2 sub-tile at (wr, wc).  On a diagonal tile only sub-tiles with wr >= wc are
+    // needed (the factorisation and the solves read the lower triangle): those NW(NW+1)/2 sub-tiles go to the first
+    // warps -- warp ids map to the four SM sub-partitions round-robin, so the DMMA work stays balanced -- and the
+    // remaining warps only help with the loads.
+    int wr = warp / NW, wc = warp % NW;
+    bool compute = true;
+    if (diag) {
+        constexpr int NACT = NW * (NW + 1) / 2;
+        if (warp < NACT) {
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= warp) ++a;
+            wr = a;
+            wc = warp - a * (a + 1) / 2;
+        } else compute = false;
+    }
     const int nk = (K + KT - 1) / KT;
 
     auto tileA = [&](int s) { return smem + (size_t)s * 2 * Cfg::TILE_DOUBLES; };
@@ -228,6 +242,7 @@ k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
         const double* ta = tileA(s);
         const double* tb = diag ? tileA(s) : tileB(s);
         const int fr = lane >> 2, fk = lane & 3;
+        if (compute)
 #pragma unroll
         for (int kk = 0; kk < KT; kk += 4) {
             double af[Cfg::MT], bf[Cfg::MT];
@@ -250,6 +265,7 @@ k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
     cp_async_wait<0>();
 
     // epilogue: C fragment layout of m8n8k4: row = lane/4, cols = 2*(lane%4) + {0,1}
+    if (!compute) return;
     double* Cb = C + (int64_t)b * strideC;
     const bool add = addC && (!addFlag || addFlag[b]);
     const double* Ad = add ? addC + (int64_t)b * strideAdd : nullptr;
