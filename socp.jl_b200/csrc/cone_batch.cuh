@@ -35,10 +35,11 @@ struct BLane {
 __device__ __forceinline__ BLane b_lane(const BLayout& L, long long gid, long long total, int lane) {
     BLane l;
     l.valid = gid < total;
-    const long long q = l.valid ? gid : 0;
-    const int ns = max(L.nsoc, 1);                 // layouts without second-order cones never have a valid lane
+    // 32-bit division: batch * nsoc < 2^32 (checked by the host when the layout is built)
+    const unsigned q = l.valid ? (unsigned)gid : 0u;
+    const unsigned ns = (unsigned)max(L.nsoc, 1);  // layouts without second-order cones never have a valid lane
     l.b = (int)(q / ns);
-    l.slot = (int)(q - (long long)l.b * ns);
+    l.slot = (int)(q - (unsigned)l.b * ns);
     l.offs = L.soc_offs[l.slot];
     const int dim = l.valid ? L.soc_dim[l.slot] : 0;
     l.g = lane & (L.lpc - 1);
@@ -78,10 +79,10 @@ __device__ __forceinline__ void b_for_each_group(const BLayout& L, int batch, F 
 }
 template <class F>
 __device__ __forceinline__ void b_for_each_poc(const BLayout& L, int batch, F f) {
-    const long long total = (long long)batch * L.kpoc;
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-        const int b = (int)(q / L.kpoc);
-        f(b, (int)(q - (long long)b * L.kpoc));
+    const unsigned total = (unsigned)batch * (unsigned)L.kpoc;       // < 2^32 (host-checked)
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const unsigned b = q / (unsigned)L.kpoc;
+        f((int)b, (int)(q - b * (unsigned)L.kpoc));
     }
 }
 
@@ -154,10 +155,10 @@ bk_build_gt(BLayout L, int batch, int n, const double* __restrict__ G, int64_t s
             const double* __restrict__ iwb, const double* __restrict__ eta, double* __restrict__ Gt, int ldgt,
             const int* __restrict__ active) {
     {   // positive-orthant rows
-        const long long total = (long long)batch * n * L.kpoc;
-        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-            const int b = (int)(q / ((long long)n * L.kpoc));
-            const int rem = (int)(q - (long long)b * n * L.kpoc);
+        const unsigned per = (unsigned)n * (unsigned)L.kpoc, total = (unsigned)batch * per;     // < 2^32 (host-checked)
+        for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+            const int b = (int)(q / per);
+            const int rem = (int)(q - (unsigned)b * per);
             const int col = rem / L.kpoc, r = rem - col * L.kpoc;
             if (active && !active[b]) continue;
             Gt[((size_t)b * n + col) * ldgt + r] = iwb[(size_t)b * L.k + r] * G[(int64_t)b * sG + (int64_t)col * L.k + r];
@@ -171,9 +172,9 @@ bk_build_gt(BLayout L, int batch, int n, const double* __restrict__ G, int64_t s
     for (long long base = wglobal * spw; base < total; base += wstride * spw) {
         const long long gid = base + lane / L.lpc;
         const bool valid = gid < total;
-        const long long q = valid ? gid : 0;
-        const int b = (int)(q / ((long long)n * L.nsoc));
-        const int rem = (int)(q - (long long)b * n * L.nsoc);
+        const unsigned q = valid ? (unsigned)gid : 0u, per = (unsigned)n * (unsigned)L.nsoc;    // < 2^32 (host-checked)
+        const int b = (int)(q / per);
+        const int rem = (int)(q - (unsigned)b * per);
         const int col = rem / L.nsoc, slot = rem - col * L.nsoc;
         const BLane l = b_lane(L, (long long)b * L.nsoc + slot, valid ? (long long)(b + 1) * L.nsoc : 0, lane);
         const bool on = l.valid && !(active && !active[b]);

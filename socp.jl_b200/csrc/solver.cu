@@ -244,7 +244,8 @@ int cone_grid(const Shard& sh) {
 void launch_build_gt(Shard& sh, bool identity, const int* active) {
     Ws& w = sh.w;
     const int n = w.L.n;
-    if (sh.bl_ok && !identity) {
+    const long long pairs = (long long)sh.batch * n * std::max({sh.bl.nsoc, sh.bl.kpoc, 1});
+    if (sh.bl_ok && !identity && pairs < (1LL << 31)) {
         const long long thr = std::max((long long)sh.batch * n * sh.bl.nsoc * sh.bl.lpc, (long long)sh.batch * n * sh.bl.kpoc);
         const int grid = (int)std::max(1LL, std::min((thr + 255) / 256, 148LL * 16));
         LAUNCH(sh, bk_build_gt, grid, 256, 0, sh.bl, sh.batch, n, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, active);
@@ -455,7 +456,8 @@ void build_shard(socp_handle* h, Shard& sh) {
             CK(cudaMemcpyAsync(d + 2 * ns, sw.data(), ns * sizeof(int), cudaMemcpyHostToDevice, sh.stream));
         }
         sh.bl = BLayout{k, kpoc, ns, f2_lpc(maxd), nc, d, d + ns, d + 2 * ns};
-        sh.bl_ok = maxd <= 128;
+        // the batch-wide cone kernels index (problem, cone) pairs and orthant rows with 32-bit arithmetic
+        sh.bl_ok = maxd <= 128 && (long long)B * std::max(ns, 1) < (1LL << 31) && (long long)B * std::max(kpoc, 1) < (1LL << 31);
         sh.bl_warp = sh.bl_ok && ns * sh.bl.lpc <= 32;
         sh.bl_sw = 1;
         while (sh.bl_sw < std::max(1, ns * sh.bl.lpc)) sh.bl_sw <<= 1;
