@@ -351,6 +351,10 @@ def main():
                        "l2": f"inputs {bytes_step / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)"
                              if bytes_step > 130e6 else "inputs fit in L2; steps re-upload nothing (device-resident leg)",
                        "converged": int(total_conv), "mean_iters": total_iters / total_B,
+                       # BASELINE.json's secondary metric: one "KKT factor+solve" = one setup_iter + one solve_kkt; a
+                       # solve does (iterations + 1) of them per problem (the initial point is one).  Amortised over the
+                       # whole job (throughput), not the latency of one problem.
+                       "us_per_kkt_factor_solve_amortised": 1e6 * t_dev / args.steps / (total_iters + total_B),
                        "timing": "CUDA events on the library's launch stream, summed over the timed steps, max over ranks",
                        "wall_s_device_leg": t_wall_dev},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
