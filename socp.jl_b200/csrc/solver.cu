@@ -650,11 +650,18 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
     sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
     sh.any_sing = false;
-    // chunks of at least 4 waves of resident CTAs, at most 8 chunks
+    // Chunk boundaries: a short first chunk (two waves of resident CTAs) so that the solve starts as soon as possible,
+    // then up to 8 equal chunks of at least 4 waves each.
     const int slots = sh.fused2.num_sms * sh.fused2.ctas_per_sm;
-    int nchunk = std::max(1, std::min(8, B / std::max(1, 4 * slots)));
-    const int per = (B + nchunk - 1) / nchunk;
-    nchunk = (B + per - 1) / per;
+    std::vector<int> bounds{0};
+    if (B > 8 * slots) bounds.push_back(2 * slots);
+    {
+        const int rest = B - bounds.back();
+        const int nrest = std::max(1, std::min(8, rest / std::max(1, 4 * slots)));
+        const int per = (rest + nrest - 1) / nrest;
+        for (int lo = bounds.back(); lo < B; lo += per) bounds.push_back(std::min(B, lo + per));
+    }
+    const int nchunk = (int)bounds.size() - 1;
     while ((int)sh.pipe_ev.size() < 2 * nchunk) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -675,7 +682,7 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     // of chunk i run out of work, so there is no drain bubble between launches.
     for (int ci = 0; ci < nchunk; ++ci) {
         cudaStream_t cs = (ci & 1) ? sh.alt_stream : sh.stream;
-        const int lo = ci * per, cb = std::min(per, B - lo);
+        const int lo = bounds[ci], cb = bounds[ci + 1] - lo;
         const int64_t g0 = f + lo;
         up(sh.d_c + (size_t)lo * n, c + g0 * n, sizeof(double) * cb * n);
         up(sh.d_h + (size_t)lo * k, hvec + g0 * k, sizeof(double) * cb * k);
