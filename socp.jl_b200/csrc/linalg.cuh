@@ -122,7 +122,8 @@ k_gemv_n(const double* __restrict__ M, int64_t strideM, int ld, int rows, int co
 // m8n8k4 DMMAs; operands staged through shared memory with a 3-stage cp.async
 // ring.  Requirements: A 16-byte aligned, lda even; KMAJOR: K % KT == 0 with the
 // pad rows of A zero.
-// grid (ntiles*(ntiles+1)/2, batch).
+// grid (ntiles*(ntiles+1)/2, batch); with first_col_only grid (ntiles, batch): only the first block column of C
+// (the next panel of a blocked Cholesky whose trailing update is delayed).
 // ---------------------------------------------------------------------------
 template <int BT, int NW, int KT, bool KMAJOR>
 struct SyrkCfg {
@@ -143,16 +144,20 @@ __global__ void __launch_bounds__(NW * NW * 32)
 k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
        double* __restrict__ C, int64_t strideC, int ldc, double alpha, double beta,
        const double* __restrict__ addC, int64_t strideAdd, int ldadd, const uint8_t* __restrict__ addFlag,
-       const int* __restrict__ active) {
+       const int* __restrict__ active, int first_col_only) {
     using Cfg = SyrkCfg<BT, NW, KT, KMAJOR>;
     const int b = blockIdx.y;
     if (active && !active[b]) return;
-    // lower-triangle tile index -> (ti, tj), ti >= tj
+    // lower-triangle tile index -> (ti, tj), ti >= tj; first_col_only: the tiles (t, 0) of the first block column
     int t = blockIdx.x;
-    int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    const int tj = t - ti * (ti + 1) / 2;
+    int ti, tj;
+    if (first_col_only) { ti = t; tj = 0; }
+    else {
+        ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        tj = t - ti * (ti + 1) / 2;
+    }
     const int i0 = ti * BT, j0 = tj * BT;
     const bool diag = (ti == tj);
 

@@ -148,7 +148,7 @@ void gemv_n(Shard& sh, const double* M, int64_t sM, int ld, int rows, int cols, 
 template <int BT, int NW, int KT, bool KM>
 void syrk_launch(Shard& sh, const double* A, int64_t sA, int lda, int N, int K, double* C, int64_t sC, int ldc,
                  double alpha, double beta, const double* addC, int64_t sAdd, int ldadd, const uint8_t* addFlag,
-                 const int* active) {
+                 const int* active, bool first_col_only = false) {
     using Cfg = SyrkCfg<BT, NW, KT, KM>;
     static bool configured[64] = {};
     if (!configured[sh.device]) {
@@ -156,9 +156,9 @@ void syrk_launch(Shard& sh, const double* A, int64_t sA, int lda, int N, int K, 
         configured[sh.device] = true;
     }
     const int nt = (N + BT - 1) / BT;
-    dim3 grid(nt * (nt + 1) / 2, sh.batch);
+    dim3 grid(first_col_only ? nt : nt * (nt + 1) / 2, sh.batch);
     LAUNCH(sh, (k_syrk<BT, NW, KT, KM>), grid, Cfg::THREADS, Cfg::SMEM, A, sA, lda, N, K, C, sC, ldc, alpha, beta,
-           addC, sAdd, ldadd, addFlag, active);
+           addC, sAdd, ldadd, addFlag, active, first_col_only ? 1 : 0);
 }
 void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, int K, double* C, int64_t sC, int ldc,
           double alpha, double beta, const double* addC, int64_t sAdd, int ldadd, const uint8_t* addFlag,
@@ -188,15 +188,35 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
         configured[sh.device] = true;
     }
     const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
-    for (int j = 0; j < nn; j += CHOL_NB) {
-        const int below = nn - j - CHOL_NB;
+    auto panel = [&](int j) {          // factor the 64-wide panel at column j: diagonal block, then L21 = A21 L11^-T
         LAUNCH(sh, k_potrf_diag_mma, sh.batch, 256, POTRF_MMA_SMEM, H, sH, ld, nn, j, Xinv, nblk, fail, active);
+        const int below = nn - j - CHOL_NB;
         if (below > 0) {
             dim3 grid((below + 127) / 128, sh.batch);
             LAUNCH(sh, k_trsm_mma, grid, 256, TRSM_MMA_SMEM, H, sH, ld, nn, j, (const double*)Xinv, nblk, (const int*)fail, active);
-            const double* P = H + (int64_t)j * ld + (j + CHOL_NB);
-            double* T = H + (int64_t)(j + CHOL_NB) * ld + (j + CHOL_NB);
-            syrk(sh, false, P, sH, ld, below, CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active);
+        }
+    };
+    // Panels are taken in groups of CHOL_GROUP with the trailing update delayed (left-looking inside the group, right-
+    // looking between groups): before panel m of a group its 64 columns receive the m earlier panels of the group (a
+    // thin product, K = 64 m); after the group the rest of the matrix receives all of them at once (K = 64 CHOL_GROUP) --
+    // 1/CHOL_GROUP of the read-modify-write passes over the trailing matrix at CHOL_GROUP times the arithmetic intensity.
+    constexpr int CHOL_GROUP = 4;
+    for (int j = 0; j < nn; j += CHOL_GROUP * CHOL_NB) {
+        for (int m = 0; m < CHOL_GROUP; ++m) {
+            const int jm = j + m * CHOL_NB;
+            if (jm >= nn) break;
+            if (m > 0) {   // rows >= jm, columns [jm, jm + 64): first block column of what is left
+                const double* P = H + (int64_t)j * ld + jm;
+                double* T = H + (int64_t)jm * ld + jm;
+                syrk_launch<64, 2, 16, false>(sh, P, sH, ld, nn - jm, m * CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active, true);
+            }
+            panel(jm);
+        }
+        const int jn = j + CHOL_GROUP * CHOL_NB;
+        if (jn < nn) {
+            const double* P = H + (int64_t)j * ld + jn;
+            double* T = H + (int64_t)jn * ld + jn;
+            syrk(sh, false, P, sH, ld, nn - jn, CHOL_GROUP * CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active);
         }
     }
 }
