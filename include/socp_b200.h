@@ -117,6 +117,25 @@ const char* socp_b200_last_error(const socp_handle* h);
 int  socp_b200_set_data(socp_handle* h, const double* c, const double* A, const double* b,
                         const double* G, const double* hvec, const uint8_t* sing, int32_t flags);
 
+/* The same constructor for callers that hold A and G the way the reference
+ * stores them: SparseMatrixCSC{Float64,Int64} (fields colptr, rowval, nzval;
+ * src/Socp.jl:25,29, built in src/moi.jl:208-210).  One sparsity pattern per
+ * matrix for the whole batch; nzval is [batch][nnz], or [nnz] with the
+ * SOCP_FLAG_SHARED_* bit.  index_base = 1 for Julia's arrays, 0 for C / scipy.
+ * Row indices must increase strictly inside every column (the invariant of
+ * SparseMatrixCSC); anything else is SOCP_ERR_LAYOUT.  Only nnz values per
+ * problem cross PCIe; the dense column-major operands of the KKT path are
+ * assembled on the device.  A may be NULL when p == 0. */
+typedef struct socp_csc {
+    int64_t        nnz;         /* stored entries of one matrix                  */
+    const int64_t* colptr;      /* [cols + 1]                                    */
+    const int64_t* rowval;      /* [nnz]                                         */
+    const double*  nzval;       /* [batch][nnz], or [nnz] when shared            */
+    int32_t        index_base;  /* 0 or 1                                        */
+} socp_csc;
+int  socp_b200_set_data_csc(socp_handle* h, const double* c, const socp_csc* A, const double* b,
+                            const socp_csc* G, const double* hvec, const uint8_t* sing, int32_t flags);
+
 /* solve_socp(prob, ss), reference src/solver.jl:40-152, for the whole batch:
  * initial point (:68-104) + Mehrotra loop (:105-151) on the device, results
  * copied back.  Any output pointer may be NULL.  Shapes: x[batch][n],

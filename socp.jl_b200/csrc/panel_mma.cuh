@@ -118,11 +118,13 @@ k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const
 // ---------------------------------------------------------------------------
 // Triangular solves with the factor and the inverted 64 x 64 diagonal blocks kept by k_potrf_diag_mma:
 //   k_trsv_blk_fwd:  X <- L^-1 X        k_trsv_blk_bwd:  X <- L^-T X        (in place, n x nrhs, ld = ldx)
-// One CTA (256 threads) per (rhs, problem), the right-hand side in shared memory.  Per 64-block: a 64 x 64 gemv
+// One CTA (NT = 256 threads, 1024 when the batch is too small to fill the machine) per (rhs, problem), the right-
+// hand side in shared memory.  Per 64-block: a 64 x 64 gemv
 // with the inverted block (no serial substitution chain) and a gemv with the panel below it.
-// grid (nrhs, batch), dynamic smem = (n + 64) * 8.
+// grid (nrhs, batch), dynamic smem = (n + 64) * 8 (+ (NT / 256) * n * 8 for the forward kernel with NT > 256).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_trsv_blk_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, const double* __restrict__ Xinv,
                int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
     const int b = blockIdx.y;
@@ -134,41 +136,71 @@ k_trsv_blk_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, co
     const double* Xi = Xinv + ((int64_t)b * nblk + blk0) * 4096;
     double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
     const int tid = threadIdx.x;
-    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
+    for (int i = tid; i < n; i += NT) xs[i] = xg[i];
     __syncthreads();
     for (int jb = 0; jb < n; jb += 64) {
         const int w = min(64, n - jb);
         const double* Xb = Xi + (int64_t)(jb >> 6) * 4096;
-        {   // ys = Xbb xs[jb .. jb+w): 4 threads per row, 16 columns each
-            const int r = tid >> 2, q = tid & 3;
+        {   // ys = Xbb xs[jb .. jb+w): NT/64 threads per row, 64/(NT/64) columns each
+            constexpr int PARTS = NT / 64, CPP = 64 / PARTS;
+            const int r = tid / PARTS, q = tid % PARTS;
             double acc = 0.0;
 #pragma unroll 4
-            for (int c = q * 16; c < q * 16 + 16; ++c)
+            for (int c = q * CPP; c < q * CPP + CPP; ++c)
                 if (c <= r && c < w) acc = fma(Xb[c * 64 + r], xs[jb + c], acc);
-            acc += __shfl_xor_sync(FULL_MASK, acc, 1);
-            acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+#pragma unroll
+            for (int o = 1; o < PARTS; o <<= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
             if (q == 0) ys[r] = acc;
         }
         __syncthreads();
-        for (int r = jb + 64 + tid; r < n; r += 256) {      // rows below: xs[r] -= L[r, jb..jb+64) ys
-            const double* lp = Lb + (int64_t)jb * ldl + r;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if constexpr (NT == 256) {
+            for (int r = jb + 64 + tid; r < n; r += NT) {    // rows below: xs[r] -= L[r, jb..jb+64) ys
+                const double* lp = Lb + (int64_t)jb * ldl + r;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll 4
-            for (int c = 0; c < 64; c += 4) {
-                a0 = fma(lp[(int64_t)c * ldl], ys[c], a0);
-                a1 = fma(lp[(int64_t)(c + 1) * ldl], ys[c + 1], a1);
-                a2 = fma(lp[(int64_t)(c + 2) * ldl], ys[c + 2], a2);
-                a3 = fma(lp[(int64_t)(c + 3) * ldl], ys[c + 3], a3);
+                for (int c = 0; c < 64; c += 4) {
+                    a0 = fma(lp[(int64_t)c * ldl], ys[c], a0);
+                    a1 = fma(lp[(int64_t)(c + 1) * ldl], ys[c + 1], a1);
+                    a2 = fma(lp[(int64_t)(c + 2) * ldl], ys[c + 2], a2);
+                    a3 = fma(lp[(int64_t)(c + 3) * ldl], ys[c + 3], a3);
+                }
+                xs[r] -= (a0 + a1) + (a2 + a3);
             }
-            xs[r] -= (a0 + a1) + (a2 + a3);
+        } else {
+            // few problems: the 64 columns are split over NT/256 thread groups as well (16 loads in flight per thread,
+            // one round for 256 rows); partial sums meet in shared memory
+            constexpr int CS = NT / 256, CW = 64 / CS;
+            const int rl = tid & 255, cp = tid >> 8;
+            double* part = tsm + n + 64;                     // [CS][n]
+            for (int r = jb + 64 + rl; r < n; r += 256) {
+                const double* lp = Lb + (int64_t)(jb + cp * CW) * ldl + r;
+                const double* yp = ys + cp * CW;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                for (int c = 0; c < CW; c += 4) {
+                    a0 = fma(lp[(int64_t)c * ldl], yp[c], a0);
+                    a1 = fma(lp[(int64_t)(c + 1) * ldl], yp[c + 1], a1);
+                    a2 = fma(lp[(int64_t)(c + 2) * ldl], yp[c + 2], a2);
+                    a3 = fma(lp[(int64_t)(c + 3) * ldl], yp[c + 3], a3);
+                }
+                part[cp * n + r] = (a0 + a1) + (a2 + a3);
+            }
+            __syncthreads();
+            for (int r = jb + 64 + tid; r < n; r += NT) {
+                double a = 0.0;
+#pragma unroll
+                for (int q = 0; q < CS; ++q) a += part[q * n + r];
+                xs[r] -= a;
+            }
         }
         if (tid < w) xs[jb + tid] = ys[tid];
         __syncthreads();
     }
-    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
+    for (int i = tid; i < n; i += NT) xg[i] = xs[i];
 }
 
-__global__ void __launch_bounds__(256)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_trsv_blk_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, const double* __restrict__ Xinv,
                int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
     const int b = blockIdx.y;
@@ -180,13 +212,13 @@ k_trsv_blk_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, co
     const double* Xi = Xinv + ((int64_t)b * nblk + blk0) * 4096;
     double* xg = X + (int64_t)b * strideX + (int64_t)blockIdx.x * ldx;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n; i += 256) xs[i] = xg[i];
+    for (int i = tid; i < n; i += NT) xs[i] = xg[i];
     __syncthreads();
     for (int jb = ((n - 1) >> 6) << 6; jb >= 0; jb -= 64) {
         const int w = min(64, n - jb);
         const double* Xb = Xi + (int64_t)(jb >> 6) * 4096;
         // ts[c] = xs[jb+c] - sum_{r >= jb+64} L[r, jb+c] xs[r]: warp per column, lanes over the rows below
-        for (int c = warp; c < 64; c += 8) {
+        for (int c = warp; c < 64; c += NT / 32) {
             double a0 = 0.0, a1 = 0.0;
             if (c < w) {
                 const double* col = Lb + (int64_t)(jb + c) * ldl;
@@ -201,19 +233,20 @@ k_trsv_blk_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, co
             if (lane == 0) ts[c] = (c < w) ? xs[jb + c] - acc : 0.0;
         }
         __syncthreads();
-        {   // xs[jb+c] = sum_{r >= c} Xbb[r, c] ts[r]: 4 threads per column, 16 rows each
-            const int c = tid >> 2, q = tid & 3;
+        {   // xs[jb+c] = sum_{r >= c} Xbb[r, c] ts[r]: NT/64 threads per column
+            constexpr int PARTS = NT / 64, RPP = 64 / PARTS;
+            const int c = tid / PARTS, q = tid % PARTS;
             double acc = 0.0;
 #pragma unroll 4
-            for (int r = q * 16; r < q * 16 + 16; ++r)
+            for (int r = q * RPP; r < q * RPP + RPP; ++r)
                 if (r >= c && r < w) acc = fma(Xb[c * 64 + r], ts[r], acc);
-            acc += __shfl_xor_sync(FULL_MASK, acc, 1);
-            acc += __shfl_xor_sync(FULL_MASK, acc, 2);
+#pragma unroll
+            for (int o = 1; o < PARTS; o <<= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
             if (q == 0 && c < w) xs[jb + c] = acc;
         }
         __syncthreads();
     }
-    for (int i = tid; i < n; i += 256) xg[i] = xs[i];
+    for (int i = tid; i < n; i += NT) xg[i] = xs[i];
 }
 
 }  // namespace socp

@@ -183,8 +183,10 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
     if (!configured[sh.device]) {
         CK(cudaFuncSetAttribute(k_potrf_diag_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_MMA_SMEM));
         CK(cudaFuncSetAttribute(k_trsm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_MMA_SMEM));
-        CK(cudaFuncSetAttribute(k_trsv_blk_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_trsv_blk_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_trsv_blk_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_trsv_blk_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_trsv_blk_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((5 * 1024 + 64) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_trsv_blk_bwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
         configured[sh.device] = true;
     }
     const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
@@ -230,16 +232,25 @@ void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, const double*
     constexpr int BS = 512;
     const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
     dim3 grid(nrhs, sh.batch);
+    // few (rhs, problem) pairs: a CTA of 1024 threads walks its factor four times faster than one of 256
+    const bool wide = (long long)nrhs * sh.batch < 148;
+    auto fwd = [&](size_t smem, const double* Lp, int rows, int blk0, double* Xp) {
+        if (wide) LAUNCH(sh, k_trsv_blk_fwd<1024>, grid, 1024, smem + (size_t)4 * rows * sizeof(double), Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
+        else LAUNCH(sh, k_trsv_blk_fwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
+    };
+    auto bwd = [&](size_t smem, const double* Lp, int rows, int blk0, double* Xp) {
+        if (wide) LAUNCH(sh, k_trsv_blk_bwd<1024>, grid, 1024, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
+        else LAUNCH(sh, k_trsv_blk_bwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
+    };
     if (nn <= 2 * BS) {
         const size_t smem = (size_t)(nn + 64) * sizeof(double);
-        LAUNCH(sh, k_trsv_blk_fwd, grid, 256, smem, L, sL, ld, nn, Xinv, nblk, 0, X, sX, ldx, active);
-        LAUNCH(sh, k_trsv_blk_bwd, grid, 256, smem, L, sL, ld, nn, Xinv, nblk, 0, X, sX, ldx, active);
+        fwd(smem, L, nn, 0, X);
+        bwd(smem, L, nn, 0, X);
         return;
     }
     for (int jb = 0; jb < nn; jb += BS) {                       // forward: L y = x
         const int bs = std::min(BS, nn - jb), below = nn - jb - bs;
-        LAUNCH(sh, k_trsv_blk_fwd, grid, 256, (size_t)(bs + 64) * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, Xinv,
-               nblk, jb / CHOL_NB, X + jb, sX, ldx, active);
+        fwd((size_t)(bs + 64) * sizeof(double), L + (int64_t)jb * ld + jb, bs, jb / CHOL_NB, X + jb);
         for (int q = 0; q < nrhs && below > 0; ++q)
             gemv_n(sh, L + (int64_t)jb * ld + jb + bs, sL, ld, below, bs, X + (int64_t)q * ldx + jb, sX,
                    X + (int64_t)q * ldx + jb + bs, sX, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
@@ -249,8 +260,7 @@ void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, const double*
         for (int q = 0; q < nrhs && below > 0; ++q)
             gemv_t(sh, L + (int64_t)jb * ld + jb + bs, sL, ld, below, bs, X + (int64_t)q * ldx + jb + bs, sX,
                    X + (int64_t)q * ldx + jb, sX, -1.0, epi(nullptr, 0, 0, nullptr, 0, 0, 1), active);
-        LAUNCH(sh, k_trsv_blk_bwd, grid, 256, (size_t)(bs + 64) * sizeof(double), L + (int64_t)jb * ld + jb, sL, ld, bs, Xinv,
-               nblk, jb / CHOL_NB, X + jb, sX, ldx, active);
+        bwd((size_t)(bs + 64) * sizeof(double), L + (int64_t)jb * ld + jb, bs, jb / CHOL_NB, X + jb);
     }
 }
 
@@ -748,6 +758,89 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     sh.have_scaling = sh.have_factor = false;
 }
 
+// what follows the upload in both constructors: the `sing` test / A'A when they are needed, bookkeeping
+void finish_set_data(Shard& sh, const uint8_t* sing, int p) {
+    const int64_t f = sh.first;
+    const int B = sh.batch;
+    // sing / A'A are only needed when there are equalities or the caller
+    // asks for the test; with p == 0 and sing given the tiled buffers stay unallocated
+    bool given_none = false;
+    if (sing) {
+        given_none = true;
+        for (int64_t q = 0; q < B; ++q) given_none &= (sing[f + q] == 0);
+    }
+    if (given_none || (sing && p == 0)) {
+        // A'A (src/densesolver.jl:32) is only used by `sing` problems: nothing to prepare
+        sh.any_sing = !given_none;
+        CK(cudaStreamSynchronize(sh.stream));
+    } else {
+        prepare_problem(sh, sing != nullptr);
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
+    sh.tim.h2d_ms = ms;
+    sh.have_data = true;
+    sh.have_scaling = sh.have_factor = false;
+}
+
+// CSC -> dense column-major on the device: dense[b][lin[j]] = val[b][j], lin = col * rows + row (host-validated, no
+// duplicates, so the scatter has no write conflicts).  One thread per (problem, stored entry).
+__global__ void __launch_bounds__(256)
+k_csc_scatter(const int* __restrict__ lin, const double* __restrict__ val, int64_t stride_val, int nnz,
+              double* __restrict__ dense, int64_t stride_dense, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / nnz;
+        const int j = (int)(i - b * nnz);
+        dense[b * stride_dense + lin[j]] = val[b * stride_val + j];
+    }
+}
+
+// host side of the pattern: SparseMatrixCSC invariants -> linear indices into a rows x cols column-major matrix
+std::vector<int> csc_linear_index(const socp_csc& m, int rows, int cols, const char* name) {
+    need(m.nnz >= 0 && m.nnz <= (int64_t)rows * cols, SOCP_ERR_SIZE, "csc: nnz out of range");
+    need(m.colptr && (m.nnz == 0 || (m.rowval && m.nzval)), SOCP_ERR_NULL, "csc: colptr / rowval / nzval must not be null");
+    need(m.index_base == 0 || m.index_base == 1, SOCP_ERR_LAYOUT, "csc: index_base must be 0 or 1");
+    const int64_t base = m.index_base;
+    need(m.colptr[0] == base && m.colptr[cols] == base + m.nnz, SOCP_ERR_LAYOUT, "csc: colptr does not span nnz");
+    std::vector<int> lin((size_t)m.nnz);
+    for (int cidx = 0; cidx < cols; ++cidx) {
+        const int64_t lo = m.colptr[cidx] - base, hi = m.colptr[cidx + 1] - base;
+        need(lo <= hi && hi <= m.nnz, SOCP_ERR_LAYOUT, "csc: colptr not monotone");
+        int64_t prev = -1;
+        for (int64_t j = lo; j < hi; ++j) {
+            const int64_t r = m.rowval[j] - base;
+            need(r > prev && r < rows, SOCP_ERR_LAYOUT, "csc: row indices must increase strictly inside a column");
+            prev = r;
+            lin[(size_t)j] = (int)((int64_t)cidx * rows + r);
+        }
+    }
+    (void)name;
+    return lin;
+}
+
+// upload one matrix of a shard in CSC form and assemble it dense in `dense`
+void upload_csc(Shard& sh, const socp_csc& m, const std::vector<int>& lin, bool shared, int rows, int cols,
+                double* dense) {
+    const int64_t nb = shared ? 1 : sh.batch;
+    CK(cudaMemsetAsync(dense, 0, sizeof(double) * nb * rows * cols, sh.stream));
+    if (m.nnz == 0) return;
+    int* d_lin = nullptr;
+    double* d_val = nullptr;
+    CK(cudaMalloc(&d_lin, sizeof(int) * m.nnz));
+    if (cudaMalloc(&d_val, sizeof(double) * nb * m.nnz) != cudaSuccess) {
+        cudaFree(d_lin);
+        throw UsageErr{SOCP_ERR_NOMEM, "csc: out of device memory for the value staging buffer"};
+    }
+    h2d(sh, d_lin, lin.data(), sizeof(int) * m.nnz);
+    h2d(sh, d_val, m.nzval + (shared ? 0 : sh.first * m.nnz), sizeof(double) * nb * m.nnz);
+    const int64_t total = nb * m.nnz;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    LAUNCH(sh, k_csc_scatter, grid, 256, 0, d_lin, d_val, m.nnz, (int)m.nnz, dense, (int64_t)rows * cols, total);
+    CK(cudaStreamSynchronize(sh.stream));
+    CK(cudaFree(d_lin));
+    CK(cudaFree(d_val));
+}
+
 }  // namespace
 
 // =========================================================================== C ABI
@@ -879,25 +972,38 @@ int socp_b200_set_data(socp_handle* h, const double* c, const double* A, const d
             sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
             if (sing) h2d(sh, sh.d_sing, sing + f, B);
             CK(cudaEventRecord(sh.ev[1], sh.stream));
-            // sing / A'A are only needed when there are equalities or the caller
-            // asks for the test; with p == 0 and sing given the tiled buffers stay unallocated
-            bool given_none = false;
-            if (sing) {
-                given_none = true;
-                for (int64_t q = 0; q < B; ++q) given_none &= (sing[f + q] == 0);
+            finish_set_data(sh, sing, p);
+        });
+    });
+}
+
+int socp_b200_set_data_csc(socp_handle* h, const double* c, const socp_csc* A, const double* b, const socp_csc* G,
+                           const double* hvec, const uint8_t* sing, int32_t flags) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        need(c && G && hvec, SOCP_ERR_NULL, "c, G, h must not be null");
+        need(h->p == 0 || (A && b), SOCP_ERR_NULL, "A, b must not be null when p > 0");
+        const int n = h->n, p = h->p, k = h->k;
+        const std::vector<int> linG = csc_linear_index(*G, k, n, "G");
+        const std::vector<int> linA = p > 0 ? csc_linear_index(*A, p, n, "A") : std::vector<int>();
+        for_each_shard(h, [&](Shard& sh) {
+            const int64_t f = sh.first;
+            const int B = sh.batch;
+            sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
+            sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
+            CK(cudaEventRecord(sh.ev[0], sh.stream));
+            h2d(sh, sh.d_c, c + f * n, sizeof(double) * B * n);
+            h2d(sh, sh.d_h, hvec + f * k, sizeof(double) * B * k);
+            if (p > 0) {
+                h2d(sh, sh.d_b, b + f * p, sizeof(double) * B * p);
+                upload_csc(sh, *A, linA, sh.sharedA, p, n, sh.d_A);
             }
-            if (given_none || (sing && p == 0)) {
-                // A'A (src/densesolver.jl:32) is only used by `sing` problems: nothing to prepare
-                sh.any_sing = !given_none;
-                CK(cudaStreamSynchronize(sh.stream));
-            } else {
-                prepare_problem(sh, sing != nullptr);
-            }
-            float ms = 0;
-            CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
-            sh.tim.h2d_ms = ms;
-            sh.have_data = true;
-            sh.have_scaling = sh.have_factor = false;
+            upload_csc(sh, *G, linG, sh.sharedG, k, n, sh.d_G);
+            sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
+            sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
+            if (sing) h2d(sh, sh.d_sing, sing + f, B);
+            CK(cudaEventRecord(sh.ev[1], sh.stream));
+            finish_set_data(sh, sing, p);
         });
     });
 }

@@ -151,6 +151,35 @@ function load!(ss::SolverState, pr::BatchProblem)
     check(ss, rc, "socp_b200_set_data")
 end
 
+# The reference keeps A and G as SparseMatrixCSC{Float64,Int64} (src/Socp.jl:25,29).  Their three fields are
+# handed to the library as they are (1-based): only nnz values per problem cross PCIe and the dense operands
+# of the KKT path are assembled on the device.  `Avals` / `Gvals` (nnz x B) give per-problem values on the
+# shared pattern; without them the one matrix is shared by the whole batch.
+struct CCsc
+    nnz::Int64; colptr::Ptr{Int64}; rowval::Ptr{Int64}; nzval::Ptr{Float64}; index_base::Int32
+end
+function load!(ss::SolverState, c::Matrix{Float64}, A::Union{Nothing,SparseMatrixCSC{Float64,Int64}}, b::Matrix{Float64},
+               G::SparseMatrixCSC{Float64,Int64}, h::Matrix{Float64};
+               Avals::Union{Nothing,Matrix{Float64}} = nothing, Gvals::Union{Nothing,Matrix{Float64}} = nothing,
+               sing::Union{Nothing,Vector{UInt8}} = nothing)
+    @assert size(G) == (ss.k, ss.n) && (ss.m == 0 || size(A) == (ss.m, ss.n))       # src/Socp.jl:43-47
+    @assert Gvals === nothing || size(Gvals) == (nnz(G), ss.B)
+    @assert Avals === nothing || size(Avals) == (nnz(A), ss.B)
+    flags = Int32((Avals === nothing && ss.m > 0 ? 1 : 0) | (Gvals === nothing ? 2 : 0))
+    gv = Gvals === nothing ? G.nzval : Gvals
+    rc = GC.@preserve c A b G h gv Avals sing begin
+        gs = Ref(CCsc(nnz(G), pointer(G.colptr), pointer(G.rowval), pointer(gv), 1))
+        as = ss.m > 0 ? Ref(CCsc(nnz(A), pointer(A.colptr), pointer(A.rowval),
+                                 pointer(Avals === nothing ? A.nzval : Avals), 1)) : Ref(CCsc(0, C_NULL, C_NULL, C_NULL, 1))
+        ccall((:socp_b200_set_data_csc, libsocp), Cint,
+              (Ptr{Cvoid}, Ptr{Float64}, Ptr{CCsc}, Ptr{Float64}, Ptr{CCsc}, Ptr{Float64}, Ptr{UInt8}, Int32),
+              ss.solver.handle, c, ss.m > 0 ? as : C_NULL,
+              ss.m > 0 ? pointer(b) : Ptr{Float64}(C_NULL), gs, h,
+              sing === nothing ? Ptr{UInt8}(C_NULL) : pointer(sing), flags)
+    end
+    check(ss, rc, "socp_b200_set_data_csc")
+end
+
 """
     solve_socp_batch(prob, ss; params, sing)
 

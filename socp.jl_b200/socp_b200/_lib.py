@@ -10,6 +10,7 @@ from . import build as _build
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 c_uint8_p = C.POINTER(C.c_uint8)
+c_int64_p = C.POINTER(C.c_int64)
 
 
 class Layout(C.Structure):
@@ -27,6 +28,11 @@ class Timings(C.Structure):
                 ("kernel_launches", C.c_int64), ("iterations_max", C.c_int32), ("path_used", C.c_int32)]
 
 
+class Csc(C.Structure):
+    _fields_ = [("nnz", C.c_int64), ("colptr", c_int64_p), ("rowval", c_int64_p), ("nzval", c_double_p),
+                ("index_base", C.c_int32)]
+
+
 # every symbol include/socp_b200.h declares: name -> (restype, argtypes)
 H = C.c_void_p
 SYMBOLS = {
@@ -37,6 +43,8 @@ SYMBOLS = {
     "socp_b200_destroy": (C.c_int, [H]),
     "socp_b200_last_error": (C.c_char_p, [H]),
     "socp_b200_set_data": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_uint8_p, C.c_int32]),
+    "socp_b200_set_data_csc": (C.c_int, [H, c_double_p, C.POINTER(Csc), c_double_p, C.POINTER(Csc), c_double_p,
+                                         c_uint8_p, C.c_int32]),
     "socp_b200_solve": (C.c_int, [H, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p,
                                   c_int32_p, c_int32_p, c_double_p, c_double_p]),
     "socp_b200_solve_host": (C.c_int, [H, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,

@@ -132,6 +132,39 @@ class _Handle:
 
 
 # ----------------------------------------------------------------------- problems
+class CscMatrix:
+    """A (batch of) SparseMatrixCSC{Float64,Int64}, the reference's storage of A and
+    G (src/Socp.jl:25,29): one pattern (colptr, rowval), values ``nzval`` of shape
+    (nnz,) -- one matrix shared by the batch -- or (B, nnz).  ``index_base`` is 1
+    for arrays taken from Julia, 0 for scipy's.  The library assembles the dense
+    operands on the device (socp_b200_set_data_csc); nothing is densified here."""
+
+    def __init__(self, shape, colptr, rowval, nzval, index_base: int = 0):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.colptr = np.ascontiguousarray(colptr, dtype=np.int64)
+        self.rowval = np.ascontiguousarray(rowval, dtype=np.int64)
+        self.nzval = _f64(nzval)
+        self.index_base = int(index_base)
+        assert self.colptr.shape == (self.shape[1] + 1,)
+        assert self.nzval.shape[-1] == self.rowval.shape[0]
+        self.shared = (self.nzval.ndim == 1)
+
+    @classmethod
+    def from_scipy(cls, m, values=None) -> "CscMatrix":
+        """From a scipy.sparse matrix (pattern + values), or its pattern with per-problem ``values`` (B, nnz)."""
+        m = m.tocsc()
+        m.sort_indices()
+        return cls(m.shape, m.indptr, m.indices, m.data if values is None else values, 0)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.rowval.shape[0])
+
+    def c_struct(self) -> L.Csc:
+        return L.Csc(self.nnz, self.colptr.ctypes.data_as(L.c_int64_p), self.rowval.ctypes.data_as(L.c_int64_p),
+                     self.nzval.ctypes.data_as(L.c_double_p), self.index_base)
+
+
 class BatchProblem:
     """B independent problems sharing (n, p, cones).
 
@@ -150,9 +183,20 @@ class BatchProblem:
         self.k = sum(cn.dim for cn in self.cones)
         self.h = _f64(h)
         assert self.h.shape == (self.B, self.k)                     # src/Socp.jl:47
-        G = np.asarray(G, dtype=np.float64)
-        self.shared_G = (G.ndim == 2)
-        if self.shared_G:
+        self.G_csc = G if isinstance(G, CscMatrix) else None
+        self.A_csc = A if isinstance(A, CscMatrix) else None
+        if self.G_csc is not None:
+            assert self.G_csc.shape == (self.k, self.n)                 # src/Socp.jl:45-46
+            assert self.G_csc.shared or self.G_csc.nzval.shape[0] == self.B
+            self.shared_G = self.G_csc.shared
+            self.G_cm = None
+            G = None
+        else:
+            G = np.asarray(G, dtype=np.float64)
+            self.shared_G = (G.ndim == 2)
+        if self.G_csc is not None:
+            pass
+        elif self.shared_G:
             Gl = G.T if colmajor else G
             assert Gl.shape == (self.k, self.n)                     # src/Socp.jl:45-46
             self.G_cm = _f64(Gl.T)                                  # (n, k) C-order == k x n column-major
@@ -163,15 +207,26 @@ class BatchProblem:
             else:
                 assert G.shape == (self.B, self.k, self.n)
                 self.G_cm = _f64(G.transpose(0, 2, 1))
-        A = np.asarray(A, dtype=np.float64)
         b = _f64(b)
         if b.ndim == 1 and b.size == 0:
             b = b.reshape(self.B, 0)
         self.b = b
         assert self.b.ndim == 2 and self.b.shape[0] == self.B
         self.p = self.b.shape[1]
-        self.shared_A = (A.ndim == 2 and self.p > 0)
-        if self.p == 0:
+        assert (self.A_csc is not None) == (self.G_csc is not None) or self.p == 0, \
+            "A and G must both be CscMatrix (or both dense) when there are equality rows"
+        if self.A_csc is not None and self.p > 0:
+            assert self.A_csc.shape == (self.p, self.n)                 # src/Socp.jl:43-44
+            assert self.A_csc.shared or self.A_csc.nzval.shape[0] == self.B
+            self.shared_A = self.A_csc.shared
+            self.A_cm = None
+        else:
+            self.A_csc = None
+            A = np.asarray(A, dtype=np.float64)
+            self.shared_A = (A.ndim == 2 and self.p > 0)
+        if self.A_csc is not None:
+            pass
+        elif self.p == 0:
             self.A_cm = np.zeros((self.B, self.n, 0))
         elif self.shared_A:
             Al = A.T if colmajor else A
@@ -195,11 +250,13 @@ class BatchProblem:
         return self.p
 
     def G_dense(self, i: int) -> np.ndarray:
+        assert self.G_csc is None, "CSC problems are assembled on the device; there is no host-side dense copy"
         return (self.G_cm if self.shared_G else self.G_cm[i]).T
 
     def A_dense(self, i: int) -> np.ndarray:
         if self.p == 0:
             return np.zeros((0, self.n))
+        assert self.A_csc is None, "CSC problems are assembled on the device; there is no host-side dense copy"
         return (self.A_cm if self.shared_A else self.A_cm[i]).T
 
 
@@ -293,9 +350,16 @@ class BatchSolverState:
             return
         flags = (1 if prob.shared_A else 0) | (2 if prob.shared_G else 0)
         sing = None if prob.sing is None else prob.sing.ctypes.data_as(L.c_uint8_p)
-        rc = h.lib.socp_b200_set_data(h.ptr, _dp(prob.c), _dp(prob.A_cm) if prob.p else None,
-                                      _dp(prob.b) if prob.p else None, _dp(prob.G_cm), _dp(prob.h), sing, flags)
-        h.check(rc, "socp_b200_set_data")
+        if prob.G_csc is not None:
+            Gs = prob.G_csc.c_struct()
+            As = prob.A_csc.c_struct() if prob.p else None
+            rc = h.lib.socp_b200_set_data_csc(h.ptr, _dp(prob.c), C.byref(As) if prob.p else None,
+                                              _dp(prob.b) if prob.p else None, C.byref(Gs), _dp(prob.h), sing, flags)
+            h.check(rc, "socp_b200_set_data_csc")
+        else:
+            rc = h.lib.socp_b200_set_data(h.ptr, _dp(prob.c), _dp(prob.A_cm) if prob.p else None,
+                                          _dp(prob.b) if prob.p else None, _dp(prob.G_cm), _dp(prob.h), sing, flags)
+            h.check(rc, "socp_b200_set_data")
         self._loaded_id = id(prob)
 
     def get_sing(self) -> np.ndarray:
@@ -326,7 +390,9 @@ def solve_socp_batch(prob: BatchProblem, ss: BatchSolverState, params: Optional[
     pobj = np.empty(B)
     dobj = np.empty(B)
     prm = params if params is not None else default_params()
-    if reload or ss._loaded_id != id(prob):
+    if prob.G_csc is not None:
+        ss.load(prob, force=reload)              # CSC in: assembled on the device, then the resident-data solve
+    if prob.G_csc is None and (reload or ss._loaded_id != id(prob)):
         # Problem(...) + solve_socp(prob, ss) in one call: upload, solve and download overlap on the fused path
         assert (prob.n, prob.p, prob.B) == (h.n, h.p, h.batch) and prob.cones == h.cones
         flags = (1 if prob.shared_A else 0) | (2 if prob.shared_G else 0)

@@ -291,6 +291,100 @@ def test_shared_G_batch():
     assert np.array_equal(ra.status, rb.status) and np.array_equal(ra.x, rb.x)
 
 
+def _csc_of(prob):
+    """The reference's storage of one batch (SparseMatrixCSC, src/Socp.jl:25,29): the union pattern of the
+    batch's dense G (and A) with per-problem values, built with scipy on the host -- test-side only."""
+    import scipy.sparse as sp
+    out = []
+    for M_cm, shared, rows in ((prob.G_cm, prob.shared_G, prob.k), (prob.A_cm, prob.shared_A, prob.p)):
+        if rows == 0:
+            out.append(None)
+            continue
+        M = M_cm[None] if shared else M_cm                      # (B, n, rows): column-major per problem
+        pat = sp.csc_matrix((np.abs(M).max(axis=0) != 0).T.astype(np.float64))
+        pat.sort_indices()
+        cols = np.repeat(np.arange(prob.n), np.diff(pat.indptr))
+        vals = M[:, cols, pat.indices]                          # (B, nnz) in CSC order
+        out.append((pat, vals[0] if shared else np.ascontiguousarray(vals)))
+    return out
+
+
+@pytest.mark.parametrize("cfg,B,base", [("C2", 300, 1), ("C3", 500, 0), ("P1", 64, 1)])
+def test_csc_ingestion_bit_exact(cfg, B, base):
+    """socp_b200_set_data_csc (the reference's SparseMatrixCSC fields in, dense operands assembled on the
+    device) must give bit-identical results to socp_b200_set_data with the densified matrices."""
+    if cfg == "P1":
+        dense = gen.random_feasible(B, 20, 3, (sb.POC(0, 6), sb.SOC(6, 5), sb.SOC(11, 9)), 0.1)
+    else:
+        dense = gen.make_config(cfg, batch=B)
+    (Gp, Gv), A_ = _csc_of(dense)
+    def mk(pat, vals):
+        return sb.CscMatrix(pat.shape, pat.indptr + base, pat.indices + base, vals, index_base=base)
+    G = mk(Gp, Gv)
+    A = mk(*A_) if A_ is not None else np.zeros((B, 0, dense.n))
+    if cfg == "C2":
+        assert G.nnz == 50 + 50 * 50 and A.nnz == 50           # -I, F, and the budget row: half of G is structural zero
+    sparse = sb.BatchProblem(dense.c, A, dense.b, G, dense.h, dense.cones, sing=dense.sing)
+    for path in (sb.PATH_AUTO, sb.PATH_TILED):
+        rd = sb.solve_socp_batch(dense, sb.SolverState(dense), sb.default_params(path=path))
+        rs = sb.solve_socp_batch(sparse, sb.SolverState(sparse), sb.default_params(path=path))
+        for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+            assert np.array_equal(getattr(rd, f), getattr(rs, f)), (path, f)
+        if cfg != "P1":                                          # the mixed-cone family is fragile under the reference's
+            assert (rs.status == sb.STATUS_CONVERGED).all()      # algorithm (DESIGN.md section 2); equality is the point
+        else:
+            assert (rs.status == sb.STATUS_CONVERGED).sum() >= B // 3
+
+
+def test_csc_shared_pattern_and_values():
+    """One SparseMatrixCSC shared by the whole batch (SOCP_FLAG_SHARED_G) == the dense shared-G upload;
+    `sing` computed on the device from the assembled matrix."""
+    base = gen.make_config("C3", batch=1)
+    import scipy.sparse as sp
+    B = 6
+    rng = np.random.default_rng(3)
+    Gd = base.G_dense(0) * (rng.random((base.k, base.n)) < 0.4)
+    Gd[np.arange(base.n), np.arange(base.n)] += 1.0             # keep full column rank
+    e = (np.arange(base.k) % 4 == 0).astype(np.float64)      # identity element of 10 x SOC(4)
+    h = e[None] * (1.0 + 0.1 * np.arange(B))[:, None]           # x = 0, s = h strictly inside the cone
+    c = np.repeat((-Gd.T @ e)[None], B, axis=0)                 # z = e strictly dual feasible
+    none = (np.zeros((B, 0, base.n)), np.zeros((B, 0)))
+    dense = sb.BatchProblem(c, *none, Gd, h, base.cones)
+    sparse = sb.BatchProblem(c, *none, sb.CscMatrix.from_scipy(sp.csc_matrix(Gd)), h, base.cones)
+    assert sparse.shared_G and sparse.G_csc.nnz < base.k * base.n // 2
+    ssd, sss = sb.SolverState(dense), sb.SolverState(sparse)
+    rd = sb.solve_socp_batch(dense, ssd, sb.default_params(path=sb.PATH_TILED))
+    rs = sb.solve_socp_batch(sparse, sss, sb.default_params(path=sb.PATH_TILED))
+    assert np.array_equal(ssd.get_sing(), sss.get_sing())
+    assert np.array_equal(rd.status, rs.status) and np.array_equal(rd.x, rs.x) and np.array_equal(rd.iters, rs.iters)
+
+
+def test_csc_rejects_broken_patterns():
+    """The SparseMatrixCSC invariants are the usage contract: violations are SOCP_ERR_LAYOUT / _SIZE, not UB."""
+    prob = gen.make_config("C3", batch=2)
+    (Gp, Gv), _ = _csc_of(prob)
+    none = (np.zeros((2, 0, prob.n)), np.zeros((2, 0)))
+    def attempt(colptr, rowval, vals, base=0):
+        G = sb.CscMatrix(Gp.shape, colptr, rowval, vals, index_base=base)
+        bad = sb.BatchProblem(prob.c, *none, G, prob.h, prob.cones)
+        sb.SolverState(bad).load(bad)
+    attempt(Gp.indptr, Gp.indices, Gv)                           # the intact pattern loads
+    rv = Gp.indices.copy(); rv[[0, 1]] = rv[[1, 0]]              # unsorted rows inside a column
+    with pytest.raises(sb.SocpError):
+        attempt(Gp.indptr, rv, Gv)
+    rv = Gp.indices.copy(); rv[1] = rv[0]                        # duplicate entry
+    with pytest.raises(sb.SocpError):
+        attempt(Gp.indptr, rv, Gv)
+    rv = Gp.indices.copy(); rv[-1] = prob.k                      # row out of range
+    with pytest.raises(sb.SocpError):
+        attempt(Gp.indptr, rv, Gv)
+    cp = Gp.indptr.copy(); cp[-1] -= 1                           # colptr does not span nnz
+    with pytest.raises(sb.SocpError):
+        attempt(cp, Gp.indices, Gv)
+    with pytest.raises(sb.SocpError):                            # 1-based arrays declared 0-based
+        attempt(Gp.indptr + 1, Gp.indices + 1, Gv, base=0)
+
+
 def test_solve_host_pipelined_matches_two_step():
     """socp_b200_solve_host (chunked upload / solve / download on three streams) must return exactly what
     set_data + solve return: same kernel, same data, only the schedule differs."""
