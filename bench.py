@@ -186,11 +186,15 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--batch", type=int, default=None, help="problems per GPU (default: the config's)")
     ap.add_argument("--path", default="auto", choices=["auto", "tiled", "fused"])
-    ap.add_argument("--ref-sample", type=int, default=2000)
-    ap.add_argument("--cpu-sample", type=int, default=2000)
+    ap.add_argument("--ref-sample", type=int, default=None, help="problems per reference-arm step (default: per config)")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="problems of the cpu_baseline leg (default: per config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    # bounded CPU samples of the workload: tens of core-seconds per pass of the C oracle (C2: the whole 10k batch)
+    cpu_default = {"C2": 10000, "C3": 50000, "C4": 16, "C5": 1}.get(args.config, 64)
+    args.ref_sample = args.ref_sample or cpu_default
+    args.cpu_sample = args.cpu_sample or cpu_default
 
     if args.impl == "reference":
         return reference_arm(args)
@@ -338,7 +342,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cpu_baseline_run(args.config, 64, threads)
+            cpu_baseline_run(args.config, min(args.cpu_sample, 64), threads)
             v, dt, r = cpu_baseline_run(args.config, args.cpu_sample, threads)
             cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_sample} problems of the same workload in {dt:.2f} s, C oracle "
