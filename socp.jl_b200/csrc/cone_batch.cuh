@@ -164,32 +164,53 @@ bk_build_gt(BLayout L, int batch, int n, const double* __restrict__ G, int64_t s
             Gt[((size_t)b * n + col) * ldgt + r] = iwb[(size_t)b * L.k + r] * G[(int64_t)b * sG + (int64_t)col * L.k + r];
         }
     }
+    // second-order cones: a lane group owns (problem, cone, chunk of GT_CH columns); the cone's wbar and scalars are
+    // loaded once per chunk and the columns go two at a time, so that two columns' loads and two shuffle chains are
+    // in flight per group (four at a time needs 115 registers: no more bytes in flight per SM at the lower occupancy) (the kernel is bound by bytes in flight, not by arithmetic)
+    constexpr int GT_CH = 8, GT_NC = 2;       // columns per chunk, columns in flight
     const int lane = threadIdx.x & 31;
     const int spw = 32 / L.lpc;
-    const long long total = (long long)batch * n * L.nsoc;
+    const unsigned nch = (unsigned)(n + GT_CH - 1) / GT_CH;
+    const long long total = (long long)batch * L.nsoc * nch;
     const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
     for (long long base = wglobal * spw; base < total; base += wstride * spw) {
         const long long gid = base + lane / L.lpc;
         const bool valid = gid < total;
-        const unsigned q = valid ? (unsigned)gid : 0u, per = (unsigned)n * (unsigned)L.nsoc;    // < 2^32 (host-checked)
-        const int b = (int)(q / per);
-        const int rem = (int)(q - (unsigned)b * per);
-        const int col = rem / L.nsoc, slot = rem - col * L.nsoc;
-        const BLane l = b_lane(L, (long long)b * L.nsoc + slot, valid ? (long long)(b + 1) * L.nsoc : 0, lane);
-        const bool on = l.valid && !(active && !active[b]);
-        const double* gc = G + (int64_t)b * sG + (int64_t)col * L.k;
-        const double* wbb = wb + (size_t)b * L.k;
-        double wv[4], gv[4];
-        B_FOR_E { const bool t = on && l.tail(e); wv[e] = t ? wbb[l.at(e)] : 0.0; gv[e] = t ? gc[l.at(e)] : 0.0; }
-        const double dl = b_dot(wv, gv, L.lpc);                                      // src/scalings.jl:145-148
-        if (!on) continue;
-        const double* es = eta + (size_t)b * 4 * L.nwork + L.soc_work[slot];
-        const double ie = es[L.nwork], g0 = gc[l.offs], w0 = wbb[l.offs];
-        const double cst = -g0 + dl * es[3 * L.nwork];                               // :151
-        double* oc = Gt + ((size_t)b * n + col) * ldgt;
-        B_FOR_E if (l.tail(e)) oc[l.at(e)] = ie * (gv[e] + cst * wv[e]);             // :153-155
-        if (l.g == 0) oc[l.offs] = ie * (w0 * g0 - dl);                              // :152
+        const unsigned q = valid ? (unsigned)gid : 0u;                                           // < 2^32 (host-checked)
+        const unsigned cone = q / nch;                                                           // b * nsoc + slot
+        const int c0 = (int)(q - cone * nch) * GT_CH;
+        const BLane l = b_lane(L, cone, valid ? (long long)batch * L.nsoc : 0, lane);
+        const int bb = l.b;
+        const bool on = l.valid && !(active && !active[bb]);
+        const double* wbb = wb + (size_t)bb * L.k;
+        const double* es = eta + (size_t)bb * 4 * L.nwork + L.soc_work[l.slot];
+        double wv[4];
+        B_FOR_E wv[e] = (on && l.tail(e)) ? wbb[l.at(e)] : 0.0;
+        const double ie = on ? es[L.nwork] : 0.0, e3 = on ? es[3 * L.nwork] : 0.0, w0 = on ? wbb[l.offs] : 0.0;
+#pragma unroll 2
+        for (int cc = 0; cc < GT_CH; cc += GT_NC) {
+            bool onc[GT_NC];
+            double gv[GT_NC][4], g0[GT_NC], dl[GT_NC];
+            const double* gbase = G + (int64_t)bb * sG + (int64_t)(c0 + cc) * L.k + l.offs;
+#pragma unroll
+            for (int j = 0; j < GT_NC; ++j) {
+                onc[j] = on && c0 + cc + j < n;
+                const double* gc = gbase + j * L.k;
+                B_FOR_E gv[j][e] = (onc[j] && l.tail(e)) ? gc[l.g + e * l.lpc] : 0.0;
+                g0[j] = onc[j] ? gc[0] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < GT_NC; ++j) dl[j] = b_dot(wv, gv[j], L.lpc);                      // src/scalings.jl:145-148
+#pragma unroll
+            for (int j = 0; j < GT_NC; ++j) {
+                if (!onc[j]) continue;
+                const double cst = -g0[j] + dl[j] * e3;                                           // :151
+                double* oc = Gt + ((size_t)bb * n + (c0 + cc + j)) * ldgt + l.offs;
+                B_FOR_E if (l.tail(e)) oc[l.g + e * l.lpc] = ie * (gv[j][e] + cst * wv[e]);       // :153-155
+                if (l.g == 0) oc[0] = ie * (w0 * g0[j] - dl[j]);                                  // :152
+            }
+        }
     }
 }
 

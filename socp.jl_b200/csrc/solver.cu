@@ -232,8 +232,9 @@ void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, const double*
     constexpr int BS = 512;
     const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
     dim3 grid(nrhs, sh.batch);
-    // few (rhs, problem) pairs: a CTA of 1024 threads walks its factor four times faster than one of 256
-    const bool wide = (long long)nrhs * sh.batch < 148;
+    // few (rhs, problem) pairs (at most two 1024-thread CTAs per SM, one wave): a CTA of 1024 threads walks its
+    // factor four times faster than one of 256
+    const bool wide = (long long)nrhs * sh.batch <= 2 * 148;
     auto fwd = [&](size_t smem, const double* Lp, int rows, int blk0, double* Xp) {
         if (wide) LAUNCH(sh, k_trsv_blk_fwd<1024>, grid, 1024, smem + (size_t)4 * rows * sizeof(double), Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
         else LAUNCH(sh, k_trsv_blk_fwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
@@ -276,7 +277,8 @@ void launch_build_gt(Shard& sh, bool identity, const int* active) {
     const int n = w.L.n;
     const long long pairs = (long long)sh.batch * n * std::max({sh.bl.nsoc, sh.bl.kpoc, 1});
     if (sh.bl_ok && !identity && pairs < (1LL << 31)) {
-        const long long thr = std::max((long long)sh.batch * n * sh.bl.nsoc * sh.bl.lpc, (long long)sh.batch * n * sh.bl.kpoc);
+        // one lane group per (problem, cone, chunk of 8 columns); one thread per positive-orthant entry
+        const long long thr = std::max((long long)sh.batch * ((n + 7) / 8) * sh.bl.nsoc * sh.bl.lpc, (long long)sh.batch * n * sh.bl.kpoc);
         const int grid = (int)std::max(1LL, std::min((thr + 255) / 256, 148LL * 16));
         LAUNCH(sh, bk_build_gt, grid, 256, 0, sh.bl, sh.batch, n, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, active);
         return;
