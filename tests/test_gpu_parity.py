@@ -427,6 +427,10 @@ GENERIC_LAYOUTS = {
     "mixed_n60_p9": (60, 9, (sb.POC(0, 10), sb.SOC(10, 30), sb.SOC(40, 30), sb.SOC(70, 30))),
     "tiny_cones": (8, 1, (sb.POC(0, 3), sb.SOC(3, 1), sb.SOC(4, 2), sb.SOC(6, 3), sb.SOC(9, 7))),
     "many_small": (30, 4, gen.soc_cones(20, 3)),
+    # the limits of the fused kernel (f2_plan): n = 64, p = 32, a 128-dimensional cone (32 lanes x 4 elements)
+    "edge_n64": (64, 0, (sb.POC(0, 16), sb.SOC(16, 64))),
+    "edge_p32": (40, 32, (sb.POC(0, 50), sb.SOC(50, 20))),
+    "edge_soc128": (24, 0, (sb.SOC(0, 128),)),
 }
 
 
