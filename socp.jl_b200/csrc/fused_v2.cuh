@@ -961,7 +961,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                     tsync<NW>();
                     if (pb == 1) {
                         // p <= 8: warp 0 alone forms M = A HiAt (:50), factors it (:51) and inverts it -- no team barrier
-                        if (warp == 0) {
+                        if (p == 1) {
+                            // one equality row (the budget row of C2): M is a scalar, no 8 x 8 factorisation
+                            if (warp == 0) {
+                                double acc = 0.0;
+                                for (int c = lane; c < n; c += 32) acc = fma(A[c], HiAt[c], acc);
+                                acc = warp_sum(acc);
+                                if (lane == 0) {
+                                    if (!(acc > 0.0)) s_fail = 1;
+                                    Minv[0] = 1.0 / acc;
+                                }
+                            }
+                        } else if (warp == 0) {
                             for (int e = 0; e < p * p; ++e) {
                                 const int i = e % p, j = e / p;
                                 double acc = 0.0;

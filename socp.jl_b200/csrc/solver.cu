@@ -682,11 +682,12 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
     sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
     sh.any_sing = false;
-    // Chunk boundaries: a short first chunk (two waves of resident CTAs) so that the solve starts as soon as possible,
-    // then up to 8 equal chunks of at least 4 waves each.
+    // Chunk boundaries: two short chunks first (one wave of resident CTAs, then two: PCIe delivers problems about
+    // twice as fast as the kernel retires them, so the upload of each next chunk ends before the previous one is
+    // solved) so that the solve starts as soon as possible, then up to 8 equal chunks of at least 4 waves each.
     const int slots = sh.fused2.num_sms * sh.fused2.ctas_per_sm;
     std::vector<int> bounds{0};
-    if (B > 8 * slots) bounds.push_back(2 * slots);
+    if (B > 8 * slots) { bounds.push_back(slots); bounds.push_back(3 * slots); }
     {
         const int rest = B - bounds.back();
         const int nrest = std::max(1, std::min(8, rest / std::max(1, 4 * slots)));

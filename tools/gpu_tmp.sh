@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_2gpu_ref.json 2> gpurun_out/bench_2gpu_ref.err
+python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests.log
+python bench.py --no-cpu-baseline > gpurun_out/bench_try.json 2> gpurun_out/bench_try.err
+python bench.py --no-cpu-baseline > gpurun_out/bench_try2.json 2> gpurun_out/bench_try2.err
