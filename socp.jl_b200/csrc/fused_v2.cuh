@@ -130,14 +130,14 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     P.oX = P.oR + P.ldh * P.npad;
     P.oA = take(p * n); P.oAt = take(p * P.npad); P.oHiAt = take(n * p); P.oK = take(n * p);
     P.oM = take(p ? P.ldm * P.ppad : 0); P.oMX = take(p ? f2_xsize(P.pb) : 0); P.oMinv = take(p * p);
-    P.oDinv = take(2 * 8 * 12);
+    P.oDinv = take((P.nw > 1 ? 2 : 1) * 8 * 12);
     P.oc = take(n); P.ox = take(n); P.odx = take(n); P.on0 = take(P.npad); P.ocx = take(n); P.okd = take(n);
     P.ob = take(p); P.oy = take(p); P.ody = take(p); P.ocy = take(p); P.omd = take(p);
     P.odw = take(P.kpad); P.ohc = take(std::max(P.nsoc, 1) * P.npad);
     P.oh = take(k); P.oz = take(k); P.os = take(k); P.olam = take(k); P.owb = take(k); P.oiwb = take(P.kpoc);
     P.odz = take(k); P.ods = take(k); P.ok0 = take(k); P.ok2 = take(k); P.ou = take(k);
     P.ocs = take(F2_CS * std::max(P.nsoc, 1));
-    P.oscr = take(2 * 8 * 8);
+    P.oscr = take(P.nw > 1 ? 2 * 8 * 8 : 0);     // team_reduce scratch: a one-warp team reduces in registers
     P.odesc = take(f2_trail_base(P.nb, P.nb)); P.odescm = take(p ? f2_trail_base(P.pb, P.pb) : 0);   // uint2 = 8 bytes each
     P.total = at;
     P.smem = (size_t)at * sizeof(double);
@@ -152,7 +152,7 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     const int per_sm = 228 * 1024;
     const int threads = P.nw * 32;
     const int reg_cap = P.variant == 0 ? 16 : (P.variant == 1 ? 4 : 2);     // matches the __launch_bounds__ below
-    P.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (P.smem + 1024 + 512)), 2048 / threads, 32, reg_cap}));
+    P.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (P.smem + 1024 + 256)), 2048 / threads, 32, reg_cap}));
     P.fits = true;
 }
 
@@ -505,7 +505,7 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, c
     const int la = fk * ld + fr;
     for (int b = 0; b < nbl; ++b) {
         const int b0 = b * 8;
-        double* Db = Dinv + (b & 1) * 96;
+        double* Db = Dinv + ((NW > 1) ? (b & 1) * 96 : 0);      // double-buffered only when warp 0 runs ahead
         if (warp == 0) {
             __syncwarp();
             double xc[8];
