@@ -1,4 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --config C4 --steps 3 --warmup 3 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err
-timeout 600 python bench.py --config C5 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
+python tools/run_case.py C2 --batch 10000 --reps 3 > gpurun_out/nw8_10k.log 2>&1
+SOCP_B200_F2_NW4=1 python tools/run_case.py C2 --batch 10000 --reps 3 > gpurun_out/nw4_10k.log 2>&1
+python tools/run_case.py C2 --batch 296 --reps 3 > gpurun_out/nw8_296.log 2>&1
+SOCP_B200_F2_NW4=1 python tools/run_case.py C2 --batch 296 --reps 3 > gpurun_out/nw4_296.log 2>&1
+python tools/run_case.py C2 --batch 148 --reps 3 > gpurun_out/nw8_148.log 2>&1
+SOCP_B200_F2_NW4=1 python tools/run_case.py C2 --batch 148 --reps 3 > gpurun_out/nw4_148.log 2>&1
