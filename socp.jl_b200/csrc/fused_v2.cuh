@@ -417,6 +417,10 @@ __device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* 
     }
 }
 
+#ifdef SOCP_PHASE_TIMING
+__device__ unsigned long long g_phase_clk2[16];       // tools/phase_timing.py; slots 13 / 15: inside f2_chol_inv (warp 0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ blocked Cholesky + inverse
 // Factor of one 8x8 diagonal tile by one warp.  The Cholesky factor is computed by all lanes redundantly in
 // registers (no shuffles); lane c (mod 8) then computes column c of its inverse by forward substitution, so that
@@ -505,9 +509,16 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, c
                                            int* fail, int lane, int warp) {
     const int fr = lane >> 2, fk = lane & 3;
     const int la = fk * ld + fr;
+#ifdef SOCP_PHASE_TIMING
+    const bool pt_on = (NW == 8) && !WRITE_L && threadIdx.x == 0 && blockIdx.x == 0;
+    long long pt_c = clock64();
+#endif
     for (int b = 0; b < nbl; ++b) {
         const int b0 = b * 8;
         double* Db = Dinv + ((NW > 1) ? (b & 1) * 96 : 0);      // double-buffered only when warp 0 runs ahead
+#ifdef SOCP_PHASE_TIMING
+        if (pt_on) pt_c = clock64();
+#endif
         if (warp == 0) {
             __syncwarp();
             double xc[8];
@@ -522,7 +533,13 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, c
                 }
             }
         }
+#ifdef SOCP_PHASE_TIMING
+        if (pt_on) { const long long t = clock64(); atomicAdd(&g_phase_clk2[13], (unsigned long long)(t - pt_c)); pt_c = t; }
+#endif
         tsync<NW>();                                   // (1) Dinv_b visible; trailing update of step b-1 complete
+#ifdef SOCP_PHASE_TIMING
+        if (pt_on) { const long long t = clock64(); atomicAdd(&g_phase_clk2[15], (unsigned long long)(t - pt_c)); pt_c = t; }
+#endif
         if (*fail) return 0;
         // ---- panel: H(i,b) <- H(i,b) Dinv_b'  (i > b);   X(b,c) <- Dinv_b X(b,c)  (c < b)
         for (int t = warp; t < nbl - 1; t += NW) {
@@ -650,7 +667,6 @@ struct F2Args {
 };
 
 #ifdef SOCP_PHASE_TIMING
-__device__ unsigned long long g_phase_clk2[16];
 #define PT2_DECL() long long pt_t0 = 0
 #define PT2_INIT() pt_t0 = clock64()
 #define PT2_MARK(idx)                                                             \
@@ -666,7 +682,8 @@ __device__ unsigned long long g_phase_clk2[16];
 #define PT2_INIT()
 #define PT2_MARK(idx)
 #endif
-enum { P2_LOAD = 0, P2_RESID, P2_HEAD_GT, P2_SYRK, P2_CHOL, P2_EQ, P2_SOLVE, P2_INIT, P2_TAIL, P2_MIDPOST, P2_OUT };
+enum { P2_LOAD = 0, P2_RESID, P2_HEAD_GT, P2_SYRK, P2_CHOL, P2_EQ, P2_SOLVE, P2_INIT, P2_TAIL, P2_MIDPOST, P2_OUT,
+       P2_XTX, P2_SOLVE_A, P2_SOLVE_B, P2_N0 };
 
 // per-thread view of one second-order cone slot: element e of this lane is index g + e*lpc of the cone; bit e of
 // `tm` says that this element exists and belongs to the tail (index > 0)
@@ -945,6 +962,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
         for (;;) {
             // ---- n0 = G'u + sc*dx                                                   src/densesolver.jl:66-67
             gemv_cols_v<NW>(G, ldg, k, n, u, lane, warp, [&](int c, double acc) { n0[c] = acc + sc * dx[c]; });
+            PT2_MARK(P2_N0);
             if (phase != 2) {
                 // ---- KKT factor, src/densesolver.jl:41-52
                 f2_syrk_w<NW, MAXT>(G, ldg, kpad, n, nb, dw, hc, nsoc, npad, H, ldh, tl, lane, warp);   // :42-43
@@ -953,6 +971,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                 tsync<NW>();
                 PT2_MARK(P2_SYRK);
                 int ok = f2_chol_inv<NW>(H, X, Dinv, desc, nb, ldh, &s_fail, lane, warp);          // :47
+                PT2_MARK(P2_XTX);              // slot 11 = f2_chol_inv; slot P2_CHOL below = f2_xtx (tools/phase_timing.py)
                 if (ok) f2_xtx<NW, MAXT>(X, ldh, nb, H, tl, lane, warp);                         // :48  Li = H^-1 (explicit)
                 tsync<NW>();
                 PT2_MARK(P2_CHOL);
@@ -1060,6 +1079,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
             if (p > 0)
                 gemv_cols<NW, false>(Km, n, n, p, n0, lane, warp, [&](int c, double acc) { cy[c] = acc - sc * md[c]; });
             tsync<NW>();
+            PT2_MARK(P2_SOLVE_A);
             const double* cxv = cx;
             gemv_rows_v<NW>(G, ldg, k, n, cxv, D::split_k(P), lane, warp, [&](int r, double acc) { u[r] = acc - k2[r]; });   // :84-85
             tsync<NW>();

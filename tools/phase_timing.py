@@ -24,8 +24,9 @@ fn = lib.socp_b200_debug_phase_clocks2
 fn(buf, 1)
 r = sb.solve_socp_batch(prob, ss, prm, reload=False, want_iterates=False)
 fn(buf, 0)
-names = ["load", "scaling+resid", "hc+head", "n0+syrk", "chol+inverse", "eq", "solve_mid", "init", "tail", "mid/post", "out", "-"]
-tot = sum(buf[i] for i in range(12))
+names = ["load", "scaling+resid", "hc+head", "syrk", "xtx", "eq", "solve: G cx", "init", "tail", "mid/post", "out",
+         "chol_inv", "solve: H n0, K n0", "  (chol: diag factor, warp 0)", "n0 = G'u", "  (chol: wait at barrier 1)"]
+tot = sum(buf[i] for i in range(16) if i not in (13, 15))       # 13 and 15 are parts of chol_inv
 print(a.config, "batch", a.batch, "solve_ms %.3f" % r.timings["solve_ms"], "mean iters %.2f" % r.iters.mean())
 for i, nm in enumerate(names):
     print(f"  {nm:14s} {buf[i]:12d} clk  {100.0*buf[i]/max(tot,1):5.1f}%")
