@@ -1,6 +1,4 @@
 #!/bin/bash
-bash tools/gpu_round.sh
-python tools/phase_timing.py C2 --batch 148 > gpurun_out/phase_c2_fine_148.txt 2>&1
-python tools/phase_timing.py C2 --batch 2960 > gpurun_out/phase_c2_fine_2960.txt 2>&1
-python tools/phase_timing.py C3 --batch 17760 > gpurun_out/phase_c3_fine.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_4gpu.json 2> gpurun_out/bench_4gpu.err
