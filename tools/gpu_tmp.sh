@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/bench_8gpu.json 2> gpurun_out/bench_8gpu.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_4gpu.json 2> gpurun_out/bench_4gpu.err
+for v in A B; do
+SOCP_B200_LIB=$PWD/socp.jl_b200/lib/libsocp_b200_$v.so python bench.py --no-cpu-baseline > gpurun_out/bench_var$v.json 2> gpurun_out/bench_var$v.err
+SOCP_B200_LIB=$PWD/socp.jl_b200/lib/libsocp_b200_$v.so python bench.py --config C3 --no-cpu-baseline > gpurun_out/bench_c3_var$v.json 2> gpurun_out/bench_c3_var$v.err
+done
