@@ -76,6 +76,10 @@ __device__ __forceinline__ double fast_sqrt(double a) {
     return (a == 0.0) ? 0.0 : y;
 }
 
+// Batch index of a CTA of the batch-wide tiled kernels: grids are (tiles, by, bz) with the batch folded over y and z
+// (gridDim.y is capped at 65535); the kernel guards b < nbatch.  Host side: batch_grid() in solver.cu.
+__device__ __forceinline__ int batch_index() { return (int)(blockIdx.z * gridDim.y + blockIdx.y); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

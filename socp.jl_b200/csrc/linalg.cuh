@@ -42,8 +42,9 @@ struct GemvEpi {
 __global__ void __launch_bounds__(256)
 k_gemv_t(const double* __restrict__ M, int64_t strideM, int ld, int rows, int cols,
          const double* __restrict__ x, int64_t strideX, double* __restrict__ out, int64_t strideOut,
-         double alpha, GemvEpi epi, const int* __restrict__ active, const uint8_t* __restrict__ flag) {
-    const int b = blockIdx.y;
+         double alpha, GemvEpi epi, const int* __restrict__ active, const uint8_t* __restrict__ flag, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     if (flag && !flag[b]) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,8 +78,9 @@ k_gemv_t(const double* __restrict__ M, int64_t strideM, int ld, int rows, int co
 __global__ void __launch_bounds__(256)
 k_gemv_n(const double* __restrict__ M, int64_t strideM, int ld, int rows, int cols,
          const double* __restrict__ x, int64_t strideX, double* __restrict__ out, int64_t strideOut,
-         double alpha, GemvEpi epi, const int* __restrict__ active, const uint8_t* __restrict__ flag) {
-    const int b = blockIdx.y;
+         double alpha, GemvEpi epi, const int* __restrict__ active, const uint8_t* __restrict__ flag, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     if (flag && !flag[b]) return;
     __shared__ double part[8][33];
@@ -144,9 +146,10 @@ __global__ void __launch_bounds__(NW * NW * 32)
 k_syrk(const double* __restrict__ A, int64_t strideA, int lda, int N, int K,
        double* __restrict__ C, int64_t strideC, int ldc, double alpha, double beta,
        const double* __restrict__ addC, int64_t strideAdd, int ldadd, const uint8_t* __restrict__ addFlag,
-       const int* __restrict__ active, int first_col_only) {
+       const int* __restrict__ active, int first_col_only, int nbatch) {
     using Cfg = SyrkCfg<BT, NW, KT, KMAJOR>;
-    const int b = blockIdx.y;
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     // lower-triangle tile index -> (ti, tj), ti >= tj; first_col_only: the tiles (t, 0) of the first block column
     int t = blockIdx.x;

@@ -65,8 +65,9 @@ constexpr size_t TRSM_MMA_SMEM = sizeof(double) * (64 * PANEL_LDH + 64 * TRSM_LD
 
 __global__ void __launch_bounds__(256)
 k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const double* __restrict__ Xinv, int nblk,
-           const int* __restrict__ fail, const int* __restrict__ active) {
-    const int b = blockIdx.y;
+           const int* __restrict__ fail, const int* __restrict__ active, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     if (fail[b]) return;
     extern __shared__ __align__(16) double psm[];
@@ -126,8 +127,9 @@ k_trsm_mma(double* __restrict__ H, int64_t strideH, int ldh, int n, int j, const
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_trsv_blk_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, const double* __restrict__ Xinv,
-               int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
-    const int b = blockIdx.y;
+               int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     extern __shared__ double tsm[];
     double* xs = tsm;
@@ -202,8 +204,9 @@ k_trsv_blk_fwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, co
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_trsv_blk_bwd(const double* __restrict__ L, int64_t strideL, int ldl, int n, const double* __restrict__ Xinv,
-               int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active) {
-    const int b = blockIdx.y;
+               int nblk, int blk0, double* __restrict__ X, int64_t strideX, int ldx, const int* __restrict__ active, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     extern __shared__ double tsm[];
     double* xs = tsm;

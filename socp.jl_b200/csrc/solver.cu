@@ -119,8 +119,17 @@ namespace {
 #define LAUNCH(sh, kern, grid, block, smem, ...)                       \
     do {                                                               \
         kern<<<grid, block, smem, (sh).stream>>>(__VA_ARGS__);         \
+        CK(cudaPeekAtLastError());   /* configuration errors must not pass silently */ \
         (sh).launches++;                                               \
     } while (0)
+
+// Grid of a batch-wide tiled kernel: `tiles` CTAs per problem on x, the batch folded over y and z (gridDim.y and
+// gridDim.z are capped at 65535; the kernels recover b with batch_index() and guard b < nbatch).
+dim3 batch_grid(int tiles, int batch) {
+    const int gz = (batch + 65534) / 65535;
+    const int gy = (batch + gz - 1) / gz;
+    return dim3((unsigned)tiles, (unsigned)gy, (unsigned)gz);
+}
 
 GemvEpi epi(const double* v1 = nullptr, double c1 = 0, int64_t s1 = 0, const double* v2 = nullptr, double c2 = 0,
             int64_t s2 = 0, int acc = 0) {
@@ -135,14 +144,14 @@ GemvEpi epi(const double* v1 = nullptr, double c1 = 0, int64_t s1 = 0, const dou
 void gemv_t(Shard& sh, const double* M, int64_t sM, int ld, int rows, int cols, const double* x, int64_t sx,
             double* out, int64_t so, double alpha, GemvEpi e, const int* active, const uint8_t* flag = nullptr) {
     if (cols == 0) return;
-    dim3 grid((cols + 7) / 8, sh.batch);
-    LAUNCH(sh, k_gemv_t, grid, 256, 0, M, sM, ld, rows, cols, x, sx, out, so, alpha, e, active, flag);
+    dim3 grid = batch_grid((cols + 7) / 8, sh.batch);
+    LAUNCH(sh, k_gemv_t, grid, 256, 0, M, sM, ld, rows, cols, x, sx, out, so, alpha, e, active, flag, sh.batch);
 }
 void gemv_n(Shard& sh, const double* M, int64_t sM, int ld, int rows, int cols, const double* x, int64_t sx,
             double* out, int64_t so, double alpha, GemvEpi e, const int* active, const uint8_t* flag = nullptr) {
     if (rows == 0) return;
-    dim3 grid((rows + 31) / 32, sh.batch);
-    LAUNCH(sh, k_gemv_n, grid, dim3(32, 8), 0, M, sM, ld, rows, cols, x, sx, out, so, alpha, e, active, flag);
+    dim3 grid = batch_grid((rows + 31) / 32, sh.batch);
+    LAUNCH(sh, k_gemv_n, grid, dim3(32, 8), 0, M, sM, ld, rows, cols, x, sx, out, so, alpha, e, active, flag, sh.batch);
 }
 
 template <int BT, int NW, int KT, bool KM>
@@ -156,9 +165,9 @@ void syrk_launch(Shard& sh, const double* A, int64_t sA, int lda, int N, int K, 
         configured[sh.device] = true;
     }
     const int nt = (N + BT - 1) / BT;
-    dim3 grid(first_col_only ? nt : nt * (nt + 1) / 2, sh.batch);
+    dim3 grid = batch_grid(first_col_only ? nt : nt * (nt + 1) / 2, sh.batch);
     LAUNCH(sh, (k_syrk<BT, NW, KT, KM>), grid, Cfg::THREADS, Cfg::SMEM, A, sA, lda, N, K, C, sC, ldc, alpha, beta,
-           addC, sAdd, ldadd, addFlag, active, first_col_only ? 1 : 0);
+           addC, sAdd, ldadd, addFlag, active, first_col_only ? 1 : 0, sh.batch);
 }
 void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, int K, double* C, int64_t sC, int ldc,
           double alpha, double beta, const double* addC, int64_t sAdd, int ldadd, const uint8_t* addFlag,
@@ -194,8 +203,8 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
         LAUNCH(sh, k_potrf_diag_mma, sh.batch, 256, POTRF_MMA_SMEM, H, sH, ld, nn, j, Xinv, nblk, fail, active);
         const int below = nn - j - CHOL_NB;
         if (below > 0) {
-            dim3 grid((below + 127) / 128, sh.batch);
-            LAUNCH(sh, k_trsm_mma, grid, 256, TRSM_MMA_SMEM, H, sH, ld, nn, j, (const double*)Xinv, nblk, (const int*)fail, active);
+            dim3 grid = batch_grid((below + 127) / 128, sh.batch);
+            LAUNCH(sh, k_trsm_mma, grid, 256, TRSM_MMA_SMEM, H, sH, ld, nn, j, (const double*)Xinv, nblk, (const int*)fail, active, sh.batch);
         }
     };
     // Panels are taken in groups of CHOL_GROUP with the trailing update delayed (left-looking inside the group, right-
@@ -231,17 +240,17 @@ void potrs(Shard& sh, const double* L, int64_t sL, int ld, int nn, const double*
     if (nn == 0 || nrhs == 0) return;
     constexpr int BS = 512;
     const int nblk = (nn + CHOL_NB - 1) / CHOL_NB;
-    dim3 grid(nrhs, sh.batch);
+    dim3 grid = batch_grid(nrhs, sh.batch);
     // few (rhs, problem) pairs (at most two 1024-thread CTAs per SM, one wave): a CTA of 1024 threads walks its
     // factor four times faster than one of 256
     const bool wide = (long long)nrhs * sh.batch <= 2 * 148;
     auto fwd = [&](size_t smem, const double* Lp, int rows, int blk0, double* Xp) {
-        if (wide) LAUNCH(sh, k_trsv_blk_fwd<1024>, grid, 1024, smem + (size_t)4 * rows * sizeof(double), Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
-        else LAUNCH(sh, k_trsv_blk_fwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
+        if (wide) LAUNCH(sh, k_trsv_blk_fwd<1024>, grid, 1024, smem + (size_t)4 * rows * sizeof(double), Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active, sh.batch);
+        else LAUNCH(sh, k_trsv_blk_fwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active, sh.batch);
     };
     auto bwd = [&](size_t smem, const double* Lp, int rows, int blk0, double* Xp) {
-        if (wide) LAUNCH(sh, k_trsv_blk_bwd<1024>, grid, 1024, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
-        else LAUNCH(sh, k_trsv_blk_bwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active);
+        if (wide) LAUNCH(sh, k_trsv_blk_bwd<1024>, grid, 1024, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active, sh.batch);
+        else LAUNCH(sh, k_trsv_blk_bwd<256>, grid, 256, smem, Lp, sL, ld, rows, Xinv, nblk, blk0, Xp, sX, ldx, active, sh.batch);
     };
     if (nn <= 2 * BS) {
         const size_t smem = (size_t)(nn + 64) * sizeof(double);
@@ -284,8 +293,8 @@ void launch_build_gt(Shard& sh, bool identity, const int* active) {
         return;
     }
     const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
-    dim3 g((n + cols_per_cta - 1) / cols_per_cta, sh.batch);
-    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active);
+    dim3 g = batch_grid((n + cols_per_cta - 1) / cols_per_cta, sh.batch);
+    LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, identity ? 1 : 0, cols_per_cta, active, sh.batch);
 }
 void launch_scaling(Shard& sh, const int* active) {
     Ws& w = sh.w;
@@ -333,11 +342,11 @@ void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
          aa ? w.AA : nullptr, (int64_t)w.ldh * n, w.ldh, w.sing, active);
     potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, active);
     if (p > 0) {
-        dim3 gt(std::max(1, std::min(64, (p * n + 255) / 256)), sh.batch);
-        LAUNCH(sh, k_transpose_A, gt, 256, 0, w.A, w.sA, p, n, w.HiAt, active);
+        dim3 gt = batch_grid(std::max(1, std::min(64, (p * n + 255) / 256)), sh.batch);
+        LAUNCH(sh, k_transpose_A, gt, 256, 0, w.A, w.sA, p, n, w.HiAt, active, sh.batch);
         potrs(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.HiAt, (int64_t)n * p, n, p, active);
-        dim3 gm(std::max(1, std::min(64, (p * p + 255) / 256)), sh.batch);
-        LAUNCH(sh, k_small_gemm, gm, 256, 0, w.A, w.sA, p, n, w.HiAt, w.M, w.ldm, active);
+        dim3 gm = batch_grid(std::max(1, std::min(64, (p * p + 255) / 256)), sh.batch);
+        LAUNCH(sh, k_small_gemm, gm, 256, 0, w.A, w.sA, p, n, w.HiAt, w.M, w.ldm, active, sh.batch);
         potrf(sh, w.M, (int64_t)w.ldm * p, w.ldm, p, w.XM, w.fail, active);
     }
 }
@@ -522,19 +531,17 @@ void prepare_problem(Shard& sh, bool have_sing) {
     ensure_tiled(sh);
     if (p > 0) {
         const int64_t sA = w.sA;
-        dim3 g(std::max(1, std::min(64, (p * n + 255) / 256)), sh.sharedA ? 1 : B);
-        LAUNCH(sh, k_pad_copy, g, 256, 0, w.A, sA, p, n, w.Ap, w.ldap);
+        dim3 g = batch_grid(std::max(1, std::min(64, (p * n + 255) / 256)), sh.sharedA ? 1 : B);
+        LAUNCH(sh, k_pad_copy, g, 256, 0, w.A, sA, p, n, w.Ap, w.ldap, sh.sharedA ? 1 : B);
         // shared A: every problem reads slice 0 of Ap
         syrk(sh, true, w.Ap, sh.sharedA ? 0 : (int64_t)w.ldap * n, w.ldap, n, w.ppad, w.AA, (int64_t)w.ldh * n, w.ldh,
              1.0, 0.0, nullptr, 0, 0, nullptr, nullptr);
     }
     if (!have_sing) {
         LAUNCH(sh, k_reset, (B + 255) / 256, 256, 0, w, B);
-        dim3 g2(n, B);
-        (void)g2;
         const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
-        dim3 g((n + cols_per_cta - 1) / cols_per_cta, B);
-        LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 1, cols_per_cta, (const int*)nullptr);
+        dim3 g = batch_grid((n + cols_per_cta - 1) / cols_per_cta, B);
+        LAUNCH(sh, k_build_gt, g, 256, 0, w.L, w.G, w.sG, w.wb, w.iwb, w.eta, w.Gt, w.ldgt, 1, cols_per_cta, (const int*)nullptr, B);
         syrk(sh, true, w.Gt, (int64_t)w.ldgt * n, w.ldgt, n, w.kpad, w.H, (int64_t)w.ldh * n, w.ldh, 1.0, 0.0, nullptr, 0,
              0, nullptr, nullptr);
         potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, nullptr);
@@ -583,12 +590,18 @@ void for_each_shard(socp_handle* h, F f) {
                 errs[i] = e;
             } catch (const UsageErr& e) {
                 errs[i] = CudaErr{e.code, e.msg};
+            } catch (const std::exception& e) {
+                errs[i] = CudaErr{SOCP_ERR_NOMEM, e.what()};
+            } catch (...) {
+                errs[i] = CudaErr{SOCP_ERR_NOMEM, "unknown exception in a shard worker"};
             }
         });
     }
     for (auto& t : th) t.join();
-    for (auto& e : errs)
-        if (e.code != 0) throw e;
+    for (auto& e : errs) {
+        if (e.code > 0) throw e;
+        if (e.code < 0) throw UsageErr{e.code, e.msg};
+    }
 }
 
 void h2d(Shard& sh, void* dst, const void* src, size_t bytes) {
@@ -827,21 +840,24 @@ void upload_csc(Shard& sh, const socp_csc& m, const std::vector<int>& lin, bool 
     const int64_t nb = shared ? 1 : sh.batch;
     CK(cudaMemsetAsync(dense, 0, sizeof(double) * nb * rows * cols, sh.stream));
     if (m.nnz == 0) return;
-    int* d_lin = nullptr;
-    double* d_val = nullptr;
-    CK(cudaMalloc(&d_lin, sizeof(int) * m.nnz));
-    if (cudaMalloc(&d_val, sizeof(double) * nb * m.nnz) != cudaSuccess) {
-        cudaFree(d_lin);
+    struct Staging {       // freed on every exit path (a CK throw included)
+        int* lin = nullptr;
+        double* val = nullptr;
+        ~Staging() { if (lin) cudaFree(lin); if (val) cudaFree(val); }
+    } st;
+    CK(cudaMalloc(&st.lin, sizeof(int) * m.nnz));
+    if (cudaMalloc(&st.val, sizeof(double) * nb * m.nnz) != cudaSuccess) {
+        cudaGetLastError();
         throw UsageErr{SOCP_ERR_NOMEM, "csc: out of device memory for the value staging buffer"};
     }
+    int* d_lin = st.lin;
+    double* d_val = st.val;
     h2d(sh, d_lin, lin.data(), sizeof(int) * m.nnz);
     h2d(sh, d_val, m.nzval + (shared ? 0 : sh.first * m.nnz), sizeof(double) * nb * m.nnz);
     const int64_t total = nb * m.nnz;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
     LAUNCH(sh, k_csc_scatter, grid, 256, 0, d_lin, d_val, m.nnz, (int)m.nnz, dense, (int64_t)rows * cols, total);
     CK(cudaStreamSynchronize(sh.stream));
-    CK(cudaFree(d_lin));
-    CK(cudaFree(d_val));
 }
 
 }  // namespace
@@ -915,6 +931,16 @@ int socp_b200_create(socp_handle** out, const socp_layout* L, int64_t batch, con
         int cur = 0;
         if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
         devs.push_back(cur);
+    }
+    {
+        int ndevices = 0;
+        if (cudaGetDeviceCount(&ndevices) != cudaSuccess) { cudaGetLastError(); ndevices = 0; }
+        for (int d : devs)
+            if (d < 0 || d >= ndevices || d >= 64) {
+                g_create_err = "device id out of range (0 <= id < cudaGetDeviceCount(), at most 64 devices)";
+                delete h;
+                return ndevices == 0 ? (int)cudaErrorNoDevice : SOCP_ERR_LAYOUT;
+            }
     }
     if ((int64_t)devs.size() > batch) devs.resize((size_t)batch);
     const int64_t per = (batch + (int64_t)devs.size() - 1) / (int64_t)devs.size();

@@ -120,8 +120,9 @@ __global__ void k_compute_step(ConeLayout L, const double* lam, const double* ds
 __global__ void __launch_bounds__(256)
 k_build_gt(ConeLayout L, const double* __restrict__ G, int64_t sG, const double* __restrict__ wb,
            const double* __restrict__ iwb, const double* __restrict__ eta, double* __restrict__ Gt, int ldgt,
-           int identity, int cols_per_cta, const int* __restrict__ active) {
-    const int b = blockIdx.y;
+           int identity, int cols_per_cta, const int* __restrict__ active, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double* Gb = G + (int64_t)b * sG;
@@ -148,8 +149,9 @@ k_build_gt(ConeLayout L, const double* __restrict__ G, int64_t sG, const double*
 }
 
 // padded copy of A (p x n, ld p) into Ap (ld ldap), pad rows left zero
-__global__ void k_pad_copy(const double* __restrict__ A, int64_t sA, int rows, int cols, double* __restrict__ Ap, int ldap) {
-    const int b = blockIdx.y;
+__global__ void k_pad_copy(const double* __restrict__ A, int64_t sA, int rows, int cols, double* __restrict__ Ap, int ldap, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     const double* Ab = A + (int64_t)b * sA;
     double* Apb = Ap + (int64_t)b * ldap * cols;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < rows * cols; q += gridDim.x * blockDim.x) {
@@ -159,8 +161,9 @@ __global__ void k_pad_copy(const double* __restrict__ A, int64_t sA, int rows, i
 }
 // HiAt[:, i] = A[i, :]   (n x p, ld n)
 __global__ void k_transpose_A(const double* __restrict__ A, int64_t sA, int p, int n, double* __restrict__ out,
-                              const int* __restrict__ active) {
-    const int b = blockIdx.y;
+                              const int* __restrict__ active, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     const double* Ab = A + (int64_t)b * sA;
     double* ob = out + (int64_t)b * n * p;
@@ -171,8 +174,9 @@ __global__ void k_transpose_A(const double* __restrict__ A, int64_t sA, int p, i
 }
 // M (p x p, ld ldm) = A (p x n) * HiAt (n x p); one thread per entry (i fastest)
 __global__ void k_small_gemm(const double* __restrict__ A, int64_t sA, int p, int n, const double* __restrict__ B,
-                             double* __restrict__ M, int ldm, const int* __restrict__ active) {
-    const int b = blockIdx.y;
+                             double* __restrict__ M, int ldm, const int* __restrict__ active, int nbatch) {
+    const int b = batch_index();
+    if (b >= nbatch) return;
     if (active && !active[b]) return;
     const double* Ab = A + (int64_t)b * sA;
     const double* Bb = B + (int64_t)b * n * p;

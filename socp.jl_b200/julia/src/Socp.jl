@@ -107,14 +107,17 @@ end
 mutable struct B200Scaling <: AbstractScaling      # fields as struct Scaling, src/scalings.jl:1-20
     l::Matrix{Float64}; wbs::Matrix{Float64}; mu::Matrix{Float64}; fail::Vector{Int32}
 end
+# The solver object only names the back end and the devices to shard over (DenseSolver's role in the plug-in seam,
+# src/densesolver.jl:1-39); the device handle is owned by the SolverState built from it, so one B200Solver can seed
+# several SolverStates without their finalizers sharing (and leaking) a handle.
 mutable struct B200Solver <: KKTSolver{B200Scaling}
-    handle::Ptr{Cvoid}
     devices::Vector{Int32}
-    B200Solver(prob = nothing; devices = Int32[]) = new(C_NULL, Vector{Int32}(devices))
+    B200Solver(prob = nothing; devices = Int32[]) = new(Vector{Int32}(devices))
 end
 
 mutable struct SolverState{S<:KKTSolver}
     solver::S
+    handle::Ptr{Cvoid}
     scaling::B200Scaling
     n::Int; m::Int; k::Int; B::Int; ncones::Int
     function SolverState(pr::BatchProblem, solver::B200Solver)
@@ -130,23 +133,22 @@ mutable struct SolverState{S<:KKTSolver}
                   h, lay, pr.B, devs, length(solver.devices))
         end
         rc == 0 || throw(SocpError(rc, unsafe_string(ccall((:socp_b200_last_error, libsocp), Cstring, (Ptr{Cvoid},), C_NULL))))
-        solver.handle = h[]
         sc = B200Scaling(zeros(pr.k, pr.B), zeros(pr.k, pr.B), zeros(length(pr.cones), pr.B), zeros(Int32, pr.B))
-        ss = new{B200Solver}(solver, sc, pr.n, pr.m, pr.k, pr.B, length(pr.cones))
-        finalizer(s -> (s.solver.handle != C_NULL && ccall((:socp_b200_destroy, libsocp), Cint, (Ptr{Cvoid},), s.solver.handle);
-                        s.solver.handle = C_NULL), ss)
+        ss = new{B200Solver}(solver, h[], sc, pr.n, pr.m, pr.k, pr.B, length(pr.cones))
+        finalizer(s -> (s.handle != C_NULL && ccall((:socp_b200_destroy, libsocp), Cint, (Ptr{Cvoid},), s.handle);
+                        s.handle = C_NULL), ss)
         return ss
     end
 end
 
 check(ss, rc, what) = rc == 0 || throw(SocpError(rc, what * ": " *
-    unsafe_string(ccall((:socp_b200_last_error, libsocp), Cstring, (Ptr{Cvoid},), ss.solver.handle))))
+    unsafe_string(ccall((:socp_b200_last_error, libsocp), Cstring, (Ptr{Cvoid},), ss.handle))))
 
 function load!(ss::SolverState, pr::BatchProblem)
     flags = Int32((ndims(pr.A) == 2 && pr.m > 0 ? 1 : 0) | (ndims(pr.G) == 2 ? 2 : 0))
     rc = GC.@preserve pr ccall((:socp_b200_set_data, libsocp), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Int32),
-        ss.solver.handle, pr.c, pr.m > 0 ? pointer(pr.A) : C_NULL, pr.m > 0 ? pointer(pr.b) : C_NULL,
+        ss.handle, pr.c, pr.m > 0 ? pointer(pr.A) : C_NULL, pr.m > 0 ? pointer(pr.b) : C_NULL,
         pr.G, pr.h, C_NULL, flags)
     check(ss, rc, "socp_b200_set_data")
 end
@@ -173,7 +175,7 @@ function load!(ss::SolverState, c::Matrix{Float64}, A::Union{Nothing,SparseMatri
                                  pointer(Avals === nothing ? A.nzval : Avals), 1)) : Ref(CCsc(0, C_NULL, C_NULL, C_NULL, 1))
         ccall((:socp_b200_set_data_csc, libsocp), Cint,
               (Ptr{Cvoid}, Ptr{Float64}, Ptr{CCsc}, Ptr{Float64}, Ptr{CCsc}, Ptr{Float64}, Ptr{UInt8}, Int32),
-              ss.solver.handle, c, ss.m > 0 ? as : C_NULL,
+              ss.handle, c, ss.m > 0 ? as : C_NULL,
               ss.m > 0 ? pointer(b) : Ptr{Float64}(C_NULL), gs, h,
               sing === nothing ? Ptr{UInt8}(C_NULL) : pointer(sing), flags)
     end
@@ -185,10 +187,12 @@ end
 
 solve_socp (src/solver.jl:40-152) for every problem of the batch on the GPU, as ONE library call from host data
 to host results (`socp_b200_solve_host`: upload, solve and download of chunks overlap).  `sing` is the reference's
-5th type parameter per problem (src/Socp.jl:49-56); pass `nothing` to have it computed on the device.
+5th type parameter per problem (src/Socp.jl:49-56: `cholesky(G'G)` fails).  The default `nothing` has the library
+run that test on the device, as the reference's constructor does on the host; pass `zeros(UInt8, B)` only when every
+`G` is known to have full column rank (skips the test).
 """
 function solve_socp_batch(pr::BatchProblem, ss::SolverState; params = default_params(),
-                          sing::Union{Nothing,Vector{UInt8}} = zeros(UInt8, pr.B))
+                          sing::Union{Nothing,Vector{UInt8}} = nothing)
     x = zeros(pr.n, pr.B); y = zeros(pr.m, pr.B); z = zeros(pr.k, pr.B); s = zeros(pr.k, pr.B)
     status = zeros(Int32, pr.B); iters = zeros(Int32, pr.B); pobj = zeros(pr.B); dobj = zeros(pr.B)
     flags = Int32((ndims(pr.A) == 2 && pr.m > 0 ? 1 : 0) | (ndims(pr.G) == 2 ? 2 : 0))
@@ -196,7 +200,7 @@ function solve_socp_batch(pr::BatchProblem, ss::SolverState; params = default_pa
         (Ptr{Cvoid}, Ref{CParams}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{UInt8}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
-        ss.solver.handle, params, pr.c, pr.m > 0 ? pointer(pr.A) : C_NULL, pr.m > 0 ? pointer(pr.b) : C_NULL,
+        ss.handle, params, pr.c, pr.m > 0 ? pointer(pr.A) : C_NULL, pr.m > 0 ? pointer(pr.b) : C_NULL,
         pr.G, pr.h, sing === nothing ? Ptr{UInt8}(C_NULL) : pointer(sing), flags,
         x, pr.m > 0 ? pointer(y) : C_NULL, z, s, status, iters, pobj, dobj)
     check(ss, rc, "socp_b200_solve_host")
@@ -216,14 +220,14 @@ function compute_scaling(ss::SolverState, s::Matrix{Float64}, z::Matrix{Float64}
     sc = ss.scaling
     rc = ccall((:socp_b200_compute_scaling, libsocp), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
-        ss.solver.handle, s, z, sc.l, sc.wbs, sc.mu, sc.fail)
+        ss.handle, s, z, sc.l, sc.wbs, sc.mu, sc.fail)
     check(ss, rc, "socp_b200_compute_scaling")
     return sc
 end
 "setup_iter(solver, prob, state, scaling) -- reference src/densesolver.jl:41-52."
 function setup_iter(ss::SolverState)
     fail = zeros(Int32, ss.B)
-    check(ss, ccall((:socp_b200_setup_iter, libsocp), Cint, (Ptr{Cvoid}, Ptr{Int32}), ss.solver.handle, fail), "socp_b200_setup_iter")
+    check(ss, ccall((:socp_b200_setup_iter, libsocp), Cint, (Ptr{Cvoid}, Ptr{Int32}), ss.handle, fail), "socp_b200_setup_iter")
     return fail
 end
 "solve_kkt(solver, prob, state, scaling, dx,dy,dz,ds, cx,cy,cz,cs) -- reference src/densesolver.jl:54-90."
@@ -231,42 +235,42 @@ function solve_kkt(ss::SolverState, dx, dy, dz, ds, cx, cy, cz, cs)
     pn(a) = isempty(a) ? Ptr{Float64}(C_NULL) : pointer(a)
     rc = GC.@preserve dx dy dz ds cx cy cz cs ccall((:socp_b200_solve_kkt, libsocp), Cint,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-        ss.solver.handle, pn(dx), pn(dy), pn(dz), pn(ds), pn(cx), pn(cy), pn(cz), pn(cs))
+        ss.handle, pn(dx), pn(dy), pn(dz), pn(ds), pn(cx), pn(cy), pn(cz), pn(cs))
     check(ss, rc, "socp_b200_solve_kkt")
 end
 for (jl, cfn) in ((:scale!, :socp_b200_scale), (:iscale!, :socp_b200_iscale))   # src/scalings.jl:159-173
     @eval function $jl(ss::SolverState, inp::Matrix{Float64}, out::Matrix{Float64})
         check(ss, ccall(($(QuoteNode(cfn)), libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-                        ss.solver.handle, inp, out), $(string(cfn)))
+                        ss.handle, inp, out), $(string(cfn)))
         return out
     end
 end
 function vprod(ss::SolverState, u::Matrix{Float64}, v::Matrix{Float64})          # src/vectors.jl:58-81
     out = similar(u)
     check(ss, ccall((:socp_b200_vprod, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                    ss.solver.handle, u, v, out), "socp_b200_vprod")
+                    ss.handle, u, v, out), "socp_b200_vprod")
     out
 end
 function iprod(ss::SolverState, lam::Matrix{Float64}, v::Matrix{Float64})        # src/vectors.jl:99-131
     out = similar(v)
     check(ss, ccall((:socp_b200_iprod, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                    ss.solver.handle, lam, v, out), "socp_b200_iprod")
+                    ss.handle, lam, v, out), "socp_b200_iprod")
     out
 end
 function make_e(ss::SolverState)                                                  # src/vectors.jl:7-24
     out = zeros(ss.k, ss.B)
-    check(ss, ccall((:socp_b200_make_e, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}), ss.solver.handle, out), "socp_b200_make_e")
+    check(ss, ccall((:socp_b200_make_e, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}), ss.handle, out), "socp_b200_make_e")
     out
 end
 function max_step(ss::SolverState, x::Matrix{Float64})                            # src/mats.jl:1-28
     out = zeros(ss.B)
-    check(ss, ccall((:socp_b200_max_step, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ss.solver.handle, x, out), "socp_b200_max_step")
+    check(ss, ccall((:socp_b200_max_step, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ss.handle, x, out), "socp_b200_max_step")
     out
 end
 function compute_step(ss::SolverState, l::Matrix{Float64}, ds::Matrix{Float64}, dz::Matrix{Float64})   # src/mats.jl:30-40
     out = zeros(ss.B)
     check(ss, ccall((:socp_b200_compute_step, libsocp), Cint,
-                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ss.solver.handle, l, ds, dz, out), "socp_b200_compute_step")
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), ss.handle, l, ds, dz, out), "socp_b200_compute_step")
     out
 end
 

@@ -286,9 +286,12 @@ def test_shared_G_batch():
                              sing=np.zeros(B, np.uint8))
     full = sb.BatchProblem(c, np.zeros((B, 0, base.n)), np.zeros((B, 0)), np.repeat(base.G_dense(0)[None], B, 0), h,
                            base.cones, sing=np.zeros(B, np.uint8))
-    ra = sb.solve_socp_batch(shared, sb.SolverState(shared), sb.default_params(path=sb.PATH_TILED))
-    rb = sb.solve_socp_batch(full, sb.SolverState(full), sb.default_params(path=sb.PATH_TILED))
-    assert np.array_equal(ra.status, rb.status) and np.array_equal(ra.x, rb.x)
+    for path in (sb.PATH_TILED, sb.PATH_AUTO):
+        ra = sb.solve_socp_batch(shared, sb.SolverState(shared), sb.default_params(path=path))
+        rb = sb.solve_socp_batch(full, sb.SolverState(full), sb.default_params(path=path))
+        assert ra.timings["path_used"] == (sb.PATH_TILED if path == sb.PATH_TILED else sb.PATH_FUSED)
+        assert (ra.status == sb.STATUS_CONVERGED).all()
+        assert np.array_equal(ra.status, rb.status) and np.array_equal(ra.x, rb.x) and np.array_equal(ra.s, rb.s)
 
 
 def _csc_of(prob):
@@ -352,11 +355,15 @@ def test_csc_shared_pattern_and_values():
     dense = sb.BatchProblem(c, *none, Gd, h, base.cones)
     sparse = sb.BatchProblem(c, *none, sb.CscMatrix.from_scipy(sp.csc_matrix(Gd)), h, base.cones)
     assert sparse.shared_G and sparse.G_csc.nnz < base.k * base.n // 2
-    ssd, sss = sb.SolverState(dense), sb.SolverState(sparse)
-    rd = sb.solve_socp_batch(dense, ssd, sb.default_params(path=sb.PATH_TILED))
-    rs = sb.solve_socp_batch(sparse, sss, sb.default_params(path=sb.PATH_TILED))
-    assert np.array_equal(ssd.get_sing(), sss.get_sing())
-    assert np.array_equal(rd.status, rs.status) and np.array_equal(rd.x, rs.x) and np.array_equal(rd.iters, rs.iters)
+    for path in (sb.PATH_TILED, sb.PATH_AUTO):
+        ssd, sss = sb.SolverState(dense), sb.SolverState(sparse)
+        rd = sb.solve_socp_batch(dense, ssd, sb.default_params(path=path))
+        rs = sb.solve_socp_batch(sparse, sss, sb.default_params(path=path))
+        assert rs.timings["path_used"] == (sb.PATH_TILED if path == sb.PATH_TILED else sb.PATH_FUSED)
+        assert np.array_equal(ssd.get_sing(), sss.get_sing())
+        assert (rs.status == sb.STATUS_CONVERGED).all()
+        assert np.array_equal(rd.status, rs.status) and np.array_equal(rd.iters, rs.iters)
+        assert np.max(np.abs(rd.x - rs.x)) <= 1e-9 * max(1.0, np.max(np.abs(rd.x)))
 
 
 def test_csc_rejects_broken_patterns():
@@ -415,6 +422,48 @@ def test_multi_device_handle_matches_single_device():
     a = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[1]))
     b = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[0, 1]))
     assert np.array_equal(a.status, b.status) and np.array_equal(a.x, b.x)
+
+
+def test_multi_shard_handle_on_one_device():
+    """The same sharding code path (for_each_shard: one host worker + stream per shard, results gathered by shard
+    offset) on a box with ONE GPU: devices=[0, 0, 0] makes three shards of the batch on device 0.  Must equal the
+    single-shard results bit for bit."""
+    prob = gen.make_config("C2", batch=301)           # odd split: 101 + 101 + 99
+    one = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0]))
+    three = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0, 0, 0]))
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+        assert np.array_equal(getattr(one, f), getattr(three, f)), f
+    # tiled path + the device-side `sing` test (sing=None) through the shards as well
+    p3 = gen.random_feasible(50, 20, 2, (sb.POC(0, 6), sb.SOC(6, 20)), 0.1, sing_known=False)
+    a = sb.solve_socp_batch(p3, sb.SolverState(p3, devices=[0]), sb.default_params(path=sb.PATH_TILED))
+    b = sb.solve_socp_batch(p3, sb.SolverState(p3, devices=[0, 0]), sb.default_params(path=sb.PATH_TILED))
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.x, b.x)
+
+
+def test_tiled_path_more_than_65535_problems():
+    """gridDim.y is capped at 65535: the batch-wide tiled kernels fold the batch over grid y and z.  70 000 tiny
+    problems through the tiled path with `sing` computed on the device must equal the fused path's outcomes."""
+    B = 70_000
+    base = gen.random_feasible(512, 4, 1, (sb.POC(0, 2), sb.SOC(2, 3)), 0.1, sing_known=False)
+    rep = (B + 511) // 512
+    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * rep, axis=0)[:B])
+    prob = sb.BatchProblem(tile(base.c), tile(base.A_cm), tile(base.b), tile(base.G_cm), tile(base.h), base.cones,
+                           sing=None, colmajor=True)
+    ss = sb.SolverState(prob)
+    ss.load(prob)
+    assert not ss.get_sing().any()
+    til = sb.solve_socp_batch(prob, ss, sb.default_params(path=sb.PATH_TILED), reload=False)
+    fus = sb.solve_socp_batch(prob, ss, sb.default_params(path=sb.PATH_FUSED), reload=False)
+    assert til.timings["path_used"] == sb.PATH_TILED and fus.timings["path_used"] == sb.PATH_FUSED
+    # the batch is 512 distinct problems repeated: every repetition must give the same answer as the first
+    for r in (til, fus):
+        assert np.array_equal(r.status.reshape(-1)[:(B // 512) * 512].reshape(-1, 512), np.broadcast_to(r.status[:512], (B // 512, 512)))
+        assert np.array_equal(r.pobj[:(B // 512) * 512].reshape(-1, 512), np.broadcast_to(r.pobj[:512], (B // 512, 512)))
+    conv = fus.status == sb.STATUS_CONVERGED
+    assert conv.mean() > 0.5
+    assert np.all(til.status[conv] == sb.STATUS_CONVERGED)
+    same = conv & (til.iters == fus.iters)
+    assert np.max(np.abs(til.pobj[same] - fus.pobj[same]) / np.maximum(1.0, np.abs(fus.pobj[same]))) <= 1e-5
 
 
 GENERIC_LAYOUTS = {
