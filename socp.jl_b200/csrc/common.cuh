@@ -1,6 +1,11 @@
 // common.cuh -- shared definitions for the socp_b200 CUDA sources (sm_100a).
 #pragma once
+#ifdef SOCP_SIMT_EMU
+// host build of the kernels for CPU-side tests (tests/simt_emu/, test infrastructure -- never part of libsocp_b200)
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <math.h>
 
@@ -49,6 +54,9 @@ struct ProbScalars {
 // inside the parity tolerances (1e-10 per step).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double a) {
+#ifdef SOCP_SIMT_EMU
+    return 1.0 / a;
+#endif
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
     double e = fma(-a, x, 1.0);
@@ -58,6 +66,9 @@ __device__ __forceinline__ double fast_rcp(double a) {
     return x;
 }
 __device__ __forceinline__ double fast_rsqrt(double a) {
+#ifdef SOCP_SIMT_EMU
+    return 1.0 / sqrt(a);
+#endif
     double x;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
     const double h = 0.5 * a;
@@ -79,6 +90,42 @@ __device__ __forceinline__ double fast_sqrt(double a) {
 // Batch index of a CTA of the batch-wide tiled kernels: grids are (tiles, by, bz) with the batch folded over y and z
 // (gridDim.y is capped at 65535); the kernel guards b < nbatch.  Host side: batch_grid() in solver.cu.
 __device__ __forceinline__ int batch_index() { return (int)(blockIdx.z * gridDim.y + blockIdx.y); }
+
+// compute_step, reference src/mats.jl:30-40: t = max(scmax(lam, ds), scmax(lam, dz), 0); step = t == 0 ? 1 : min(1, 1/t)
+__device__ __forceinline__ double step_from_t(double t) {
+    t = fmax(t, 0.0);
+    return (t == 0.0) ? 1.0 : fmin(1.0, fast_rcp(t));
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe (SASS DMMA.8x8x4).  Lane l holds A[l>>2][l&3],
+// B[l&3][l>>2] and C[l>>2][2(l&3) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+#ifdef SOCP_SIMT_EMU
+    simt_emu::dmma884(c0, c1, a, b);
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+#endif
+}
+// named barrier `ID` (1..15) over NT threads: arrive-only for a warp that need not wait (it must not touch what the
+// waiting warps go on to write before it has synchronised with them again)
+template <int ID, int NT>
+__device__ __forceinline__ void named_bar_sync() {
+#ifdef SOCP_SIMT_EMU
+    emu_bar_sync(ID, NT);
+#else
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NT) : "memory");
+#endif
+}
+template <int ID, int NT>
+__device__ __forceinline__ void named_bar_arrive() {
+#ifdef SOCP_SIMT_EMU
+    emu_bar_arrive(ID, NT);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NT) : "memory");
+#endif
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

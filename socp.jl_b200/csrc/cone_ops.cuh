@@ -261,10 +261,7 @@ __device__ __forceinline__ double cta_scmax_partial(const ConeLayout& L, const d
     return mx;
 }
 // compute_step(cones, l, ds, dz), reference src/mats.jl:30-40
-__device__ __forceinline__ double step_from_t(double t) {
-    t = fmax(t, 0.0);
-    return (t == 0.0) ? 1.0 : fmin(1.0, fast_rcp(t));
-}
+// step_from_t lives in common.cuh
 // make_e!, reference src/vectors.jl:7-24: value of e at index i of a block
 __device__ __forceinline__ double e_value(int kind, int i) { return (kind == KIND_POC || i == 0) ? 1.0 : 0.0; }
 

@@ -22,12 +22,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core.
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
+// dmma884 (mma.sync m8n8k4 f64) lives in common.cuh
 
 // ---------------------------------------------------------------------------
 // gemv, transposed:  out[c] = sum_r M[r,c] x[r]  (+ c1*v1[c] + c2*v2[c] [+ out[c]])
