@@ -46,6 +46,12 @@ struct ProbScalars {
     double dobj;
 };
 
+// solver constants of one solve (defaults: reference src/solver.jl:105,122,146,91)
+struct LoopParams {
+    int max_iter;
+    double tol, step_damp, init_eps;
+};
+
 // ---------------------------------------------------------------------------
 // Fast FP64 reciprocal / rsqrt / sqrt: MUFU seed (rcp.approx / rsqrt.approx, ~20
 // bits) + two Newton steps, accurate to ~1-2 ulp.  The IEEE div/sqrt sequences

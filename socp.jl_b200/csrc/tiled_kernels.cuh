@@ -39,11 +39,6 @@ struct Ws {
     int* nactive;          // [max_iter+2] counters
 };
 
-struct LoopParams {
-    int max_iter;
-    double tol, step_damp, init_eps;
-};
-
 #define SOCP_VEC(ptr, len) ((ptr) + (int64_t)b * (len))
 
 // ------------------------------------------------------------ step-level kernels
