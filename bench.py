@@ -50,6 +50,16 @@ def workload_meta(name):
     return n, p, k, cfg["batch"], desc
 
 
+def config_dict(name, problems_per_gpu):
+    """The `config` object of the JSON line: identical in both arms (`--impl b200` and `--impl reference`) for the same
+    command line; everything measured goes under `detail`."""
+    n, p, k, batch, desc = workload_meta(name)
+    bytes_step = problems_per_gpu * (8.0 * (k * n + p * n + n + p + k) + 8.0 * (n + p + 2 * k) + 24.0)
+    return {"workload": desc, "problems_per_step_per_gpu": int(problems_per_gpu),
+            "l2": (f"inputs {bytes_step / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)" if bytes_step > 130e6
+                   else "inputs fit in L2; the device-resident leg re-reads them from L2/HBM every step (no flush)")}
+
+
 def flops_per_iteration(n, p, k):
     """factor n(n+1)k + n^3/3 (+p terms), solve 2n^2 + 4nk, residuals 4nk + 4pn."""
     ff = n * (n + 1) * k + n ** 3 / 3.0 + (p * n * n + p * p * n + p ** 3 / 3.0 if p else 0.0)
@@ -107,25 +117,35 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measure_fp64_peak(torch, dev):
-    """FP64 GEMM peak of this GPU, measured in-run (cuBLAS DGEMM through torch.matmul):
-    MEASURED_PEAKS.json has no FP64 figure.  Burst = best of 10."""
-    n = 4096
+def measure_fp64_peak(torch, dev, sustained_s=4.0):
+    """FP64 GEMM peak of this GPU, measured in-run (cuBLAS DGEMM through torch.matmul; MEASURED_PEAKS.json has no FP64
+    figure): burst = best of 10 at 8192^3, sustained = back to back for `sustained_s` seconds."""
+    n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device=dev)
     b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    c = torch.empty(n, n, dtype=torch.float64, device=dev)
     for _ in range(2):
-        torch.matmul(a, b)
+        torch.matmul(a, b, out=c)
     torch.cuda.synchronize(dev)
     best = 1e30
     for _ in range(10):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        torch.matmul(a, b)
+        torch.matmul(a, b, out=c)
         e1.record()
         torch.cuda.synchronize(dev)
         best = min(best, e0.elapsed_time(e1))
-    del a, b
-    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    burst = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    reps = max(4, int(sustained_s / (best * 1e-3)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sustained = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b, c
+    return burst, sustained
 
 
 def cpu_baseline_run(name, nproblems, nthreads):
@@ -165,7 +185,8 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sample": f"{sample} problems per step (bounded sample of the workload)"},
+        "config": config_dict(args.config, args.batch or batch),
+        "detail": {"sample": f"{sample} problems per step (bounded sample of the workload)", "converged": conv},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} problems/step x {args.steps} steps, C oracle (oracle/socp_oracle.c) "
                                    f"= C restatement of Socp.jl's dense path; Julia is not installed so the reference "
@@ -274,7 +295,7 @@ def main():
     h2d_bytes = sum(t.numel() * t.element_size() for t in (hc, hh, hG, hA, hb, hsing) if t is not None)
     d2h_bytes = sum(t.numel() * t.element_size() for t in (ox, ostatus, oiters, opobj, odobj))
 
-    fp64_peak = measure_fp64_peak(torch, dev)
+    fp64_peak, fp64_sustained = measure_fp64_peak(torch, dev)
     hbm_peak, hbm_src = measured_peaks()
 
     # ---- device-resident leg (`value`)
@@ -329,16 +350,20 @@ def main():
         # kernels on the tiled path): algorithmic FP64 flops = F_it x iterations actually taken
         f_it = flops_per_iteration(n, p, k)
         # +1: the initial point costs one factor + one solve (counted as one iteration's factor+solve share)
-        flops_step = f_it * (float(iters.sum()) + B * 1.0)
-        achieved = flops_step * args.steps / (dev_ms * 1e-3) / 1e12
+        flops_step = f_it * (total_iters + total_B) / world          # per GPU
+        achieved = flops_step * args.steps / t_dev / 1e12             # t_dev: max over ranks
         bytes_step = B * (8.0 * (k * n + p * n + n + p + k) + 8.0 * (n + p + 2 * k) + 24.0)
-        hbm_ach = bytes_step * args.steps / (dev_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        hbm_ach = bytes_step * args.steps / t_dev / 1e9
+        # DRAM traffic of the dominant kernel from the latest `ncu --set full` capture (tools/gpu_profiles.sh writes
+        # profiles/ncu_traffic.json with the kernel name and the git SHA it was taken at); null when it is not for
+        # this workload / batch / path
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath)).get(args.config)
             if t and t.get("problems_per_launch") == B and path_used == 2:
                 traffic = t["dram_bytes"]
+                traffic_src = f"{t.get('kernel', '?')} @ {t.get('git_sha', '?')}"
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -351,10 +376,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "problems_per_gpu": B, "path": {1: "tiled", 2: "fused"}.get(path_used, "?"),
-                       "l2": f"inputs {bytes_step / 1e6:.0f} MB per step exceed the 126 MB L2 (no flush needed)"
-                             if bytes_step > 130e6 else "inputs fit in L2; steps re-upload nothing (device-resident leg)",
-                       "converged": int(total_conv), "mean_iters": total_iters / total_B,
+            "config": config_dict(args.config, B),
+            "detail": {"path": {1: "tiled", 2: "fused"}.get(path_used, "?"), "converged": int(total_conv),
+                       "mean_iters": total_iters / total_B,
                        # BASELINE.json's secondary metric: one "KKT factor+solve" = one setup_iter + one solve_kkt; a
                        # solve does (iterations + 1) of them per problem (the initial point is one).  Amortised over the
                        # whole job (throughput), not the latency of one problem.
@@ -366,9 +390,12 @@ def main():
                            "streams) -> pinned host results; wall clock between barriers, max over ranks"},
             "gpu_launches": int(total_launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": traffic,
-                         "peak_source": "FP64: cuBLAS DGEMM 4096^3 through torch.matmul, best of 10, measured in this run "
-                                        "(MEASURED_PEAKS.json has no FP64 figure)",
+                         "frac": achieved / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": "FP64 burst: cuBLAS DGEMM 8192^3 through torch.matmul, best of 10, measured in this "
+                                        "run (MEASURED_PEAKS.json has no FP64 figure); the kernel is timed alone, so burst",
+                         "peak_sustained": fp64_sustained, "frac_of_sustained": achieved / fp64_sustained,
+                         "flops_note": "algorithmic flops of the dense formulation (SURVEY.md 8d) x iterations taken; "
+                                       "the kernel skips the structural zeros of G (singleton / empty rows)",
                          "flops_per_step": flops_step, "hbm_achieved_gbs": hbm_ach, "hbm_peak_gbs": hbm_peak,
                          "hbm_frac": hbm_ach / hbm_peak, "hbm_peak_source": hbm_src},
             "clocks": sampler.summary(),

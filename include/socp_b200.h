@@ -204,6 +204,16 @@ int  socp_b200_compute_step(socp_handle* h, const double* lambda, const double* 
 int  socp_b200_get_H(socp_handle* h, double* out);
 int  socp_b200_get_L(socp_handle* h, double* out);
 
+/* Parity aid (no reference counterpart as a call; it exposes the inputs and outputs of the reference's
+ * compute_scaling / setup_iter / solve_kkt, src/densesolver.jl:41-90, from inside the fused whole-solve kernel): problem
+ * `index` is solved again on its own and at Mehrotra iteration `iter` (0-based) the kernel writes out s, z [k] (what
+ * the scaling is computed from), H [n*n, column-major] = G'W^-2 G (+A'A if sing) before its factorisation, the
+ * right-hand side dx [n], dy [p], dz [k], ds [k] and the result cx, cy, cz, cs of the affine (phase 1) or combined
+ * (phase 2) solve_kkt.  Null outputs are skipped.  Needs a layout the fused kernel takes (16 < n <= 64). */
+int  socp_b200_debug_fused_step(socp_handle* h, int64_t index, int32_t iter, int32_t phase,
+                                double* s, double* z, double* H, double* dx, double* dy, double* dz, double* ds,
+                                double* cx, double* cy, double* cz, double* cs);
+
 /* Measurement utility (no reference counterpart): mean CUDA-event time, in ms, of
  * the device kernels behind one step-level call over `reps` repetitions on the data
  * resident after _set_data + _compute_scaling.  which: 0 compute_scaling, 1 scale!,

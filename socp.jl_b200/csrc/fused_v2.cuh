@@ -31,8 +31,6 @@
 // Restrictions (the tiled path takes everything else): no `sing` problems, n <= 64, p <= 32,
 // second-order cones of dimension <= 128, at most 64 of them.
 #pragma once
-#include "tiled_kernels.cuh"
-#include "linalg.cuh"
 #include "fused_common.cuh"
 #include <vector>
 #include <algorithm>
@@ -83,8 +81,6 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     else if (n <= 32) { P.variant = 1; P.nw = 4; }
     else if (n <= 56) { P.variant = 2; P.nw = 8; }
     else { P.variant = 3; P.nw = 8; }
-    // experiment switch: a 4-warp team for 32 < n <= 56
-    if (P.variant == 2 && getenv("SOCP_B200_F2_NW4")) { P.variant = 4; P.nw = 4; }
     P.npad = (n + 7) / 8 * 8; P.nb = P.npad / 8;
     P.kpad = (k + 3) / 4 * 4;
     P.ldg = f2_ld(P.kpad);
@@ -122,7 +118,7 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     if (P.smem + 512 > (size_t)dev_smem) return;
     const int per_sm = 228 * 1024;
     const int threads = P.nw * 32;
-    const int reg_cap = P.variant == 0 ? 16 : (P.variant == 1 ? 4 : (P.variant == 4 ? 4 : 2));     // matches the __launch_bounds__ below
+    const int reg_cap = P.variant == 0 ? 16 : (P.variant == 1 ? 4 : 2);     // matches the __launch_bounds__ below
     P.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (P.smem + 1024 + 256)), 2048 / threads, 32, reg_cap}));
     P.fits = true;
 }
@@ -226,7 +222,7 @@ __device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* 
 }
 
 #ifdef SOCP_PHASE_TIMING
-__device__ unsigned long long g_phase_clk2[16];       // tools/phase_timing.py; slots 13 / 15: inside f2_chol_inv (warp 0)
+static __device__ unsigned long long g_phase_clk2[16];       // tools/phase_timing.py; slots 13 / 15: inside f2_chol_inv (warp 0)
 #endif
 
 // ------------------------------------------------------------------------------------------------ blocked Cholesky + inverse
@@ -1006,6 +1002,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                 phase = 1;
             }
             // ---- head of solve_kkt (src/densesolver.jl:61-66 + W^-2) from ds and sc*dz: k0, k2, u
+            __syncwarp();       // ds[head] was written by the cone's head lane, every lane of the group reads it
             for_each_slot([&](const SocLane& L, int slot) { soc_head(L, slot, sc); });
             for (int i = tid; i < kpoc; i += T) {
                 const double w = wb[i], iw = iwb[i];
@@ -1058,7 +1055,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
 // compile-time specialised layouts (BASELINE.json): C2 = portfolio n=50, p=1, POC 50 + SOC 51; C3 = n=12, 10 x SOC 4
 using DimsC2 = DimsStatic<8, 50, 1, 50, 1, 51>;
 using DimsC3 = DimsStatic<1, 12, 0, 0, 10, 4>;
-using DimsC2w4 = DimsStatic<4, 50, 1, 50, 1, 51>;      // experiment: C2 on a 4-warp team
 
 template <int NW, int MAXT, int MINB, class D>
 inline void fused2_launch(const F2Plan& plan, const F2Args& args, int grid, cudaStream_t stream) {
@@ -1079,11 +1075,6 @@ inline void solve_fused2(F2Plan& plan, const Ws& g, int first, int batch, int ma
     args.batch = batch;
     args.counter = plan.d_counter + counter_slot;
     const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
-    if (plan.variant == 4) {
-        if (allow_static && DimsC2w4::matches(plan)) fused2_launch<4, 7, 4, DimsC2w4>(plan, args, grid, stream);
-        else fused2_launch<4, 7, 4, DimsDyn>(plan, args, grid, stream);
-        return;
-    }
     if (allow_static && DimsC2::matches(plan)) { fused2_launch<8, 4, 2, DimsC2>(plan, args, grid, stream); return; }
     if (allow_static && DimsC3::matches(plan)) { fused2_launch<1, 3, 16, DimsC3>(plan, args, grid, stream); return; }
     switch (plan.variant) {
@@ -1093,5 +1084,9 @@ inline void solve_fused2(F2Plan& plan, const Ws& g, int first, int batch, int ma
         default: fused2_launch<8, 5, 2, DimsDyn>(plan, args, grid, stream); break;     // n <= 64: 36 tiles over 8 warps
     }
 }
+
+// non-inline entry of solve_fused2, compiled once in fused2.cu (the kernels are instantiated there only)
+void solve_fused2_ext(F2Plan& plan, const Ws& g, int first, int batch, int max_iter, double tol, double step_damp,
+                      double init_eps, cudaStream_t stream, bool allow_static, int counter_slot);
 
 }  // namespace socp

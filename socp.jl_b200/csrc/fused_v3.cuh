@@ -334,7 +334,7 @@ __device__ __forceinline__ int f3_diag_factor(const double* T, int lane, double 
 }
 
 #ifdef SOCP_PHASE_TIMING
-__device__ unsigned long long g_phase_clk3[16];
+static __device__ unsigned long long g_phase_clk3[16];
 #endif
 
 // In-place blocked Cholesky that carries the inverse along.  Tt: nbl x nbl packed lower tiles (unit pad diagonal).
@@ -1358,6 +1358,9 @@ inline void solve_fused3(const F3Plan& plan, const F3Glob& g, int first, int bat
     else if (plan.nb <= 7) fused3_launch<4, 7, 4, Dims3Dyn>(plan, args, grid, stream);     // n <= 56: 28 tiles
     else fused3_launch<4, 9, 3, Dims3Dyn>(plan, args, grid, stream);                       // n <= 64: 36 tiles
 }
+// non-inline entry of solve_fused3, compiled once in fused3.cu (the kernels are instantiated there only)
+void solve_fused3_ext(const F3Plan& plan, const F3Glob& g, int first, int batch, const LoopParams& prm, int sing_detect,
+                      int verify, cudaStream_t stream, bool allow_static, int counter_slot);
 #endif
 
 }  // namespace socp

@@ -5,6 +5,7 @@
 #include "linalg.cuh"
 #include "tiled_kernels.cuh"
 #include "fused_v2.cuh"
+#include "fused_v3.cuh"
 #include "cone_batch.cuh"
 #include "panel_mma.cuh"
 
@@ -74,6 +75,16 @@ struct Shard {
     int threads = 256;     // CTA size of the per-problem cone kernels
     socp_timings tim{};
     F2Plan fused2{};
+    // second-generation whole-solve kernel (fused_v3.cuh): planned per data set, from the row pattern of G
+    F3Plan fused3{};
+    bool f3_planned = false;     // fused3 belongs to the data now resident
+    bool f3_dense = false;       // ... and was planned with every row dense (fallback after a pattern violation)
+    int* d_f3_tables = nullptr;  // capacity 2k + n + 1 ints
+    int* d_rowcol = nullptr;     // k ints: row pattern found on the device
+    int* d_npattern = nullptr;   // problems reported ST_PATTERN by the verifying kernel
+    int* h_rowcol = nullptr;     // pinned, k + 1 ints
+    bool sing_known = false;     // d_sing holds the flags (given by the caller, tested on the device, or found by the kernel)
+    bool prepared = false;       // tiled-path prerequisites done (sing known, any_sing scanned, A'A when needed)
 
     template <class T>
     T* alloc(size_t count, bool zero = true) {
@@ -89,6 +100,7 @@ struct Shard {
         for (void* p : allocs) cudaFree(p);
         allocs.clear();
         if (h_nactive) cudaFreeHost(h_nactive);
+        if (h_rowcol) cudaFreeHost(h_rowcol);
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         for (auto& e : pipe_ev) cudaEventDestroy(e);
@@ -506,6 +518,10 @@ void build_shard(socp_handle* h, Shard& sh) {
     }
     f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
     sh.fused2.d_counter = sh.alloc<int>(16);
+    sh.d_f3_tables = sh.alloc<int>((size_t)2 * k + n + 2);
+    sh.d_rowcol = sh.alloc<int>(k);
+    sh.d_npattern = sh.alloc<int>(1);
+    CK(cudaMallocHost((void**)&sh.h_rowcol, sizeof(int) * (k + 1)));
     CK(cudaStreamSynchronize(sh.stream));
 }
 
@@ -523,21 +539,15 @@ void ensure_tiled(Shard& sh) {
     w.XM = sh.alloc<double>((size_t)B * ((p + 63) / 64) * 4096 * (p > 0 ? 1 : 0), false);
 }
 
-// AA = A'A (reference src/densesolver.jl:32) and, when the caller gave no
-// `sing`, the test of src/Socp.jl:49-56: cholesky(G'G) fails.
-void prepare_problem(Shard& sh, bool have_sing) {
+// Prerequisites of the tiled path (and of get_sing): `sing` known -- when the caller gave none, the test of
+// src/Socp.jl:49-56, cholesky(G'G) fails -- and AA = A'A (reference src/densesolver.jl:32) when some problem is sing.
+// Lazy: the whole-solve kernel of fused_v3.cuh needs neither (it tests and handles sing problems itself).
+void ensure_prepared(Shard& sh) {
+    if (sh.prepared) return;
     Ws& w = sh.w;
     const int n = w.L.n, p = w.L.p, B = sh.batch;
-    ensure_tiled(sh);
-    if (p > 0) {
-        const int64_t sA = w.sA;
-        dim3 g = batch_grid(std::max(1, std::min(64, (p * n + 255) / 256)), sh.sharedA ? 1 : B);
-        LAUNCH(sh, k_pad_copy, g, 256, 0, w.A, sA, p, n, w.Ap, w.ldap, sh.sharedA ? 1 : B);
-        // shared A: every problem reads slice 0 of Ap
-        syrk(sh, true, w.Ap, sh.sharedA ? 0 : (int64_t)w.ldap * n, w.ldap, n, w.ppad, w.AA, (int64_t)w.ldh * n, w.ldh,
-             1.0, 0.0, nullptr, 0, 0, nullptr, nullptr);
-    }
-    if (!have_sing) {
+    if (!sh.sing_known) {
+        ensure_tiled(sh);
         LAUNCH(sh, k_reset, (B + 255) / 256, 256, 0, w, B);
         const int cols_per_cta = std::max(1, std::min(n, 2048 / std::max(1, w.L.ncones * 8)));
         dim3 g = batch_grid((n + cols_per_cta - 1) / cols_per_cta, B);
@@ -546,12 +556,24 @@ void prepare_problem(Shard& sh, bool have_sing) {
              0, nullptr, nullptr);
         potrf(sh, w.H, (int64_t)w.ldh * n, w.ldh, n, w.XH, w.fail, nullptr);
         LAUNCH(sh, k_fail_to_sing, (B + 255) / 256, 256, 0, w.fail, sh.d_sing, B);
+        sh.sing_known = true;
     }
     std::vector<uint8_t> hs(B);
     CK(cudaMemcpyAsync(hs.data(), sh.d_sing, B, cudaMemcpyDeviceToHost, sh.stream));
     CK(cudaStreamSynchronize(sh.stream));
     sh.any_sing = false;
     for (uint8_t v : hs) sh.any_sing |= (v != 0);
+    if (p > 0 && sh.any_sing) {
+        ensure_tiled(sh);
+        const int64_t sA = w.sA;
+        dim3 g = batch_grid(std::max(1, std::min(64, (p * n + 255) / 256)), sh.sharedA ? 1 : B);
+        LAUNCH(sh, k_pad_copy, g, 256, 0, w.A, sA, p, n, w.Ap, w.ldap, sh.sharedA ? 1 : B);
+        // shared A: every problem reads slice 0 of Ap
+        syrk(sh, true, w.Ap, sh.sharedA ? 0 : (int64_t)w.ldap * n, w.ldap, n, w.ppad, w.AA, (int64_t)w.ldh * n, w.ldh,
+             1.0, 0.0, nullptr, 0, 0, nullptr, nullptr);
+        CK(cudaStreamSynchronize(sh.stream));
+    }
+    sh.prepared = true;
 }
 
 template <class F>
@@ -615,30 +637,143 @@ void need(bool cond, int code, const char* msg) {
     if (!cond) throw UsageErr{code, msg};
 }
 
-int choose_path(const Shard& sh, const socp_params& prm) {
-    if (prm.path == SOCP_PATH_TILED) return SOCP_PATH_TILED;
-    const bool ok = sh.fused2.fits && !sh.any_sing;
-    if (prm.path == SOCP_PATH_FUSED) {
-        need(ok, SOCP_ERR_SIZE, "the fused shared-memory kernel needs a layout that fits and no sing problems");
-        return SOCP_PATH_FUSED;
+// Row pattern of G over problems [first, first + count) of the shard (-1 empty, j single column, -2 dense) ->
+// sh.h_rowcol (pinned).  One pass over G; per-CTA state in shared memory, merged into global memory at the end.
+__global__ void __launch_bounds__(256)
+k_row_pattern(const double* __restrict__ G, int64_t sG, int nbatch, int n, int k, int* __restrict__ rowcol) {
+    extern __shared__ int s_col[];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) s_col[i] = -1;
+    __syncthreads();
+    const int64_t per = (int64_t)n * k;
+    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+        const double* Gb = G + (int64_t)b * sG;
+        for (int64_t e = threadIdx.x; e < per; e += blockDim.x) {
+            if (Gb[e] != 0.0) {
+                const int j = (int)(e / k), i = (int)(e - (int64_t)j * k);
+                const int old = atomicCAS(&s_col[i], -1, j);
+                if (old != -1 && old != j) s_col[i] = -2;
+            }
+        }
     }
-    return ok ? SOCP_PATH_FUSED : SOCP_PATH_TILED;
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const int c = s_col[i];
+        if (c == -1) continue;
+        if (c == -2) { rowcol[i] = -2; continue; }
+        const int old = atomicCAS(&rowcol[i], -1, c);
+        if (old != -1 && old != c) rowcol[i] = -2;
+    }
 }
 
-void run_solve(Shard& sh, const socp_params& prm) {
+bool f3_candidate(const socp_handle* h) {
+    return h->n > 16 && h->n <= 64 && h->p <= 32 && getenv("SOCP_B200_NO_V3") == nullptr;
+}
+
+// plans the whole-solve kernel of fused_v3.cuh for the row pattern `rowcol` (k entries) and uploads its tables
+void plan_fused3(const socp_handle* h, Shard& sh, const std::vector<int>& rowcol, cudaStream_t stream) {
+    int dev_smem = 0, sms = 148;
+    CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, sh.device));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+    std::vector<int> tables;
+    int* counter = sh.fused2.d_counter;
+    f3_plan(sh.fused3, h->n, h->p, h->k, h->kind, h->offs, h->dim, rowcol, dev_smem, sms, tables);
+    sh.fused3.d_counter = counter;
+    sh.fused3.d_tables = sh.d_f3_tables;
+    sh.f3_planned = true;
+    if (!sh.fused3.fits) return;
+    // the tables are read by the launch that follows on the same stream; the host vector dies with this call, so
+    // the copy must have left pageable memory before returning (cudaMemcpyAsync from pageable memory stages it)
+    CK(cudaMemcpyAsync(sh.d_f3_tables, tables.data(), sizeof(int) * tables.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+}
+
+// pattern of problems [first, first + count) (or of the one shared G) found on the device, then the plan
+void detect_and_plan_fused3(const socp_handle* h, Shard& sh, int first, int count, cudaStream_t stream) {
+    const int k = h->k, n = h->n;
+    std::vector<int> rowcol(k, -2);
+    if (!sh.f3_dense) {
+        CK(cudaMemsetAsync(sh.d_rowcol, 0xFF, sizeof(int) * k, stream));
+        const int nb = sh.sharedG ? 1 : count;
+        const double* G = sh.w.G + (sh.sharedG ? 0 : (int64_t)first * sh.w.sG);
+        const int grid = std::max(1, std::min(nb, 148 * 4));
+        k_row_pattern<<<grid, 256, sizeof(int) * k, stream>>>(G, sh.w.sG, nb, n, k, sh.d_rowcol);
+        CK(cudaPeekAtLastError());
+        sh.launches++;
+        CK(cudaMemcpyAsync(sh.h_rowcol, sh.d_rowcol, sizeof(int) * k, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        rowcol.assign(sh.h_rowcol, sh.h_rowcol + k);
+    }
+    plan_fused3(h, sh, rowcol, stream);
+}
+
+F3Glob f3_glob(const Shard& sh) {
+    const Ws& w = sh.w;
+    F3Glob g{};
+    g.c = w.c; g.A = w.A; g.b = w.b; g.G = w.G; g.h = w.h;
+    g.sA = w.sA; g.sG = w.sG;
+    g.sing = sh.sing_known ? sh.d_sing : nullptr;
+    g.sing_out = sh.d_sing;
+    g.x = w.x; g.y = w.y; g.z = w.z; g.s = w.s; g.pobj = w.pobj; g.dobj = w.dobj;
+    g.status = w.status; g.iters = w.iters; g.active = w.active; g.fail = w.fail;
+    g.deg = w.L.deg;
+    g.npattern = sh.d_npattern;
+    g.dbg = nullptr; g.dbg_prob = -1; g.dbg_iter = -1; g.dbg_phase = 1;
+    return g;
+}
+
+enum { FUSED_NONE = 0, FUSED_V2 = 2, FUSED_V3 = 3 };
+
+// which whole-solve kernel can take the data now resident (plans fused_v3 on first use)
+int fused_kind(const socp_handle* h, Shard& sh) {
+    if (f3_candidate(h)) {
+        if (!sh.f3_planned) detect_and_plan_fused3(h, sh, 0, sh.batch, sh.stream);
+        if (sh.fused3.fits) return FUSED_V3;
+    }
+    if (sh.fused2.fits) {
+        if (!sh.sing_known) ensure_prepared(sh);       // fused_v2 cannot take sing problems: the flags must be known
+        if (!sh.prepared) ensure_prepared(sh);
+        if (!sh.any_sing) return FUSED_V2;
+    }
+    return FUSED_NONE;
+}
+
+int choose_path(const socp_handle* h, Shard& sh, const socp_params& prm, int& kind) {
+    kind = FUSED_NONE;
+    if (prm.path == SOCP_PATH_TILED) return SOCP_PATH_TILED;
+    kind = fused_kind(h, sh);
+    if (prm.path == SOCP_PATH_FUSED) {
+        need(kind != FUSED_NONE, SOCP_ERR_SIZE, "the fused shared-memory kernel needs a layout that fits (and, for n <= 16, no sing problems)");
+        return SOCP_PATH_FUSED;
+    }
+    return kind != FUSED_NONE ? SOCP_PATH_FUSED : SOCP_PATH_TILED;
+}
+
+void run_solve(const socp_handle* h, Shard& sh, const socp_params& prm) {
     need(sh.have_data, SOCP_ERR_STATE, "solve called before set_data");
     sh.launches = 0;
+    int kind = FUSED_NONE;
+    const int path = choose_path(h, sh, prm, kind);      // may run the pattern / sing tests: outside the timed region
     CK(cudaEventRecord(sh.ev[0], sh.stream));
-    const int path = choose_path(sh, prm);
-    if (path == SOCP_PATH_FUSED) {
-        solve_fused2(sh.fused2, sh.w, 0, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream,
-                     /*allow_static=*/getenv("SOCP_B200_GENERIC_ONLY") == nullptr);
+    const bool allow_static = getenv("SOCP_B200_GENERIC_ONLY") == nullptr;
+    if (path == SOCP_PATH_FUSED && kind == FUSED_V3) {
+        const LoopParams lp{prm.max_iter, prm.tol, prm.step_damp, prm.init_eps};
+        const bool detect = !sh.sing_known;
+        solve_fused3_ext(sh.fused3, f3_glob(sh), 0, sh.batch, lp, detect ? 1 : 0, 0, sh.stream, allow_static, 0);
+        CK(cudaGetLastError());
+        if (detect) { sh.sing_known = true; sh.prepared = false; }      // the kernel left the flags in d_sing
+        sh.launches += 1;
+        sh.tim.path_used = SOCP_PATH_FUSED;
+        sh.tim.iterations_max = -1;
+    } else if (path == SOCP_PATH_FUSED) {
+        solve_fused2_ext(sh.fused2, sh.w, 0, sh.batch, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, sh.stream, allow_static, 0);
         CK(cudaGetLastError());
         sh.launches += 1;
         sh.tim.path_used = SOCP_PATH_FUSED;
         sh.tim.iterations_max = -1;
     } else {
+        ensure_prepared(sh);
         ensure_tiled(sh);
+        CK(cudaEventRecord(sh.ev[0], sh.stream));
         solve_tiled(sh, prm);
     }
     CK(cudaEventRecord(sh.ev[1], sh.stream));
@@ -673,14 +808,18 @@ void fetch_results(socp_handle* h, Shard& sh, double* x, double* y, double* z, d
 
 // Problem(c, A, b, G, h, cones) + solve_socp(prob, ss) in one pass over host data (fused path only): the batch is
 // cut into chunks; chunk i+1 uploads (copy engine) while chunk i solves and chunk i-1 downloads.
-bool can_pipeline(const Shard& sh, const socp_params& prm, const uint8_t* sing, int64_t first) {
-    if (!sh.fused2.fits || prm.path == SOCP_PATH_TILED || !sing) return false;
+bool can_pipeline(const socp_handle* h, const Shard& sh, const socp_params& prm, const uint8_t* sing, int64_t first) {
+    if (prm.path == SOCP_PATH_TILED) return false;
+    if (f3_candidate(h)) return true;          // fused_v3 takes sing problems and finds them itself when sing == NULL
+    if (!sh.fused2.fits || !sing) return false;
     for (int64_t q = 0; q < sh.batch; ++q)
         if (sing[first + q]) return false;
     return true;
 }
 
-void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const double* c, const double* A, const double* b,
+// returns false when the pipeline could not be used after all (the first chunk's pattern does not fit the fused
+// kernel): the caller falls back to set_data + solve
+bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const double* c, const double* A, const double* b,
                    const double* G, const double* hvec, const uint8_t* sing, int flags, double* x, double* y, double* z,
                    double* s, int32_t* status, int32_t* iters, double* pobj, double* dobj) {
     const int n = h->n, p = h->p, k = h->k, B = sh.batch;
@@ -690,15 +829,21 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         CK(cudaStreamCreateWithFlags(&sh.down_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&sh.alt_stream, cudaStreamNonBlocking));
     }
+    const bool v3 = f3_candidate(h);
     sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
     sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
     sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
     sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
     sh.any_sing = false;
+    sh.prepared = false;
+    sh.sing_known = sing != nullptr;
+    sh.f3_planned = false;
+    sh.f3_dense = false;
+    sh.have_data = false;
     // Chunk boundaries: two short chunks first (one wave of resident CTAs, then two: PCIe delivers problems about
     // twice as fast as the kernel retires them, so the upload of each next chunk ends before the previous one is
     // solved) so that the solve starts as soon as possible, then up to 8 equal chunks of at least 4 waves each.
-    const int slots = sh.fused2.num_sms * sh.fused2.ctas_per_sm;
+    const int slots = v3 ? sh.fused2.num_sms * 4 : sh.fused2.num_sms * sh.fused2.ctas_per_sm;
     std::vector<int> bounds{0};
     if (B > 8 * slots) { bounds.push_back(slots); bounds.push_back(3 * slots); }
     {
@@ -714,20 +859,14 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         sh.pipe_ev.push_back(e);
     }
     const bool allow_static = getenv("SOCP_B200_GENERIC_ONLY") == nullptr;
+    const LoopParams lp{prm.max_iter, prm.tol, prm.step_damp, prm.init_eps};
     auto up = [&](void* dst, const void* src, size_t bytes) {
         if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, sh.up_stream));
     };
     auto down = [&](void* dst, const void* src, size_t bytes) {
         if (bytes && dst) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, sh.down_stream));
     };
-    CK(cudaEventRecord(sh.ev[0], sh.stream));
-    CK(cudaStreamWaitEvent(sh.up_stream, sh.ev[0], 0));
-    CK(cudaStreamWaitEvent(sh.alt_stream, sh.ev[0], 0));
-    sh.launches = 0;
-    // Consecutive chunks alternate between two compute streams: the persistent CTAs of chunk i+1 move in as those
-    // of chunk i run out of work, so there is no drain bubble between launches.
-    for (int ci = 0; ci < nchunk; ++ci) {
-        cudaStream_t cs = (ci & 1) ? sh.alt_stream : sh.stream;
+    auto upload_chunk = [&](int ci) {
         const int lo = bounds[ci], cb = bounds[ci + 1] - lo;
         const int64_t g0 = f + lo;
         up(sh.d_c + (size_t)lo * n, c + g0 * n, sizeof(double) * cb * n);
@@ -739,10 +878,38 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         }
         if (sh.sharedG) { if (ci == 0) up(sh.d_G, G, sizeof(double) * k * n); }
         else up(sh.d_G + (size_t)lo * k * n, G + g0 * (int64_t)k * n, sizeof(double) * cb * k * n);
-        up(sh.d_sing + lo, sing + g0, cb);
+        if (sing) up(sh.d_sing + lo, sing + g0, cb);
         CK(cudaEventRecord(sh.pipe_ev[2 * ci], sh.up_stream));
+    };
+    CK(cudaEventRecord(sh.ev[0], sh.stream));
+    CK(cudaStreamWaitEvent(sh.up_stream, sh.ev[0], 0));
+    CK(cudaStreamWaitEvent(sh.alt_stream, sh.ev[0], 0));
+    sh.launches = 0;
+    if (!sing) CK(cudaMemsetAsync(sh.d_sing, 0, B, sh.up_stream));
+    if (v3) CK(cudaMemsetAsync(sh.d_npattern, 0, sizeof(int), sh.up_stream));
+    upload_chunk(0);
+    // Consecutive chunks alternate between two compute streams: the persistent CTAs of chunk i+1 move in as those
+    // of chunk i run out of work, so there is no drain bubble between launches.
+    for (int ci = 0; ci < nchunk; ++ci) {
+        cudaStream_t cs = (ci & 1) ? sh.alt_stream : sh.stream;
+        const int lo = bounds[ci], cb = bounds[ci + 1] - lo;
+        const int64_t g0 = f + lo;
+        if (ci + 1 < nchunk) upload_chunk(ci + 1);        // the copy engine stays one chunk ahead
         CK(cudaStreamWaitEvent(cs, sh.pipe_ev[2 * ci], 0));
-        solve_fused2(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, cs, allow_static, ci & 15);
+        if (v3) {
+            if (ci == 0) {
+                // the row pattern of G is taken from the first chunk (one small kernel and a host round trip while the
+                // second chunk uploads); the later chunks are verified against it by the solve kernel itself
+                detect_and_plan_fused3(h, sh, 0, cb, cs);
+                if (!sh.fused3.fits) {
+                    CK(cudaStreamSynchronize(sh.up_stream));
+                    return false;
+                }
+            }
+            solve_fused3_ext(sh.fused3, f3_glob(sh), lo, cb, lp, sing ? 0 : 1, ci > 0 && !sh.sharedG ? 1 : 0, cs, allow_static, ci & 15);
+        } else {
+            solve_fused2_ext(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, cs, allow_static, ci & 15);
+        }
         CK(cudaGetLastError());
         sh.launches += 1;
         CK(cudaEventRecord(sh.pipe_ev[2 * ci + 1], cs));
@@ -756,6 +923,7 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         if (pobj) down(pobj + g0, sh.w.pobj + lo, sizeof(double) * cb);
         if (dobj) down(dobj + g0, sh.w.dobj + lo, sizeof(double) * cb);
     }
+    if (v3) CK(cudaMemcpyAsync(sh.h_rowcol + k, sh.d_npattern, sizeof(int), cudaMemcpyDeviceToHost, sh.down_stream));
     if (nchunk > 1) CK(cudaStreamWaitEvent(sh.stream, sh.pipe_ev[2 * (nchunk - 1) + 1], 0));   // join the alternate stream
     CK(cudaEventRecord(sh.ev[1], sh.stream));
     CK(cudaStreamSynchronize(sh.up_stream));
@@ -772,31 +940,42 @@ void run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     sh.tim.iterations_max = -1;
     sh.have_data = true;
     sh.have_scaling = sh.have_factor = false;
+    if (v3 && !sing) sh.sing_known = true;          // found by the kernel, left in d_sing
+    if (v3 && sh.h_rowcol[k] > 0) {
+        // some problem of a later chunk has nonzeros outside the first chunk's pattern: the data is resident, so solve
+        // the shard again on the all-dense plan and fetch everything (rare; correctness over speed)
+        sh.f3_dense = true;
+        sh.f3_planned = false;
+        if (!sing) {           // the reported problems were not tested for `sing`: start over
+            sh.sing_known = false;
+            CK(cudaMemsetAsync(sh.d_sing, 0, B, sh.stream));
+        }
+        run_solve(h, sh, prm);
+        fetch_results(h, sh, x, y, z, s, status, iters, pobj, dobj);
+    }
+    return true;
 }
 
-// what follows the upload in both constructors: the `sing` test / A'A when they are needed, bookkeeping
-void finish_set_data(Shard& sh, const uint8_t* sing, int p) {
-    const int64_t f = sh.first;
+// what follows the upload in both constructors: bookkeeping; the `sing` test and A'A are left to ensure_prepared
+// (only the tiled path and get_sing need them).  rowcol: the row pattern of G when the caller knows it (CSC upload).
+void finish_set_data(const socp_handle* h, Shard& sh, const uint8_t* sing, const std::vector<int>* rowcol) {
     const int B = sh.batch;
-    // sing / A'A are only needed when there are equalities or the caller
-    // asks for the test; with p == 0 and sing given the tiled buffers stay unallocated
-    bool given_none = false;
-    if (sing) {
-        given_none = true;
-        for (int64_t q = 0; q < B; ++q) given_none &= (sing[f + q] == 0);
-    }
-    if (given_none || (sing && p == 0)) {
-        // A'A (src/densesolver.jl:32) is only used by `sing` problems: nothing to prepare
-        sh.any_sing = !given_none;
-        CK(cudaStreamSynchronize(sh.stream));
-    } else {
-        prepare_problem(sh, sing != nullptr);
-    }
+    sh.sing_known = sing != nullptr;
+    sh.prepared = false;
+    sh.any_sing = false;
+    sh.f3_planned = false;
+    sh.f3_dense = false;
+    if (!sing) CK(cudaMemsetAsync(sh.d_sing, 0, B, sh.stream));
+    CK(cudaStreamSynchronize(sh.stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, sh.ev[0], sh.ev[1]));
     sh.tim.h2d_ms = ms;
     sh.have_data = true;
     sh.have_scaling = sh.have_factor = false;
+    if (f3_candidate(h)) {
+        if (rowcol) plan_fused3(h, sh, *rowcol, sh.stream);
+        else detect_and_plan_fused3(h, sh, 0, B, sh.stream);
+    }
 }
 
 // CSC -> dense column-major on the device: dense[b][lin[j]] = val[b][j], lin = col * rows + row (host-validated, no
@@ -1001,7 +1180,7 @@ int socp_b200_set_data(socp_handle* h, const double* c, const double* A, const d
             sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
             if (sing) h2d(sh, sh.d_sing, sing + f, B);
             CK(cudaEventRecord(sh.ev[1], sh.stream));
-            finish_set_data(sh, sing, p);
+            finish_set_data(h, sh, sing, nullptr);
         });
     });
 }
@@ -1015,6 +1194,12 @@ int socp_b200_set_data_csc(socp_handle* h, const double* c, const socp_csc* A, c
         const int n = h->n, p = h->p, k = h->k;
         const std::vector<int> linG = csc_linear_index(*G, k, n, "G");
         const std::vector<int> linA = p > 0 ? csc_linear_index(*A, p, n, "A") : std::vector<int>();
+        // row pattern of G from the stored entries: one entry in a row = singleton, none = empty (fused_v3.cuh)
+        std::vector<int> rowcolG(k, -1);
+        for (int li : linG) {
+            const int i = li % k, j = li / k;
+            rowcolG[i] = rowcolG[i] == -1 ? j : -2;
+        }
         for_each_shard(h, [&](Shard& sh) {
             const int64_t f = sh.first;
             const int B = sh.batch;
@@ -1032,7 +1217,7 @@ int socp_b200_set_data_csc(socp_handle* h, const double* c, const socp_csc* A, c
             sh.w.sG = sh.sharedG ? 0 : (int64_t)k * n;
             if (sing) h2d(sh, sh.d_sing, sing + f, B);
             CK(cudaEventRecord(sh.ev[1], sh.stream));
-            finish_set_data(sh, sing, p);
+            finish_set_data(h, sh, sing, &rowcolG);
         });
     });
 }
@@ -1044,7 +1229,7 @@ int socp_b200_solve_dev(socp_handle* h, const socp_params* params) {
         socp_b200_default_params(&prm);
         if (params) prm = *params;
         need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
-        for_each_shard(h, [&](Shard& sh) { run_solve(sh, prm); });
+        for_each_shard(h, [&](Shard& sh) { run_solve(h, sh, prm); });
     });
 }
 
@@ -1065,7 +1250,7 @@ int socp_b200_solve(socp_handle* h, const socp_params* params, double* x, double
         if (params) prm = *params;
         need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
         for_each_shard(h, [&](Shard& sh) {
-            run_solve(sh, prm);
+            run_solve(h, sh, prm);
             fetch_results(h, sh, x, y, z, s, status, iters, pobj, dobj);
         });
     });
@@ -1083,11 +1268,14 @@ int socp_b200_solve_host(socp_handle* h, const socp_params* params, const double
         need(c && G && hvec, SOCP_ERR_NULL, "c, G, h must not be null");
         need(h->p == 0 || (A && b), SOCP_ERR_NULL, "A, b must not be null when p > 0");
         need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
-        for (auto& sh : h->shards) pipelined &= can_pipeline(sh, prm, sing, sh.first);
+        for (auto& sh : h->shards) pipelined &= can_pipeline(h, sh, prm, sing, sh.first);
         if (!pipelined) return;
+        std::vector<char> okv(h->shards.size(), 1);
         for_each_shard(h, [&](Shard& sh) {
-            run_pipelined(h, sh, prm, c, A, b, G, hvec, sing, flags, x, y, z, s, status, iters, pobj, dobj);
+            okv[&sh - h->shards.data()] =
+                run_pipelined(h, sh, prm, c, A, b, G, hvec, sing, flags, x, y, z, s, status, iters, pobj, dobj) ? 1 : 0;
         });
+        for (char v : okv) pipelined &= (v != 0);
     });
     if (rc != 0 || pipelined) return rc;
     rc = socp_b200_set_data(h, c, A, b, G, hvec, sing, flags);
@@ -1100,6 +1288,7 @@ int socp_b200_get_sing(socp_handle* h, uint8_t* sing) {
     return guarded(h, [&]() {
         for_each_shard(h, [&](Shard& sh) {
             need(sh.have_data, SOCP_ERR_STATE, "get_sing called before set_data");
+            ensure_prepared(sh);
             d2h(sh, sing + sh.first, sh.d_sing, sh.batch);
             CK(cudaStreamSynchronize(sh.stream));
         });
@@ -1167,6 +1356,7 @@ int socp_b200_compute_scaling(socp_handle* h, const double* s, const double* z, 
 
 int socp_b200_setup_iter(socp_handle* h, int32_t* fail) {
     STEP_PROLOGUE(sh.have_data && sh.have_scaling, "setup_iter needs set_data and compute_scaling first")
+        ensure_prepared(sh);
         ensure_tiled(sh);
         CK(cudaMemsetAsync(w.fail, 0, sizeof(int) * B, sh.stream));
         factor(sh, false, true, nullptr);
@@ -1285,6 +1475,64 @@ int socp_b200_get_H(socp_handle* h, double* out) {
     return 0;
 }
 
+// Parity aid (not a reference interface): one Mehrotra step of the fused whole-solve kernel, taken out of the middle
+// of a real solve.  Problem `index` is solved again on its own; at iteration `iter` the kernel dumps the (s, z) it
+// computes the scaling from, H = G'W^-2 G (+A'A for a sing problem) before the factorisation, and the right-hand side
+// and result of the affine (`phase` = 1) or combined (2) solve_kkt -- the inputs and outputs of the reference's
+// compute_scaling / setup_iter / solve_kkt (src/densesolver.jl:41-90), so that a test can feed the same inputs to the
+// oracle.  Any output pointer may be null.  The problem's entries of the result arrays are overwritten.
+int socp_b200_debug_fused_step(socp_handle* h, int64_t index, int32_t iter, int32_t phase, double* s, double* z,
+                               double* H, double* dx, double* dy, double* dz, double* ds, double* cx, double* cy,
+                               double* cz, double* cs) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        need(index >= 0 && index < h->batch, SOCP_ERR_SIZE, "problem index out of range");
+        need(iter >= 0 && (phase == 1 || phase == 2), SOCP_ERR_SIZE, "iter >= 0 and phase 1 or 2");
+        const int n = h->n, p = h->p, k = h->k;
+        for (auto& sh : h->shards) {
+            if (index < sh.first || index >= sh.first + sh.batch) continue;
+            CK(cudaSetDevice(sh.device));
+            need(sh.have_data, SOCP_ERR_STATE, "debug_fused_step called before set_data");
+            need(fused_kind(h, sh) == FUSED_V3, SOCP_ERR_SIZE, "debug_fused_step needs a layout the fused_v3 kernel takes");
+            const int len = f3_dbg_size(n, p, k);
+            double* d_dbg = nullptr;
+            CK(cudaMalloc((void**)&d_dbg, sizeof(double) * len));
+            std::vector<double> buf((size_t)len, 0.0);
+            int rc = 0;
+            try {
+                CK(cudaMemsetAsync(d_dbg, 0, sizeof(double) * len, sh.stream));
+                socp_params prm;
+                socp_b200_default_params(&prm);
+                F3Glob g = f3_glob(sh);
+                g.dbg = d_dbg;
+                g.dbg_prob = (int)(index - sh.first);
+                g.dbg_iter = iter;
+                g.dbg_phase = phase;
+                const LoopParams lp{prm.max_iter, prm.tol, prm.step_damp, prm.init_eps};
+                solve_fused3_ext(sh.fused3, g, g.dbg_prob, 1, lp, sh.sing_known ? 0 : 1, 0, sh.stream,
+                                 getenv("SOCP_B200_GENERIC_ONLY") == nullptr, 0);
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(buf.data(), d_dbg, sizeof(double) * len, cudaMemcpyDeviceToHost, sh.stream));
+                CK(cudaStreamSynchronize(sh.stream));
+            } catch (...) {
+                cudaFree(d_dbg);
+                throw;
+            }
+            (void)rc;
+            cudaFree(d_dbg);
+            const double* o = buf.data();
+            auto take = [&](double* dst, int cnt) {
+                if (dst) memcpy(dst, o, sizeof(double) * cnt);
+                o += cnt;
+            };
+            take(s, k); take(z, k); take(H, n * n);
+            take(dx, n); take(dy, p); take(dz, k); take(ds, k);
+            take(cx, n); take(cy, p); take(cz, k); take(cs, k);
+            return;
+        }
+    });
+}
+
 // Measurement utility (not a reference interface): runs the device kernels of one step-level call `reps` times on
 // the data already resident after compute_scaling / setup_iter and returns the mean CUDA-event time per call.
 //   0 compute_scaling   1 scale! (W v)   2 iscale! (W^-1 v)   3 vprod!   4 iprod!   5 compute_step
@@ -1300,6 +1548,7 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
         need(sh.have_data && sh.have_scaling, SOCP_ERR_STATE, "profile_step needs set_data and compute_scaling first");
         Ws& w = sh.w;
         const int n = w.L.n, k = w.L.k, B = sh.batch;
+        ensure_prepared(sh);
         ensure_tiled(sh);
         double* Hcopy = nullptr;
         const size_t hbytes = sizeof(double) * (size_t)B * w.ldh * n;
@@ -1349,16 +1598,5 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
     });
 }
 
-#ifdef SOCP_PHASE_TIMING
-// profiling build only (not declared in include/socp_b200.h)
-int socp_b200_debug_phase_clocks2(unsigned long long* out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, socp::g_phase_clk2, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(socp::g_phase_clk2, z, sizeof z);
-    }
-    return 0;
-}
-#endif
 
 }  // extern "C"

@@ -10,34 +10,6 @@
 namespace socp {
 
 // All device pointers of one device shard.  Passed by value to the kernels.
-struct Ws {
-    ConeLayout L;
-    int ldgt, kpad;        // Gt: kpad x n, column stride ldgt (= kpad), pad rows zero
-    int ldh;               // H: n x n, column stride ldh
-    int ldap, ppad;        // Ap: padded copy of A (ppad x n)
-    int ldm;               // M: p x p, column stride ldm
-    // problem data (strides 0 when shared across the batch)
-    const double *c, *A, *b, *G, *h;
-    int64_t sA, sG;
-    const uint8_t* sing;
-    // iterate
-    double *x, *y, *z, *s;
-    // scaling
-    double *lam, *wb, *iwb, *eta;   // eta: 4 scalars per cone (eta, 1/eta, 1/eta^2, 1/(1+wbar0)), [4][ncones]
-    // right-hand side / direction
-    double *dx, *dy, *dz, *ds;
-    double *rx, *ry, *rz, *rs;
-    // solve_kkt temporaries (k-vectors)
-    double *k0, *k2, *u;
-    double *kt2, *kt3;
-    // factor workspaces
-    double *Gt, *H, *HiAt, *M, *AA, *Ap;
-    double *XH, *XM;       // [batch][ceil(n/64)][64*64] inverted diagonal blocks of the factors of H and M
-    ProbScalars* sc;
-    double *pobj, *dobj;   // [batch] objectives of the returned iterate
-    int *status, *iters, *active, *fail;
-    int* nactive;          // [max_iter+2] counters
-};
 
 #define SOCP_VEC(ptr, len) ((ptr) + (int64_t)b * (len))
 

@@ -68,6 +68,7 @@ SYMBOLS = {
     "socp_b200_compute_step": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p]),
     "socp_b200_get_H": (C.c_int, [H, c_double_p]),
     "socp_b200_get_L": (C.c_int, [H, c_double_p]),
+    "socp_b200_debug_fused_step": (C.c_int, [H, C.c_int64, C.c_int32, C.c_int32] + [c_double_p] * 11),
     "socp_b200_profile_step": (C.c_int, [H, C.c_int32, C.c_int32, c_double_p]),
 }
 

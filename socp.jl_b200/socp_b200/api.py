@@ -368,6 +368,22 @@ class BatchSolverState:
         h.check(h.lib.socp_b200_get_sing(h.ptr, out.ctypes.data_as(L.c_uint8_p)), "socp_b200_get_sing")
         return out
 
+    def debug_fused_step(self, index: int, it: int, phase: int = 1) -> dict:
+        """socp_b200_debug_fused_step: the inputs and outputs of one compute_scaling / setup_iter / solve_kkt
+        (reference src/densesolver.jl:41-90) taken from inside the fused whole-solve kernel at Mehrotra iteration
+        `it` of problem `index` (phase 1 = affine solve, 2 = combined solve).  H is returned as (n, n) with
+        H[i, j] = (G'W^-2 G)[i, j]."""
+        h = self.handle
+        n, p, k = h.n, h.p, h.k
+        out = dict(s=np.zeros(k), z=np.zeros(k), H=np.zeros((n, n)), dx=np.zeros(n), dy=np.zeros(max(p, 1)),
+                   dz=np.zeros(k), ds=np.zeros(k), cx=np.zeros(n), cy=np.zeros(max(p, 1)), cz=np.zeros(k), cs=np.zeros(k))
+        order = ("s", "z", "H", "dx", "dy", "dz", "ds", "cx", "cy", "cz", "cs")
+        h.check(h.lib.socp_b200_debug_fused_step(h.ptr, int(index), int(it), int(phase), *[_dp(out[f]) for f in order]),
+                "socp_b200_debug_fused_step")
+        out["H"] = out["H"].T.copy()
+        out["dy"], out["cy"] = out["dy"][:p], out["cy"][:p]
+        return out
+
     def close(self):
         self.handle.close()
 

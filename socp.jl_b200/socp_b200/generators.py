@@ -93,6 +93,49 @@ def random_feasible(batch: int, n: int, p: int, cones: Sequence[Cone], scale: fl
     return BatchProblem(c, A, b, G, h, cones, sing=sing, colmajor=True)
 
 
+def random_feasible_pattern(batch: int, n: int, p: int, cones: Sequence[Cone], mask: np.ndarray, scale: float = 0.1,
+                            first: int = 0, seed0: int = SEED0) -> BatchProblem:
+    """random_feasible with a sparsity pattern on G: `mask` (k x n booleans) says which entries are stored -- one
+    pattern for the whole batch, values per problem (the reference keeps G as a SparseMatrixCSC, src/Socp.jl:29).
+    Stored entries are kept away from zero.  Rows with one stored entry are bounds / single-variable cone rows, empty
+    rows are constants; zero columns make G rank deficient (`sing`, src/Socp.jl:49-56)."""
+    cones = tuple(cones)
+    k = sum(cn.dim for cn in cones)
+    assert mask.shape == (k, n)
+    c = np.empty((batch, n))
+    G = np.zeros((batch, n, k))
+    A = np.empty((batch, n, p))
+    b = np.empty((batch, p))
+    h = np.empty((batch, k))
+    for q in range(batch):
+        r = _rng(first + q, seed0)
+        Gq = (r.standard_normal((n, k)) / np.sqrt(n)) * mask.T
+        Gq[mask.T & (np.abs(Gq) < 1e-3)] = 0.5
+        Aq = r.standard_normal((n, p)) / np.sqrt(n)
+        s0 = np.empty(k)
+        z0 = np.empty(k)
+        for cn in cones:
+            sl = slice(cn.offs, cn.offs + cn.dim)
+            if cn.kind == 0:
+                s0[sl] = r.uniform(0.5, 2.0, cn.dim)
+                z0[sl] = r.uniform(0.5, 2.0, cn.dim)
+            else:
+                for v in (s0, z0):
+                    tail = r.standard_normal(cn.dim - 1)
+                    v[cn.offs + 1:cn.offs + cn.dim] = tail
+                    v[cn.offs] = np.linalg.norm(tail) + r.uniform(0.5, 1.5)
+        x0 = r.standard_normal(n) * scale
+        y0 = r.standard_normal(p) * scale
+        s0 *= scale
+        z0 *= scale
+        G[q] = Gq
+        A[q] = Aq
+        h[q] = Gq.T @ x0 + s0
+        b[q] = Aq.T @ x0
+        c[q] = -(Aq @ y0) - Gq @ z0
+    return BatchProblem(c, A, b, G, h, cones, sing=None, colmajor=True)
+
+
 # BASELINE.json configs (SURVEY.md section 8): name -> generator kwargs
 CONFIGS: Dict[str, dict] = {
     "C2": dict(kind="portfolio", n=50, batch=10_000),

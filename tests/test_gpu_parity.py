@@ -409,18 +409,18 @@ def test_solve_host_pipelined_matches_two_step():
 
 def test_multi_device_handle_matches_single_device():
     """socp_b200_create(devices=[0, 1]) shards the batch contiguously over the devices of one process (no collective);
-    results must equal the single-device ones bit for bit (same kernels, same problems).  Needs two GPUs."""
+    results must equal the single-device ones bit for bit (same kernels, same problems).  On a box with one GPU the
+    second shard lives on device 0 as well (the same for_each_shard code path: one host worker + stream per shard)."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two CUDA devices")
+    d1 = 1 if torch.cuda.device_count() >= 2 else 0
     prob = gen.make_config("C2", batch=301)           # odd split: 151 + 150
     one = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0]))
-    two = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0, 1]))
+    two = sb.solve_socp_batch(prob, sb.SolverState(prob, devices=[0, d1]))
     for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
         assert np.array_equal(getattr(one, f), getattr(two, f)), f
     prob3 = gen.make_config("C3", batch=1000)
-    a = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[1]))
-    b = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[0, 1]))
+    a = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[d1]))
+    b = sb.solve_socp_batch(prob3, sb.SolverState(prob3, devices=[0, d1]))
     assert np.array_equal(a.status, b.status) and np.array_equal(a.x, b.x)
 
 
@@ -515,3 +515,127 @@ def test_fused_generic_layouts_vs_c_oracle(name):
     both = (til.iters == res.iters) & conv
     dt = rel(til.pobj[both], res.pobj[both])
     assert dt.max() <= 1e-5 and np.median(dt) <= 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ fused_v3 kernel
+STEP_LAYOUTS = {
+    "C2": None,
+    "mixed_p2": (20, 2, (sb.POC(0, 6), sb.SOC(6, 9), sb.SOC(15, 5))),
+    "mixed_n60_p9": (60, 9, (sb.POC(0, 10), sb.SOC(10, 30), sb.SOC(40, 30), sb.SOC(70, 30))),
+    "edge_p32": (40, 32, (sb.POC(0, 50), sb.SOC(50, 20))),
+    "edge_n64": (64, 0, (sb.POC(0, 16), sb.SOC(16, 64))),
+}
+
+
+@pytest.mark.parametrize("name", list(STEP_LAYOUTS))
+def test_fused_step_level_vs_oracle(name):
+    """One Mehrotra step taken out of the fused whole-solve kernel (socp_b200_debug_fused_step) against
+    DenseSolver.setup_iter / solve_kkt of the numpy oracle (reference src/densesolver.jl:41-90) from the kernel's own
+    (s, z) and right-hand sides: H = G'W^-2 G <= 1e-12, cx, cy, cz, cs <= 1e-10 on C2 (1e-9 on the generated families,
+    whose systems are worse conditioned).  Pins the diagonal + low-rank assembly of the KKT matrix (SURVEY.md section
+    8, row f4) and the fused factor / solve, which the whole-solve tests only see end to end."""
+    from oracle import socp_oracle as so
+    if STEP_LAYOUTS[name] is None:
+        prob = gen.make_config("C2", batch=8)
+        tol = 1e-10
+    else:
+        n, p, cones = STEP_LAYOUTS[name]
+        prob = gen.random_feasible(8, n, p, cones, 0.1)
+        tol = 1e-9
+    ss = sb.SolverState(prob)
+    ss.load(prob)
+    nrm = lambda a, b: np.max(np.abs(a - b)) / np.max(np.abs(b))
+    for q, it, phase in ((0, 0, 1), (3, 2, 2), (7, 4, 1)):
+        d = ss.debug_fused_step(q, it, phase)
+        pr = so.Problem.create(prob.c[q], prob.A_dense(q), prob.b[q], prob.G_dense(q), prob.h[q], ocones(prob.cones), sing=False)
+        sc = so.compute_scaling(pr.cones, so.Scaling.create(pr.cones), d["s"], d["z"])
+        dsv = so.DenseSolver(pr)
+        dsv.setup_iter(pr, sc)
+        assert nrm(d["H"], dsv.H) <= 1e-12, (q, it, nrm(d["H"], dsv.H))
+        cx, cy, cz, cs = dsv.solve_kkt(pr, sc, d["dx"], d["dy"], d["dz"], d["ds"], fast_iprod=True)
+        for nm, v in (("cx", cx), ("cy", cy), ("cz", cz), ("cs", cs)):
+            if v.size:
+                assert nrm(d[nm], v) <= tol, (q, it, phase, nm, nrm(d[nm], v))
+
+
+def _sing_mask(n, k, zero_cols):
+    m = np.ones((k, n), dtype=bool)
+    m[:, list(zero_cols)] = False
+    return m
+
+
+def test_mixed_sing_batch_through_solve_host():
+    """`sing` on the production entry (reference src/Socp.jl:49-56): socp_b200_solve_host with sing == NULL on a batch
+    where every second problem has a rank-deficient G (two variables appear in no cone row; the equality rows pin them
+    down).  The fused kernel's initial factorisation of G'G is the reference's test; the flagged problems are solved
+    with A'A added (src/densesolver.jl:44-46,68-80).  Statuses / objectives against the C oracle told which are sing."""
+    from oracle import c_oracle as co
+    n, p = 20, 3
+    cones = (sb.POC(0, 8), sb.SOC(8, 14))
+    B = 64
+    reg = gen.random_feasible_pattern(B, n, p, cones, np.ones((22, n), dtype=bool), 0.1)
+    sng = gen.random_feasible_pattern(B, n, p, cones, _sing_mask(n, 22, (18, 19)), 0.1, seed0=999)
+    pick = lambda a, b: np.ascontiguousarray(np.where((np.arange(B) % 2 == 0).reshape((B,) + (1,) * (a.ndim - 1)), a, b))
+    prob = sb.BatchProblem(pick(reg.c, sng.c), pick(reg.A_cm, sng.A_cm), pick(reg.b, sng.b), pick(reg.G_cm, sng.G_cm),
+                           pick(reg.h, sng.h), cones, sing=None, colmajor=True)
+    ss = sb.SolverState(prob)
+    res = sb.solve_socp_batch(prob, ss)                    # reload=True -> socp_b200_solve_host, sing == NULL
+    assert res.timings["path_used"] == sb.PATH_FUSED
+    flags = (np.arange(B) % 2).astype(np.uint8)
+    assert np.array_equal(ss.get_sing(), flags)
+    ref = co.solve_batch(prob.c, prob.A_cm, prob.b, prob.G_cm, prob.h, ocones(cones), sing=flags, nthreads=4)
+    conv = ref["status"] == sb.STATUS_CONVERGED
+    assert conv[flags == 1].mean() >= 0.8                  # the sing problems are solvable (and solved) with A'A
+    agree = (res.status == sb.STATUS_CONVERGED) == conv
+    assert agree.mean() >= 0.9, (res.status, ref["status"])
+    same = agree & conv & (res.iters == ref["iters"])
+    assert same.sum() >= B // 2
+    rel = lambda a, b: np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    d = np.maximum(rel(res.pobj[same], ref["pobj"][same]), rel(res.dobj[same], ref["dobj"][same]))
+    assert d.max() <= 1e-5 and np.median(d) <= 1e-7, (d.max(), np.median(d))
+    # the same batch with the flags given, and on the tiled path, finds the same flags / outcomes
+    given = sb.BatchProblem(prob.c, prob.A_cm, prob.b, prob.G_cm, prob.h, cones, sing=flags, colmajor=True)
+    rg = sb.solve_socp_batch(given, sb.SolverState(given))
+    assert np.array_equal(rg.status, res.status) and np.array_equal(rg.pobj, res.pobj)
+    til = sb.solve_socp_batch(prob, sb.SolverState(prob), sb.default_params(path=sb.PATH_TILED))
+    assert ((til.status == sb.STATUS_CONVERGED) == conv).mean() >= 0.9
+
+
+def test_compressed_pattern_matches_dense_plan():
+    """C2's G = [-I; 0'; -F]: the fused kernel keeps rows 0..49 as (column, value) pairs, drops row 50 and stores only
+    the 50 dense rows.  SOCP_B200_NO_V3=1 runs the first-generation kernel on the full 101 x 50 matrix: same statuses and
+    iteration counts, objectives within 1e-9 (the two differ in summation order only)."""
+    import subprocess, sys, json, os
+    prob = gen.make_config("C2", batch=600)
+    res = sb.solve_socp_batch(prob, sb.SolverState(prob))
+    code = ("import sys, json, numpy as np; sys.path[:0] = %r; import socp_b200 as sb; from socp_b200 import generators as gen;"
+            "prob = gen.make_config('C2', batch=600); r = sb.solve_socp_batch(prob, sb.SolverState(prob));"
+            "print(json.dumps(dict(status=r.status.tolist(), iters=r.iters.tolist(), pobj=r.pobj.tolist())))") % (sys.path[:4],)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, SOCP_B200_NO_V3="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    old = json.loads(out.stdout.strip().splitlines()[-1])
+    assert np.array_equal(res.status, np.array(old["status"])) and (res.status == sb.STATUS_CONVERGED).all()
+    assert np.array_equal(res.iters, np.array(old["iters"]))
+    assert np.max(np.abs(res.pobj - np.array(old["pobj"])) / np.maximum(1.0, np.abs(res.pobj))) <= 1e-9
+
+
+def test_pattern_violation_in_a_later_chunk_falls_back():
+    """The pipelined one-shot solve takes the row pattern of G from its first chunk; a problem of a later chunk with a
+    nonzero outside that pattern is reported by the kernel (verify mode) and the shard is solved again on the all-dense
+    plan -- the results must be those of the same batch loaded with set_data (pattern over the whole batch)."""
+    prob = gen.make_config("C2", batch=5000)          # > 8 waves of 592 resident CTAs: several chunks
+    G = prob.G_cm.copy()
+    G[4100, 7, 3] = 0.25                               # row 3 of problem 4100 gets a second nonzero (column 7)
+    bad = sb.BatchProblem(prob.c, prob.A_cm, prob.b, G, prob.h, prob.cones, sing=prob.sing, colmajor=True)
+    one = sb.solve_socp_batch(bad, sb.SolverState(bad))                      # solve_host, pipelined
+    ss2 = sb.SolverState(bad)
+    ss2.load(bad)
+    two = sb.solve_socp_batch(bad, ss2, reload=False)                        # set_data + solve
+    assert (one.status == sb.STATUS_CONVERGED).all() and np.array_equal(one.status, two.status)
+    assert np.all(np.abs(one.iters.astype(int) - two.iters.astype(int)) <= 1) and (one.iters == two.iters).mean() >= 0.99
+    assert np.max(np.abs(one.pobj - two.pobj) / np.maximum(1.0, np.abs(two.pobj))) <= 1e-9
+    from oracle import socp_oracle as so
+    pr = so.Problem.create(bad.c[4100], bad.A_dense(4100), bad.b[4100], bad.G_dense(4100), bad.h[4100], ocones(bad.cones), sing=False)
+    ref = so.solve_socp(pr, init="reduced", fast_iprod=True)
+    assert ref.status == one.status[4100] and abs(ref.iters - int(one.iters[4100])) <= 1
+    assert abs(ref.pobj - one.pobj[4100]) <= 1e-8 * max(1.0, abs(ref.pobj))
