@@ -8,15 +8,3 @@ void solve_fused2_ext(F2Plan& plan, const Ws& g, int first, int batch, int max_i
     solve_fused2(plan, g, first, batch, max_iter, tol, step_damp, init_eps, stream, allow_static, counter_slot);
 }
 }  // namespace socp
-
-#ifdef SOCP_PHASE_TIMING
-// profiling build only (not declared in include/socp_b200.h)
-extern "C" int socp_b200_debug_phase_clocks2(unsigned long long* out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, socp::g_phase_clk2, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(socp::g_phase_clk2, z, sizeof z);
-    }
-    return 0;
-}
-#endif

@@ -45,6 +45,7 @@ struct F2Plan {
     int ctas_per_sm = 1, num_sms = 148;
     size_t smem = 0;
     int* d_counter = nullptr;
+    unsigned long long* d_clk = nullptr;   // 16 phase-cycle counters (SOCP_PHASE_TIMING builds)
     // layout
     int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
     int npad = 0, nb = 0, kpad = 0, ldg = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
@@ -221,9 +222,6 @@ __device__ __forceinline__ void f2_xtx(const double* X, int ld, int nb, double* 
     }
 }
 
-#ifdef SOCP_PHASE_TIMING
-static __device__ unsigned long long g_phase_clk2[16];       // tools/phase_timing.py; slots 13 / 15: inside f2_chol_inv (warp 0)
-#endif
 
 // ------------------------------------------------------------------------------------------------ blocked Cholesky + inverse
 // Trailing-update tile descriptors of the blocked factorisation: for block column b, tile (i, j), i > b, j <= i
@@ -263,11 +261,11 @@ __device__ __forceinline__ void f2_build_trail(uint2* desc, int nbl, int ld, int
 // PosDefException, src/densesolver.jl:47,51.
 template <int NW, bool WRITE_L = false>
 __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, const uint2* desc, int nbl, int ld,
-                                           int* fail, int lane, int warp) {
+                                           int* fail, int lane, int warp, unsigned long long* clk = nullptr) {
     const int fr = lane >> 2, fk = lane & 3;
     const int la = fk * ld + fr;
 #ifdef SOCP_PHASE_TIMING
-    const bool pt_on = (NW == 8) && !WRITE_L && threadIdx.x == 0 && blockIdx.x == 0;
+    const bool pt_on = clk && (NW == 8) && !WRITE_L && threadIdx.x == 0 && blockIdx.x == 0;
     long long pt_c = clock64();
 #endif
     for (int b = 0; b < nbl; ++b) {
@@ -291,11 +289,11 @@ __device__ __forceinline__ int f2_chol_inv(double* H, double* X, double* Dinv, c
             }
         }
 #ifdef SOCP_PHASE_TIMING
-        if (pt_on) { const long long t = clock64(); atomicAdd(&g_phase_clk2[13], (unsigned long long)(t - pt_c)); pt_c = t; }
+        if (pt_on) { const long long t = clock64(); atomicAdd(&clk[13], (unsigned long long)(t - pt_c)); pt_c = t; }
 #endif
         tsync<NW>();                                   // (1) Dinv_b visible; trailing update of step b-1 complete
 #ifdef SOCP_PHASE_TIMING
-        if (pt_on) { const long long t = clock64(); atomicAdd(&g_phase_clk2[15], (unsigned long long)(t - pt_c)); pt_c = t; }
+        if (pt_on) { const long long t = clock64(); atomicAdd(&clk[15], (unsigned long long)(t - pt_c)); pt_c = t; }
 #endif
         if (*fail) return 0;
         // ---- panel: H(i,b) <- H(i,b) Dinv_b'  (i > b);   X(b,c) <- Dinv_b X(b,c)  (c < b)
@@ -430,7 +428,7 @@ struct F2Args {
     do {                                                                          \
         if (tid == 0 && blockIdx.x == 0) {                                        \
             const long long t_ = clock64();                                       \
-            atomicAdd(&g_phase_clk2[idx], (unsigned long long)(t_ - pt_t0));      \
+            atomicAdd(&a.P.d_clk[idx], (unsigned long long)(t_ - pt_t0));      \
             pt_t0 = t_;                                                           \
         }                                                                         \
     } while (0)
@@ -715,7 +713,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
                 if (tid == 0) s_fail = 0;
                 tsync<NW>();
                 PT2_MARK(P2_SYRK);
-                int ok = f2_chol_inv<NW>(H, X, Dinv, desc, nb, ldh, &s_fail, lane, warp);          // :47
+                int ok = f2_chol_inv<NW>(H, X, Dinv, desc, nb, ldh, &s_fail, lane, warp, a.P.d_clk);          // :47
                 PT2_MARK(P2_XTX);              // slot 11 = f2_chol_inv; slot P2_CHOL below = f2_xtx (tools/phase_timing.py)
                 if (ok) f2_xtx<NW, MAXT>(X, ldh, nb, H, tl, lane, warp);                         // :48  Li = H^-1 (explicit)
                 tsync<NW>();

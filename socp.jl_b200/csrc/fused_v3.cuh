@@ -63,6 +63,7 @@ struct F3Plan {
     int ctas_per_sm = 1, num_sms = 148;
     size_t smem = 0;
     int* d_counter = nullptr;
+    unsigned long long* d_clk = nullptr;   // 16 phase-cycle counters (SOCP_PHASE_TIMING builds, tools/phase_timing.py)
     const int* d_tables = nullptr;   // device copy of `tables` (srow_col[k] | scol_ptr[n+1] | scol_rows[nsing])
     int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
     int npad = 0, nb = 0, ntl = 0;
@@ -333,9 +334,6 @@ __device__ __forceinline__ int f3_diag_factor(const double* T, int lane, double 
     return ok;
 }
 
-#ifdef SOCP_PHASE_TIMING
-static __device__ unsigned long long g_phase_clk3[16];
-#endif
 
 // In-place blocked Cholesky that carries the inverse along.  Tt: nbl x nbl packed lower tiles (unit pad diagonal).
 // On exit every tile holds the corresponding tile of X = L^-1 (diagonal tiles lower triangular, zeros above).
@@ -349,10 +347,10 @@ static __device__ unsigned long long g_phase_clk3[16];
 // clears both.
 template <int NW>
 __device__ __forceinline__ int f3_chol_inv(double* Tt, double* Lp, const unsigned short* tij, int nbl, int* fail,
-                                           int lane, int warp, const T3Lane& TL) {
+                                           int lane, int warp, const T3Lane& TL, unsigned long long* clk = nullptr) {
     const int ntl = nbl * (nbl + 1) / 2;
 #ifdef SOCP_PHASE_TIMING
-    const bool pt_on = threadIdx.x == 0 && blockIdx.x == 0;
+    const bool pt_on = clk && threadIdx.x == 0 && blockIdx.x == 0;
     long long pt_c = clock64();
 #endif
     for (int b = 0; b < nbl; ++b) {
@@ -373,11 +371,11 @@ __device__ __forceinline__ int f3_chol_inv(double* Tt, double* Lp, const unsigne
             }
         }
 #ifdef SOCP_PHASE_TIMING
-        if (pt_on) { const long long t = clock64(); atomicAdd(&g_phase_clk3[13], (unsigned long long)(t - pt_c)); pt_c = t; }
+        if (pt_on) { const long long t = clock64(); atomicAdd(&clk[13], (unsigned long long)(t - pt_c)); pt_c = t; }
 #endif
         tsync<NW>();                                   // (1) X_bb visible; trailing update of step b-1 complete
 #ifdef SOCP_PHASE_TIMING
-        if (pt_on) { const long long t = clock64(); atomicAdd(&g_phase_clk3[15], (unsigned long long)(t - pt_c)); pt_c = t; }
+        if (pt_on) { const long long t = clock64(); atomicAdd(&clk[15], (unsigned long long)(t - pt_c)); pt_c = t; }
 #endif
         if (fail[b & 1]) return 0;
         // ---- panel
@@ -527,7 +525,7 @@ __device__ __forceinline__ void f3_symv(const double* Tt, int nb, const double* 
     do {                                                                          \
         if (tid == 0 && blockIdx.x == 0) {                                        \
             const long long t_ = clock64();                                       \
-            atomicAdd(&g_phase_clk3[idx], (unsigned long long)(t_ - pt_t0));      \
+            atomicAdd(&a.P.d_clk[idx], (unsigned long long)(t_ - pt_t0));      \
             pt_t0 = t_;                                                           \
         }                                                                         \
     } while (0)
@@ -897,7 +895,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                     tsync<NW>();
                 }
                 PT3_MARK(P3_SYRK);
-                int ok = f3_chol_inv<NW>(Tt, Lp, tij, nb, s_fail, lane, warp, TL);          // :47
+                int ok = f3_chol_inv<NW>(Tt, Lp, tij, nb, s_fail, lane, warp, TL, a.P.d_clk);          // :47
                 PT3_MARK(P3_CHOL);
                 if (!ok && phase == 0 && a.sing_detect && !sing && p > 0) {
                     // cholesky(G'G) threw: the reference's `sing` (src/Socp.jl:49-56).  Repeat the initial point with A'A.

@@ -518,6 +518,7 @@ void build_shard(socp_handle* h, Shard& sh) {
     }
     f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
     sh.fused2.d_counter = sh.alloc<int>(16);
+    sh.fused2.d_clk = sh.alloc<unsigned long long>(32);
     sh.d_f3_tables = sh.alloc<int>((size_t)2 * k + n + 2);
     sh.d_rowcol = sh.alloc<int>(k);
     sh.d_npattern = sh.alloc<int>(1);
@@ -676,8 +677,10 @@ void plan_fused3(const socp_handle* h, Shard& sh, const std::vector<int>& rowcol
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
     std::vector<int> tables;
     int* counter = sh.fused2.d_counter;
+    unsigned long long* clk = sh.fused2.d_clk + 16;
     f3_plan(sh.fused3, h->n, h->p, h->k, h->kind, h->offs, h->dim, rowcol, dev_smem, sms, tables);
     sh.fused3.d_counter = counter;
+    sh.fused3.d_clk = clk;
     sh.fused3.d_tables = sh.d_f3_tables;
     sh.f3_planned = true;
     if (!sh.fused3.fits) return;
@@ -1598,5 +1601,20 @@ int socp_b200_profile_step(socp_handle* h, int32_t which, int32_t reps, double* 
     });
 }
 
+
+#ifdef SOCP_PHASE_TIMING
+// profiling build only (not declared in include/socp_b200.h): the 2 x 16 phase-cycle counters of shard 0
+// (fused_v2 | fused_v3), see tools/phase_timing.py
+int socp_b200_debug_phase_clocks(socp_handle* h, unsigned long long* out32, int reset) {
+    if (!h) return SOCP_ERR_NULL;
+    return guarded(h, [&]() {
+        Shard& sh = h->shards[0];
+        CK(cudaSetDevice(sh.device));
+        CK(cudaStreamSynchronize(sh.stream));
+        if (out32) CK(cudaMemcpy(out32, sh.fused2.d_clk, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost));
+        if (reset) CK(cudaMemset(sh.fused2.d_clk, 0, sizeof(unsigned long long) * 32));
+    });
+}
+#endif
 
 }  // extern "C"
