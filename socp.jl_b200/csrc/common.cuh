@@ -163,6 +163,24 @@ __device__ __forceinline__ void named_bar_arrive() {
 #endif
 }
 
+// the same with the barrier number in a register (teams of one CTA each own a pair of barriers)
+template <int NT>
+__device__ __forceinline__ void bar_sync_id(int id) {
+#ifdef SOCP_SIMT_EMU
+    emu_bar_sync(id, NT);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory");
+#endif
+}
+template <int NT>
+__device__ __forceinline__ void bar_arrive_id(int id) {
+#ifdef SOCP_SIMT_EMU
+    emu_bar_arrive(id, NT);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory");
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);

@@ -46,6 +46,12 @@ __device__ __forceinline__ void tsync() {
     if (NW == 1) __syncwarp();
     else __syncthreads();
 }
+// barrier of one team of NW warps inside a CTA that holds several teams: hardware barrier `bar` (1..15) is the team's
+template <int NW>
+__device__ __forceinline__ void tsync_t(int bar) {
+    if (NW == 1) __syncwarp();
+    else bar_sync_id<NW * 32>(bar);
+}
 __device__ __forceinline__ double grp_sum(double v, int lpc) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -55,7 +61,7 @@ __device__ __forceinline__ double grp_sum(double v, int lpc) {
 // Team-wide reduction of NS sums (v[0..NS)), NM maxima (v[NS..NS+NM)) and one flag through a scratch slot
 // (8 doubles per warp).  One team barrier (none for a one-warp team); the caller alternates `scr` between two slots.
 template <int NW, int NS, int NM>
-__device__ __forceinline__ void team_reduce(double (&v)[NS + NM], int& flag, double* scr, int lane, int warp) {
+__device__ __forceinline__ void team_reduce(double (&v)[NS + NM], int& flag, double* scr, int lane, int warp, int bar = -1) {
 #pragma unroll
     for (int i = 0; i < NS; ++i) v[i] = warp_sum(v[i]);
 #pragma unroll
@@ -68,7 +74,8 @@ __device__ __forceinline__ void team_reduce(double (&v)[NS + NM], int& flag, dou
         for (int i = 0; i < NS + NM; ++i) q[i] = v[i];
         q[7] = (double)flag;
     }
-    __syncthreads();
+    if (bar < 0) __syncthreads();
+    else bar_sync_id<NW * 32>(bar);
 #pragma unroll
     for (int i = 0; i < NS; ++i) v[i] = 0.0;
 #pragma unroll

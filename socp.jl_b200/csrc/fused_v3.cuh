@@ -57,11 +57,52 @@ __device__ __forceinline__ double t3_sym(const double* Tt, int i, int j) {
     return Tt[t3_idx(r >> 3, c >> 3) * 64 + t3_off(r & 7, c & 7)];
 }
 
-struct F3Plan {
+// offsets into one team's slice of the dynamic shared memory, in doubles -- a pure function of the layout, so that the
+// kernels specialised on a layout at compile time address shared memory with immediates
+struct F3Offs {
+    int oG, oT, oLp, oA, oAt, oHiAt, oK, oMt, oMLp, oMinv;
+    int oc, ox, odx, on0, ocx, okd, osd, oatdy, ob, oy, ody, ocy, omd, ohc;
+    int oh, oz, os, olam, owb, oiwb, odz, ods, ok0, ok2, ou, odw, osval, ocs, oscr;
+    int otab, otij, otijm;
+    int total;
+};
+__host__ __device__ constexpr F3Offs f3_offsets(int n, int p, int k, int kpoc, int nsoc, int kd, int nsing, int nw) {
+    const int npad = (n + 7) / 8 * 8, nb = npad / 8, ntl = nb * (nb + 1) / 2;
+    const int pb = ((p > 1 ? p : 1) + 7) / 8, ntlm = pb * (pb + 1) / 2;
+    const int kdpad = (kd + 3) / 4 * 4, ldg = f2_ld(kdpad > 4 ? kdpad : 4);
+    const int kvl = (k + 5 + 1) / 2 * 2;
+    const int ns1 = nsoc > 1 ? nsoc : 1;
+    F3Offs O{};
+    int at = 0;
+#define F3_TAKE(field, cnt) do { O.field = at; at += ((cnt) + 1) / 2 * 2; } while (0)
+    F3_TAKE(oG, ldg * n);
+    F3_TAKE(oT, ntl * 64);
+    F3_TAKE(oLp, (nb - 1 > 3 ? nb - 1 : 3) * 64);      // panel L_ib of the current block column; 2 x (8x12) scratch when p <= 8
+    F3_TAKE(oA, p * n); F3_TAKE(oAt, p * npad); F3_TAKE(oHiAt, p * npad); F3_TAKE(oK, p * npad);
+    F3_TAKE(oMt, p > 8 ? ntlm * 64 : 0); F3_TAKE(oMLp, p > 8 ? (pb - 1) * 64 : 0); F3_TAKE(oMinv, p * p);
+    F3_TAKE(oc, npad); F3_TAKE(ox, npad); F3_TAKE(odx, npad); F3_TAKE(on0, npad); F3_TAKE(ocx, npad);
+    F3_TAKE(okd, p ? npad : 0); F3_TAKE(osd, npad); F3_TAKE(oatdy, p ? npad : 0);
+    F3_TAKE(ob, p); F3_TAKE(oy, p); F3_TAKE(ody, p); F3_TAKE(ocy, p); F3_TAKE(omd, p);
+    F3_TAKE(ohc, ns1 * npad);
+    F3_TAKE(oh, kvl); F3_TAKE(oz, kvl); F3_TAKE(os, kvl); F3_TAKE(olam, kvl); F3_TAKE(owb, kvl);
+    F3_TAKE(odz, kvl); F3_TAKE(ods, kvl); F3_TAKE(ok0, kvl); F3_TAKE(ok2, kvl); F3_TAKE(ou, kvl);
+    F3_TAKE(odw, kvl); F3_TAKE(osval, kvl);
+    F3_TAKE(oiwb, kpoc);
+    F3_TAKE(ocs, F2_CS * ns1);
+    F3_TAKE(oscr, 2 * 8 * nw);
+    F3_TAKE(otab, (k + n + 1 + nsing + 1) / 2);                          // ints: srow_col[k] | scol_ptr[n+1] | scol_rows[nsing]
+    F3_TAKE(otij, (ntl + 3) / 4); F3_TAKE(otijm, p > 8 ? (ntlm + 3) / 4 : 0);   // unsigned shorts
+#undef F3_TAKE
+    O.total = at;
+    return O;
+}
+
+struct F3Plan : F3Offs {
     bool fits = false;
     int nw = 4;
     int ctas_per_sm = 1, num_sms = 148;
-    size_t smem = 0;
+    bool teams4 = false;             // four teams (problems) fit into one CTA's shared memory
+    size_t smem = 0;                 // per team
     int* d_counter = nullptr;
     unsigned long long* d_clk = nullptr;   // 16 phase-cycle counters (SOCP_PHASE_TIMING builds, tools/phase_timing.py)
     const int* d_tables = nullptr;   // device copy of `tables` (srow_col[k] | scol_ptr[n+1] | scol_rows[nsing])
@@ -73,12 +114,6 @@ struct F3Plan {
     int split_kd = 1, split_p = 1;
     int shape = 0;
     int soc_offs[F2_MAX_SOC], soc_dim[F2_MAX_SOC];
-    // offsets into the dynamic shared memory, in doubles
-    int oG, oT, oLp, oA, oAt, oHiAt, oK, oMt, oMLp, oMinv;
-    int oc, ox, odx, on0, ocx, okd, osd, oatdy, ob, oy, ody, ocy, omd, ohc;
-    int oh, oz, os, olam, owb, oiwb, odz, ods, ok0, ok2, ou, odw, osval, ocs, oscr;
-    int otab, otij, otijm;
-    int total = 0;
 };
 
 // rowcol[i]: -1 = row i of G is empty in every problem, j >= 0 = its only nonzeros sit in column j, -2 = dense.
@@ -134,31 +169,13 @@ inline void f3_plan(F3Plan& P, int n, int p, int k, const std::vector<int>& kind
     tables.insert(tables.end(), crow.begin(), crow.end());
     P.split_kd = f2_split((std::max(P.kd, 1) + 1) / 2, P.nw);
     P.split_p = f2_split(std::max(p, 1), P.nw);
-    int at = 0;
-    auto take = [&](int cnt) { int r = at; at += (cnt + 1) / 2 * 2; return r; };
-    P.oG = take(P.ldg * n);
-    P.oT = take(P.ntl * 64);
-    P.oLp = take(std::max(P.nb - 1, 3) * 64);          // panel L_ib of the current block column; 2 x (8x12) scratch when p <= 8
-    P.oA = take(p * n); P.oAt = take(p * P.npad); P.oHiAt = take(p * P.npad); P.oK = take(p * P.npad);
-    P.oMt = take(p > 8 ? P.ntlm * 64 : 0); P.oMLp = take(p > 8 ? (P.pb - 1) * 64 : 0); P.oMinv = take(p * p);
-    P.oc = take(P.npad); P.ox = take(P.npad); P.odx = take(P.npad); P.on0 = take(P.npad); P.ocx = take(P.npad);
-    P.okd = take(p ? P.npad : 0); P.osd = take(P.npad); P.oatdy = take(p ? P.npad : 0);
-    P.ob = take(p); P.oy = take(p); P.ody = take(p); P.ocy = take(p); P.omd = take(p);
-    P.ohc = take(std::max(P.nsoc, 1) * P.npad);
-    P.oh = take(P.kvl); P.oz = take(P.kvl); P.os = take(P.kvl); P.olam = take(P.kvl); P.owb = take(P.kvl);
-    P.odz = take(P.kvl); P.ods = take(P.kvl); P.ok0 = take(P.kvl); P.ok2 = take(P.kvl); P.ou = take(P.kvl);
-    P.odw = take(P.kvl); P.osval = take(P.kvl);
-    P.oiwb = take(P.kpoc);
-    P.ocs = take(F2_CS * std::max(P.nsoc, 1));
-    P.oscr = take(2 * 8 * P.nw);
-    P.otab = take(((int)tables.size() + 1) / 2);                         // ints
-    P.otij = take((P.ntl + 3) / 4); P.otijm = take(p > 8 ? (P.ntlm + 3) / 4 : 0);   // unsigned shorts
-    P.total = at;
-    P.smem = (size_t)at * sizeof(double);
+    static_cast<F3Offs&>(P) = f3_offsets(n, p, k, P.kpoc, P.nsoc, P.kd, P.nsing, P.nw);
+    P.smem = (size_t)P.total * sizeof(double);
     P.num_sms = num_sms;
     if (P.smem + 512 > (size_t)dev_smem_optin) return;
     const int per_sm = 228 * 1024;
     P.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (P.smem + 1024)), 2048 / (P.nw * 32), 4}));
+    P.teams4 = 4 * P.smem + 256 <= (size_t)dev_smem_optin;
     P.fits = true;
 }
 
@@ -187,6 +204,7 @@ struct F3Args {
     int* counter;
     int sing_detect;          // 1: `sing` is unknown -- a failing factorisation of G'G switches the problem to sing
     int verify;               // 1: check every entry of G outside the pattern while loading
+    int align;                // TEAMS > 1: re-align the teams of a CTA at the top of every iteration
 };
 
 // ------------------------------------------------------------------------------------------------ layout providers
@@ -205,6 +223,8 @@ struct Dims3Dyn {
     __device__ __forceinline__ static int split_p(const F3Plan& P) { return P.split_p; }
     __device__ __forceinline__ static int soc_offs(const F3Plan& P, int slot) { return P.soc_offs[slot]; }
     __device__ __forceinline__ static int soc_dim(const F3Plan& P, int slot) { return P.soc_dim[slot]; }
+    __device__ __forceinline__ static const F3Offs& offs(const F3Plan& P) { return P; }
+    __device__ __forceinline__ static int nsing(const F3Plan& P) { return P.nsing; }
 };
 // N variables, PE equality rows, one POC block of KPOC rows then NSOC cones of dimension SDIM; dense rows [D0, D0+KD),
 // identity singleton block (IDENT) or the generic tables
@@ -225,9 +245,12 @@ struct Dims3Static {
     __device__ __forceinline__ static constexpr int split_p(const F3Plan&) { return f2_split(PE > 0 ? PE : 1, NW); }
     __device__ __forceinline__ static constexpr int soc_offs(const F3Plan&, int slot) { return KPOC + slot * SDIM; }
     __device__ __forceinline__ static constexpr int soc_dim(const F3Plan&, int) { return SDIM; }
+    static constexpr int NSING = IDENT ? N : 0;          // static layouts: identity singleton block or none
+    __device__ __forceinline__ static constexpr F3Offs offs(const F3Plan&) { return f3_offsets(N, PE, K, KPOC, NSOC, KD, NSING, NW); }
+    __device__ __forceinline__ static constexpr int nsing(const F3Plan&) { return NSING; }
     static bool matches(const F3Plan& P) {
         if (P.n != N || P.p != PE || P.kpoc != KPOC || P.nsoc != NSOC || P.k != K || P.nw != NW) return false;
-        if (P.d0 != D0 || P.kd != KD || P.ident != IDENT) return false;
+        if (P.d0 != D0 || P.kd != KD || P.ident != IDENT || P.nsing != NSING) return false;
         for (int i = 0; i < NSOC; ++i)
             if (P.soc_dim[i] != SDIM || P.soc_offs[i] != KPOC + i * SDIM) return false;
         return true;
@@ -347,7 +370,8 @@ __device__ __forceinline__ int f3_diag_factor(const double* T, int lane, double 
 // clears both.
 template <int NW>
 __device__ __forceinline__ int f3_chol_inv(double* Tt, double* Lp, const unsigned short* tij, int nbl, int* fail,
-                                           int lane, int warp, const T3Lane& TL, unsigned long long* clk = nullptr) {
+                                           int lane, int warp, const T3Lane& TL, unsigned long long* clk = nullptr,
+                                           int bar = 0, int bar2 = 1) {
     const int ntl = nbl * (nbl + 1) / 2;
 #ifdef SOCP_PHASE_TIMING
     const bool pt_on = clk && threadIdx.x == 0 && blockIdx.x == 0;
@@ -373,7 +397,7 @@ __device__ __forceinline__ int f3_chol_inv(double* Tt, double* Lp, const unsigne
 #ifdef SOCP_PHASE_TIMING
         if (pt_on) { const long long t = clock64(); atomicAdd(&clk[13], (unsigned long long)(t - pt_c)); pt_c = t; }
 #endif
-        tsync<NW>();                                   // (1) X_bb visible; trailing update of step b-1 complete
+        tsync_t<NW>(bar);                                   // (1) X_bb visible; trailing update of step b-1 complete
 #ifdef SOCP_PHASE_TIMING
         if (pt_on) { const long long t = clock64(); atomicAdd(&clk[15], (unsigned long long)(t - pt_c)); pt_c = t; }
 #endif
@@ -402,8 +426,8 @@ __device__ __forceinline__ int f3_chol_inv(double* Tt, double* Lp, const unsigne
         }
         // (2) panel visible.  Warp 0 needs only the panel tile it wrote itself (row b+1), so it merely arrives.
         if (NW > 1) {
-            if (warp == 0) { named_bar_arrive<1, NW * 32>(); __syncwarp(); }
-            else named_bar_sync<1, NW * 32>();
+            if (warp == 0) { bar_arrive_id<NW * 32>(bar2); __syncwarp(); }
+            else bar_sync_id<NW * 32>(bar2);
         } else __syncwarp();
         // ---- trailing update
         if (b + 1 < nbl) {
@@ -459,14 +483,15 @@ __device__ __forceinline__ int f3_chol_inv(double* Tt, double* Lp, const unsigne
             }
         }
     }
-    tsync<NW>();
+    tsync_t<NW>(bar);
     return 1;
 }
 
 // Tt <- X'X in place (X = L^-1 as left by f3_chol_inv): H^-1 = L^-T L^-1, the reference's Li (src/densesolver.jl:48).
 // Out(i,j) = sum_{m >= i} X(m,i)' X(m,j).  Every warp keeps its tiles in registers until all reads are done.
 template <int NW, int MAXT>
-__device__ __forceinline__ void f3_xtx(double* Tt, int nb, const int (&tl)[MAXT], int lane, int warp, const T3Lane& TL) {
+__device__ __forceinline__ void f3_xtx(double* Tt, int nb, const int (&tl)[MAXT], int lane, int warp, const T3Lane& TL,
+                                       int bar = 0) {
     const int ntl = nb * (nb + 1) / 2;
     double acc[MAXT][2];
 #pragma unroll
@@ -482,7 +507,7 @@ __device__ __forceinline__ void f3_xtx(double* Tt, int nb, const int (&tl)[MAXT]
             }
         }
     }
-    tsync<NW>();
+    tsync_t<NW>(bar);
 #pragma unroll
     for (int q = 0; q < MAXT; ++q) {
         if (warp + q * NW < ntl) {
@@ -523,7 +548,7 @@ __device__ __forceinline__ void f3_symv(const double* Tt, int nb, const double* 
 #define PT3_INIT() pt_t0 = clock64()
 #define PT3_MARK(idx)                                                             \
     do {                                                                          \
-        if (tid == 0 && blockIdx.x == 0) {                                        \
+        if (tid_all == 0 && blockIdx.x == 0) {                                    \
             const long long t_ = clock64();                                       \
             atomicAdd(&a.P.d_clk[idx], (unsigned long long)(t_ - pt_t0));      \
             pt_t0 = t_;                                                           \
@@ -538,18 +563,33 @@ enum { P3_LOAD = 0, P3_RESID, P3_HEAD_GT, P3_SYRK, P3_XTX, P3_EQ, P3_SOLVE, P3_I
        P3_CHOL, P3_SOLVE_A, P3_SOLVE_B, P3_N0 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int NW, int MAXT, int MINB, class D>
-__global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
+// TEAMS teams of NW warps per CTA, every team on its own problem with its own slice of the dynamic shared memory and
+// its own pair of hardware barriers (one 512-thread CTA per SM instead of four 128-thread CTAs: the kernel then knows
+// which SM sub-partition each of its warps issues from, see the warp rotation below).  a.align (experiments): the
+// teams re-align at the top of every Mehrotra iteration with two CTA-wide barriers.
+template <int NW, int TEAMS, int MAXT, int MINB, class D>
+__global__ void __launch_bounds__(NW * 32 * TEAMS, MINB) k_fused3(const F3Args a) {
 #ifdef SOCP_SIMT_EMU
-    double* sm = reinterpret_cast<double*>(emu_dyn_smem());
-    const int tid = (int)(unsigned)threadIdx.x;
+    double* sm_all = reinterpret_cast<double*>(emu_dyn_smem());
+    const int tid_all = (int)(unsigned)threadIdx.x;
 #else
-    extern __shared__ __align__(16) double sm[];
-    int tid;
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    extern __shared__ __align__(16) double sm_all[];
+    int tid_all;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_all));
 #endif
-    __shared__ int s_prob, s_fail[2], s_bad;
+    __shared__ int s_prob_[TEAMS], s_fail_[TEAMS][2], s_bad_[TEAMS], s_live;
+    const int team = (TEAMS > 1) ? tid_all / (NW * 32) : 0;
+    // warp w of the CTA issues from SM sub-partition w % 4.  The serial stretches of the solve (diagonal-tile factor,
+    // cone chains of a single cone) run on the team's warp 0: rotate the warp numbering by the team index so that the
+    // four teams' chain warps sit on four different sub-partitions.
+    const int tid = (TEAMS > 1) ? ((tid_all + team * 32) & (NW * 32 - 1)) : tid_all;
+    int& s_prob = s_prob_[team];
+    int* const s_fail = s_fail_[team];
+    int& s_bad = s_bad_[team];
+    const int bar = 1 + team, bar2 = 1 + TEAMS + team;       // hardware barriers of this team (0 is the CTA's)
+    double* sm = sm_all + (size_t)team * D::offs(a.P).total;
     const F3Plan& P = a.P;
+    const F3Offs O = D::offs(P);
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int T = NW * 32;
     const int n = D::n(P), p = D::p(P), k = D::k(P), kpoc = D::kpoc(P), nsoc = D::nsoc(P), lpc = D::lpc(P);
@@ -559,49 +599,49 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
     const bool ident = D::ident(P) != 0;
     const int ppad = (max(p, 1) + 7) / 8 * 8, pb = ppad / 8;
     const T3Lane TL = t3_lane(lane);
-    double* G = sm + P.oG;           // dense rows [d0, d0 + kd) of G: kdpad x n, ld ldg
-    double* Tt = sm + P.oT;          // G'W^-2 G, then L^-1, then H^-1
-    double* Lp = sm + P.oLp;
-    double* A = sm + P.oA;
-    double* At = sm + P.oAt;         // A' (rows of A contiguous, stride npad)
-    double* HiAt = sm + P.oHiAt;     // H^-1 A'         (p x npad)
-    double* Km = sm + P.oK;          // H^-1 A' M^-1    (p x npad)
-    double* Mt = sm + P.oMt;
-    double* MLp = sm + P.oMLp;
-    double* Minv = sm + P.oMinv;
-    double* cv = sm + P.oc;
-    double* bv = sm + P.ob;
-    double* x = sm + P.ox; double* y = sm + P.oy;
-    double* dx = sm + P.odx; double* dy = sm + P.ody;
-    double* n0 = sm + P.on0; double* cx = sm + P.ocx; double* cy = sm + P.ocy;
-    double* kd_ = sm + P.okd;        // K dy (+ H^-1 A' dy for sing problems inside the loop)   (n)
-    double* md = sm + P.omd;         // M^-1 dy         (p)
-    double* sd = sm + P.osd;         // singleton rows' share of diag(G'W^-2 G)                 (n)
-    double* atdy = sm + P.oatdy;     // A'dy            (n)
-    double* hc = sm + P.ohc;         // sqrt(2)/eta G_c'q per cone (nsoc x npad)
+    double* G = sm + O.oG;           // dense rows [d0, d0 + kd) of G: kdpad x n, ld ldg
+    double* Tt = sm + O.oT;          // G'W^-2 G, then L^-1, then H^-1
+    double* Lp = sm + O.oLp;
+    double* A = sm + O.oA;
+    double* At = sm + O.oAt;         // A' (rows of A contiguous, stride npad)
+    double* HiAt = sm + O.oHiAt;     // H^-1 A'         (p x npad)
+    double* Km = sm + O.oK;          // H^-1 A' M^-1    (p x npad)
+    double* Mt = sm + O.oMt;
+    double* MLp = sm + O.oMLp;
+    double* Minv = sm + O.oMinv;
+    double* cv = sm + O.oc;
+    double* bv = sm + O.ob;
+    double* x = sm + O.ox; double* y = sm + O.oy;
+    double* dx = sm + O.odx; double* dy = sm + O.ody;
+    double* n0 = sm + O.on0; double* cx = sm + O.ocx; double* cy = sm + O.ocy;
+    double* kd_ = sm + O.okd;        // K dy (+ H^-1 A' dy for sing problems inside the loop)   (n)
+    double* md = sm + O.omd;         // M^-1 dy         (p)
+    double* sd = sm + O.osd;         // singleton rows' share of diag(G'W^-2 G)                 (n)
+    double* atdy = sm + O.oatdy;     // A'dy            (n)
+    double* hc = sm + O.ohc;         // sqrt(2)/eta G_c'q per cone (nsoc x npad)
     // k-vectors start at an odd offset when d0 is odd, so that their dense-row part is 16-byte aligned
-    double* hv = sm + P.oh + ksh; double* z = sm + P.oz + ksh; double* s = sm + P.os + ksh;
-    double* lam = sm + P.olam + ksh; double* wb = sm + P.owb + ksh; double* iwb = sm + P.oiwb;
-    double* dz = sm + P.odz + ksh; double* ds = sm + P.ods + ksh;
-    double* k0 = sm + P.ok0 + ksh; double* k2 = sm + P.ok2 + ksh; double* u = sm + P.ou + ksh;
-    double* dw = sm + P.odw + ksh;   // row weights of the SYRK
-    double* sval = sm + P.osval + ksh;   // value of the only nonzero of a singleton row (0 elsewhere)
-    double* cs = sm + P.ocs;
-    double* scr = sm + P.oscr;
-    const int* srow_col = reinterpret_cast<const int*>(sm + P.otab);
+    double* hv = sm + O.oh + ksh; double* z = sm + O.oz + ksh; double* s = sm + O.os + ksh;
+    double* lam = sm + O.olam + ksh; double* wb = sm + O.owb + ksh; double* iwb = sm + O.oiwb;
+    double* dz = sm + O.odz + ksh; double* ds = sm + O.ods + ksh;
+    double* k0 = sm + O.ok0 + ksh; double* k2 = sm + O.ok2 + ksh; double* u = sm + O.ou + ksh;
+    double* dw = sm + O.odw + ksh;   // row weights of the SYRK
+    double* sval = sm + O.osval + ksh;   // value of the only nonzero of a singleton row (0 elsewhere)
+    double* cs = sm + O.ocs;
+    double* scr = sm + O.oscr;
+    const int* srow_col = reinterpret_cast<const int*>(sm + O.otab);
     const int* scol_ptr = srow_col + k;
     const int* scol_rows = scol_ptr + n + 1;
-    unsigned short* tij = reinterpret_cast<unsigned short*>(sm + P.otij);
-    unsigned short* tijm = reinterpret_cast<unsigned short*>(sm + P.otijm);
+    unsigned short* tij = reinterpret_cast<unsigned short*>(sm + O.otij);
+    unsigned short* tijm = reinterpret_cast<unsigned short*>(sm + O.otijm);
     int scr_par = 0;
     const LoopParams prm = a.prm;
     PT3_DECL();
 
-    for (int q = tid; q < P.total; q += T) sm[q] = 0.0;
-    tsync<NW>();
+    for (int q = tid; q < O.total; q += T) sm[q] = 0.0;
+    tsync_t<NW>(bar);
     {
-        int* tab = reinterpret_cast<int*>(sm + P.otab);
-        const int ntab = k + n + 1 + P.nsing;
+        int* tab = reinterpret_cast<int*>(sm + O.otab);
+        const int ntab = k + n + 1 + D::nsing(P);
         for (int q = tid; q < ntab; q += T) tab[q] = a.P.d_tables[q];
         for (int t = tid; t < ntl; t += T) {
             int i = 0;
@@ -617,7 +657,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
     }
     int tl[MAXT];
     f3_my_tiles<NW, MAXT>(nb, warp, tl);
-    tsync<NW>();
+    if (TEAMS > 1) {
+        if (tid_all == 0) s_live = TEAMS;
+        __syncthreads();
+    }
+    tsync_t<NW>(bar);
 
     // contribution of the singleton rows to column c of G'v
     auto sing_col = [&](int c, const double* v) -> double {
@@ -807,12 +851,34 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
         }
     };
 
+    // work distribution: the first problem of a team is fixed (a small batch spreads over the SMs one problem per CTA
+    // before any CTA gets a second one), further ones come from the shard's atomic counter
+    bool first_round = true;
     for (;;) {
-        if (tid == 0) s_prob = atomicAdd(a.counter, 1);
-        tsync<NW>();
-        const int b = s_prob + a.first;
-        tsync<NW>();
-        if (b >= a.first + a.batch) break;
+        int b;
+        if (first_round) {
+            b = a.first + (int)blockIdx.x + team * (int)gridDim.x;
+            first_round = false;
+        } else {
+            if (tid == 0) s_prob = atomicAdd(a.counter, 1) + (int)gridDim.x * TEAMS;
+            tsync_t<NW>(bar);
+            b = s_prob + a.first;
+            tsync_t<NW>(bar);
+        }
+        if (b >= a.first + a.batch) {
+            if (TEAMS > 1 && a.align) {
+                // out of work: keep the CTA-wide alignment barriers of the other teams company until every team is
+                // here.  Pairs of barriers: s_live changes only between pairs and is read only inside one.
+                if (tid == 0) atomicAdd(&s_live, -1);
+                for (;;) {
+                    __syncthreads();
+                    const int live = *(volatile int*)&s_live;
+                    __syncthreads();
+                    if (live == 0) break;
+                }
+            }
+            break;
+        }
         PT3_INIT();
 
         // ---- load the problem (global -> shared)
@@ -840,20 +906,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
         int sing = (a.g.sing && !a.sing_detect) ? (a.g.sing[b] != 0) : 0;
         if (a.verify) {
             if (tid == 0) s_bad = 0;
-            tsync<NW>();
+            tsync_t<NW>(bar);
             if (bad) s_bad = 1;
-            tsync<NW>();
+            tsync_t<NW>(bar);
             if (s_bad) {
                 if (tid == 0) {
                     a.g.status[b] = ST_PATTERN;
                     a.g.iters[b] = 0;
                     if (a.g.npattern) atomicAdd(a.g.npattern, 1);
                 }
-                tsync<NW>();
+                tsync_t<NW>(bar);
                 continue;
             }
         }
-        tsync<NW>();
+        tsync_t<NW>(bar);
 
         // The initial point (src/solver.jl:68-104, W = I) is the same factor + solve as a loop iteration with
         // u = h, dx = -c, dy = b, k2 = h: then cx = x, cy = y and u = G x - h = z0.
@@ -870,7 +936,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
             sd[i] = sdv;
         }
         for (int i = tid; i < p; i += T) dy[i] = bv[i];
-        tsync<NW>();
+        tsync_t<NW>(bar);
         PT3_MARK(P3_LOAD);
 
         int phase = 0;              // 0: initial point, 1: affine direction (solve #1), 2: combined direction (solve #2)
@@ -888,29 +954,29 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                 // ---- KKT factor, src/densesolver.jl:41-52
                 f3_syrk<NW, MAXT>(G, ldg, kdpad, n, nb, dw + d0, hc, nsoc, npad, sd, A, p, sing != 0, Tt, tl, lane, warp, TL);   // :42-46
                 if (tid == 0) s_fail[0] = s_fail[1] = 0;
-                tsync<NW>();
+                tsync_t<NW>(bar);
                 if (a.g.dbg && b == a.g.dbg_prob && phase == 1 && iters == a.g.dbg_iter) {
                     double* o = a.g.dbg + 2 * k;
                     for (int q = tid; q < n * n; q += T) o[q] = t3_sym(Tt, q % n, q / n);
-                    tsync<NW>();
+                    tsync_t<NW>(bar);
                 }
                 PT3_MARK(P3_SYRK);
-                int ok = f3_chol_inv<NW>(Tt, Lp, tij, nb, s_fail, lane, warp, TL, a.P.d_clk);          // :47
+                int ok = f3_chol_inv<NW>(Tt, Lp, tij, nb, s_fail, lane, warp, TL, a.P.d_clk, bar, bar2);          // :47
                 PT3_MARK(P3_CHOL);
                 if (!ok && phase == 0 && a.sing_detect && !sing && p > 0) {
                     // cholesky(G'G) threw: the reference's `sing` (src/Socp.jl:49-56).  Repeat the initial point with A'A.
-                    tsync<NW>();
+                    tsync_t<NW>(bar);
                     sing = 1;
                     if (tid == 0 && a.g.sing_out) a.g.sing_out[b] = 1;
                     continue;
                 }
-                if (ok) f3_xtx<NW, MAXT>(Tt, nb, tl, lane, warp, TL);                        // :48  Li = H^-1 (explicit)
-                tsync<NW>();
+                if (ok) f3_xtx<NW, MAXT>(Tt, nb, tl, lane, warp, TL, bar);                        // :48  Li = H^-1 (explicit)
+                tsync_t<NW>(bar);
                 PT3_MARK(P3_XTX);
                 if (ok && p > 0) {
                     for (int q = 0; q < p; ++q)          // HiAt = H^-1 A'                           :49
                         f3_symv<NW>(Tt, nb, At + q * npad, lane, warp, TL, [&](int r, double acc) { HiAt[q * npad + r] = acc; });
-                    tsync<NW>();
+                    tsync_t<NW>(bar);
                     if (p == 1) {
                         // one equality row (the budget row of C2): M is a scalar
                         if (warp == 0) {
@@ -922,7 +988,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                                 Minv[0] = 1.0 / acc;
                             }
                         }
-                        tsync<NW>();
+                        tsync_t<NW>(bar);
                         ok = !s_fail[0];
                     } else if (p <= 8) {
                         // warp 0 alone forms M = A HiAt (:50), factors it (:51) and inverts it (8 x 12 scratch in Lp)
@@ -955,12 +1021,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                                 Minv[j * p + i] = acc;
                             }
                         }
-                        tsync<NW>();
+                        tsync_t<NW>(bar);
                         ok = !s_fail[0];
                     } else {
                         // M = A HiAt into packed tiles (unit pad diagonal), blocked factor + inverse, Minv = X'X
                         for (int e = tid; e < pb * (pb + 1) / 2 * 64; e += T) Mt[e] = 0.0;
-                        tsync<NW>();
+                        tsync_t<NW>(bar);
                         for (int e = tid; e < ppad * ppad; e += T) {
                             const int i = e % ppad, j = e / ppad;
                             if (i < j) continue;
@@ -970,8 +1036,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                             Mt[t3_idx(i >> 3, j >> 3) * 64 + t3_off(i & 7, j & 7)] = acc;
                             if ((i >> 3) == (j >> 3)) Mt[t3_idx(i >> 3, j >> 3) * 64 + t3_off(j & 7, i & 7)] = acc;
                         }
-                        tsync<NW>();
-                        ok = f3_chol_inv<NW>(Mt, MLp, tijm, pb, s_fail, lane, warp, TL);        // :51
+                        tsync_t<NW>(bar);
+                        ok = f3_chol_inv<NW>(Mt, MLp, tijm, pb, s_fail, lane, warp, TL, nullptr, bar, bar2);        // :51
                         if (ok) {
                             for (int q = tid; q < p * p; q += T) {          // Minv = X'X, X lower triangular in packed tiles
                                 const int i = q % p, j = q / p;
@@ -981,7 +1047,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                                               Mt[t3_idx(m >> 3, j >> 3) * 64 + t3_off(m & 7, j & 7)], acc);
                                 Minv[j * p + i] = acc;
                             }
-                            tsync<NW>();
+                            tsync_t<NW>(bar);
                         }
                     }
                     if (ok) {
@@ -1013,7 +1079,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                 if (!ok) { status = ST_NUMERICAL; break; }                                   // cholesky! threw
             }
             // ---- middle of solve_kkt, src/densesolver.jl:66-85: out cx, cy, u = G cx - k2
-            tsync<NW>();
+            tsync_t<NW>(bar);
             if (a.g.dbg && b == a.g.dbg_prob && phase == a.g.dbg_phase && iters == a.g.dbg_iter) {
                 double* o = a.g.dbg + 2 * k + n * n;
                 for (int i = tid; i < n; i += T) o[i] = sc * dx[i];
@@ -1057,14 +1123,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                     acc = warp_sum(acc);
                     if (lane == 0) cy[q] = acc - sc * md[q];
                 }
-                tsync<NW>();
+                tsync_t<NW>(bar);
                 for (int r = tid; r < n; r += T) {                // cx = H^-1 n0 - HiAt cy
                     double acc = cx[r];
                     for (int q = 0; q < p; ++q) acc = fma(-HiAt[q * npad + r], cy[q], acc);
                     cx[r] = acc;
                 }
             }
-            tsync<NW>();
+            tsync_t<NW>(bar);
             PT3_MARK(P3_SOLVE_A);
             const double* cxv = cx;
             gemv_rows_v<NW>(G, ldg, kd, n, cxv, D::split_kd(P), lane, warp, [&](int r, double acc) { u[d0 + r] = acc - k2[d0 + r]; });   // :84-85
@@ -1072,7 +1138,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                 const int r = i < d0 ? i : i + kd;
                 u[r] = sing_row(r, cxv) - k2[r];
             }
-            tsync<NW>();
+            tsync_t<NW>(bar);
             PT3_MARK(P3_SOLVE);
 
             bool new_iter;
@@ -1095,7 +1161,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                         r2[1] = fmax(r2[1], nr - z0);
                     }
                 });
-                team_reduce<NW, 0, 2>(r2, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp);
+                team_reduce<NW, 0, 2>(r2, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp, bar);
                 const double mp = r2[0], mdl = r2[1];
                 const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(mdl) < prm.init_eps);
                 for (int i = tid; i < k; i += T) {
@@ -1103,7 +1169,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                     s[i] = -z0;
                     z[i] = z0;
                 }
-                tsync<NW>();
+                tsync_t<NW>(bar);
                 for (int i = tid; i < kpoc; i += T) {
                     if (shp) s[i] += 1.0 + mp;
                     if (shd) z[i] += 1.0 + mdl;
@@ -1113,7 +1179,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                     if (shp) s[o] += 1.0 + mp;
                     if (shd) z[o] += 1.0 + mdl;
                 }
-                tsync<NW>();
+                tsync_t<NW>(bar);
                 PT3_MARK(P3_INIT);
                 new_iter = true;
             } else {
@@ -1140,7 +1206,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                     for (int i = tid; i < kpoc; i += T) fl |= !isfinite(u[i]) | !isfinite(k0[i]);
                 }
                 PT3_MARK(P3_TAIL);
-                team_reduce<NW, 1, 1>(r2, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp);
+                team_reduce<NW, 1, 1>(r2, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp, bar);
                 if (NW == 1) __syncwarp();
                 if (a.g.dbg && b == a.g.dbg_prob && phase == a.g.dbg_phase && iters == a.g.dbg_iter) {
                     double* o = a.g.dbg + 2 * k + n * n + n + p + 2 * k;
@@ -1177,7 +1243,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                         s[i] = fma(k0[i], step, s[i]);                                   // :150
                     }
                     ++iters;
-                    tsync<NW>();
+                    tsync_t<NW>(bar);
                     new_iter = true;
                 }
                 PT3_MARK(P3_MIDPOST);
@@ -1186,6 +1252,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
             if (new_iter) {
                 // ---- top of a Mehrotra iteration, src/solver.jl:105-126
                 if (iters >= prm.max_iter) break;
+                if (TEAMS > 1 && a.align) { __syncthreads(); __syncthreads(); }      // re-align the teams of this CTA
                 if (a.g.dbg && b == a.g.dbg_prob && iters == a.g.dbg_iter)
                     for (int i = tid; i < k; i += T) { a.g.dbg[i] = s[i]; a.g.dbg[k + i] = z[i]; }
                 // compute_scaling (:106) and the negated residuals (:110-118,:125) in one phase
@@ -1223,7 +1290,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                         dy[r] = v;
                         r4[1] = fma(v, v, r4[1]);
                     });
-                team_reduce<NW, 4, 0>(r4, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp);
+                team_reduce<NW, 4, 0>(r4, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp, bar);
                 if (NW == 1) __syncwarp();
                 PT3_MARK(P3_RESID);
                 if (fl) { status = ST_NUMERICAL; break; }                              // compute_scaling threw
@@ -1283,11 +1350,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                 const double kz = sc * dz[i] - w * kk;
                 k0[i] = kk; k2[i] = kz; u[i] = iw * iw * kz;
             }
-            tsync<NW>();
+            tsync_t<NW>(bar);
             PT3_MARK(P3_HEAD_GT);
         }
         if (status == ST_RUNNING) status = ST_MAXITER;
-        tsync<NW>();
+        tsync_t<NW>(bar);
 
         // ---- results: iterate and objectives (pobj = c'x, dobj = -b'y - h'z)
         {
@@ -1310,7 +1377,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                 a.g.s[(int64_t)b * k + i] = dead ? 0.0 : s[i];
                 r2[1] = fma(-hv[i], zi, r2[1]);
             }
-            team_reduce<NW, 2, 0>(r2, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp);
+            team_reduce<NW, 2, 0>(r2, fl, scr + (scr_par ^= 1) * 8 * NW, lane, warp, bar);
             if (tid == 0) {
                 a.g.pobj[b] = r2[0];
                 a.g.dobj[b] = r2[1];
@@ -1320,7 +1387,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
                 a.g.fail[b] = (status == ST_NUMERICAL);
             }
         }
-        tsync<NW>();
+        tsync_t<NW>(bar);
         PT3_MARK(P3_OUT);
     }
 }
@@ -1330,14 +1397,18 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused3(const F3Args a) {
 using Dims3C2 = Dims3Static<4, 50, 1, 50, 1, 51, 51, 50, 1>;
 
 #ifndef SOCP_SIMT_EMU
-template <int NW, int MAXT, int MINB, class D>
+template <int NW, int TEAMS, int MAXT, int MINB, class D>
 inline void fused3_launch(const F3Plan& plan, const F3Args& args, int grid, cudaStream_t stream) {
-    cudaFuncSetAttribute(k_fused3<NW, MAXT, MINB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    k_fused3<NW, MAXT, MINB, D><<<grid, NW * 32, plan.smem, stream>>>(args);
+    const size_t smem = plan.smem * TEAMS;
+    cudaFuncSetAttribute(k_fused3<NW, TEAMS, MAXT, MINB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fused3<NW, TEAMS, MAXT, MINB, D><<<grid, NW * 32 * TEAMS, smem, stream>>>(args);
 }
+void fused3_launch_c2(const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream);    // fused3.cu
+void fused3_launch_dyn(const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream);   // fused3_dyn.cu
 
 // Solves problems [first, first + batch) of the shard.  counter_slot: which of the plan's work counters this launch
-// uses (launches that may overlap need different ones).
+// uses (launches that may overlap need different ones).  Batches that give every SM several problems run with four
+// teams per CTA (one CTA per SM, teams aligned per iteration); smaller ones with one team per CTA, spread over the SMs.
 inline void solve_fused3(const F3Plan& plan, const F3Glob& g, int first, int batch, const LoopParams& prm, int sing_detect,
                          int verify, cudaStream_t stream, bool allow_static = true, int counter_slot = 0) {
     cudaMemsetAsync(plan.d_counter + counter_slot, 0, sizeof(int), stream);
@@ -1350,11 +1421,16 @@ inline void solve_fused3(const F3Plan& plan, const F3Glob& g, int first, int bat
     args.counter = plan.d_counter + counter_slot;
     args.sing_detect = sing_detect;
     args.verify = verify;
-    const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
-    if (allow_static && Dims3C2::matches(plan)) { fused3_launch<4, 7, 4, Dims3C2>(plan, args, grid, stream); return; }
-    if (plan.nb <= 4) fused3_launch<4, 3, 4, Dims3Dyn>(plan, args, grid, stream);          // n <= 32: 10 tiles
-    else if (plan.nb <= 7) fused3_launch<4, 7, 4, Dims3Dyn>(plan, args, grid, stream);     // n <= 56: 28 tiles
-    else fused3_launch<4, 9, 3, Dims3Dyn>(plan, args, grid, stream);                       // n <= 64: 36 tiles
+    // experiment switch (default off): with the chain warps spread over the sub-partitions, re-aligning the teams every
+    // iteration costs 2 % (1.107M against 1.126M problems/s on C2); before that spread it gained 16 %
+    { const char* e = getenv("SOCP_B200_F3_ALIGN"); args.align = e ? atoi(e) : 0; }
+    // four teams per CTA whenever they fit: one kernel per layout whatever the batch size, so that the results do not
+    // depend on how a batch is cut into shards or chunks
+    const char* e4 = getenv("SOCP_B200_F3_TEAMS");          // experiments only
+    const int teams = (plan.teams4 && !(e4 && atoi(e4) == 1)) ? 4 : 1;
+    const int grid = teams > 1 ? std::min(batch, plan.num_sms) : std::min(batch, plan.num_sms * plan.ctas_per_sm);
+    if (allow_static && Dims3C2::matches(plan)) fused3_launch_c2(plan, args, teams, grid, stream);
+    else fused3_launch_dyn(plan, args, teams, grid, stream);
 }
 // non-inline entry of solve_fused3, compiled once in fused3.cu (the kernels are instantiated there only)
 void solve_fused3_ext(const F3Plan& plan, const F3Glob& g, int first, int batch, const LoopParams& prm, int sing_detect,

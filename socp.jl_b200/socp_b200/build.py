@@ -19,6 +19,7 @@ UNITS = {
     "solver.cu": None,                                                 # everything
     "fused2.cu": ["common.cuh", "fused_common.cuh", "fused_v2.cuh"],
     "fused3.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
+    "fused3_dyn.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
 }
 
 

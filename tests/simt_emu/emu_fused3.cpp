@@ -35,7 +35,8 @@ extern "C" int emu_fused3_plan(int n, int p, int k, int ncones, const int* kind,
     return 0;
 }
 
-// flags: bit 0 = generic kernel only, bit 1 = sing_detect, bit 2 = verify; rowcol_in may be null (detected from G).
+// flags: bit 0 = generic kernel only, bit 1 = sing_detect, bit 2 = verify, bit 3 = four teams per CTA; rowcol_in may be
+// null (detected from G).
 // order: fibre schedule of the emulator (0 forward, 1 reverse, 2 random).  Returns 0, or -1 when the plan does not fit.
 extern "C" int emu_fused3_solve(int n, int p, int k, int ncones, const int* kind, const int* offs, const int* dim,
                                 int batch, const double* c, const double* A, int64_t sA, const double* b,
@@ -70,16 +71,26 @@ extern "C" int emu_fused3_solve(int n, int p, int k, int ncones, const int* kind
     a.counter = &counter;
     a.sing_detect = (flags >> 1) & 1;
     a.verify = (flags >> 2) & 1;
+    a.align = 1;
     simt_emu::LaunchCfg cfg;
-    cfg.grid = (unsigned)std::max(1, std::min(batch, grid_cap > 0 ? grid_cap : 4));
-    cfg.block = 128;
-    cfg.smem = P.smem;
+    const bool teams4 = (flags >> 3) & 1;
+    if (teams4 && !P.teams4) return -1;
+    cfg.grid = (unsigned)std::max(1, std::min(teams4 ? (batch + 3) / 4 : batch, grid_cap > 0 ? grid_cap : 4));
+    cfg.block = teams4 ? 512 : 128;
+    cfg.smem = P.smem * (teams4 ? 4 : 1);
     cfg.order = order;
     const bool generic = flags & 1;
-    if (!generic && Dims3C2::matches(P)) simt_emu::launch(cfg, [&]() { k_fused3<4, 7, 4, Dims3C2>(a); });
-    else if (P.nb <= 4) simt_emu::launch(cfg, [&]() { k_fused3<4, 3, 4, Dims3Dyn>(a); });
-    else if (P.nb <= 7) simt_emu::launch(cfg, [&]() { k_fused3<4, 7, 4, Dims3Dyn>(a); });
-    else simt_emu::launch(cfg, [&]() { k_fused3<4, 9, 3, Dims3Dyn>(a); });
+    if (teams4) {
+        if (!generic && Dims3C2::matches(P)) simt_emu::launch(cfg, [&]() { k_fused3<4, 4, 7, 1, Dims3C2>(a); });
+        else if (P.nb <= 4) simt_emu::launch(cfg, [&]() { k_fused3<4, 4, 3, 1, Dims3Dyn>(a); });
+        else if (P.nb <= 7) simt_emu::launch(cfg, [&]() { k_fused3<4, 4, 7, 1, Dims3Dyn>(a); });
+        else simt_emu::launch(cfg, [&]() { k_fused3<4, 4, 9, 1, Dims3Dyn>(a); });
+        return 0;
+    }
+    if (!generic && Dims3C2::matches(P)) simt_emu::launch(cfg, [&]() { k_fused3<4, 1, 7, 4, Dims3C2>(a); });
+    else if (P.nb <= 4) simt_emu::launch(cfg, [&]() { k_fused3<4, 1, 3, 4, Dims3Dyn>(a); });
+    else if (P.nb <= 7) simt_emu::launch(cfg, [&]() { k_fused3<4, 1, 7, 4, Dims3Dyn>(a); });
+    else simt_emu::launch(cfg, [&]() { k_fused3<4, 1, 9, 3, Dims3Dyn>(a); });
     return 0;
 }
 

@@ -80,6 +80,34 @@ def test_c2_schedule_independent(order):
         assert np.array_equal(a[f], b[f]), f
 
 
+@pytest.mark.parametrize("generic,B,grid_cap,order", [(False, 7, 1, 0), (True, 6, 2, 2), (False, 3, 1, 1)])
+def test_c2_four_teams_per_cta(generic, B, grid_cap, order):
+    """Four teams (problems) per CTA, re-aligned at the top of every Mehrotra iteration by CTA-wide barriers: bit
+    identical to one team per CTA, whatever the number of problems per team (teams run out of work at different
+    times and keep the alignment barriers company; B = 3 leaves one team without any problem) and the schedule."""
+    prob = gen.make_config("C2", batch=B)
+    a = run(prob, generic=generic)
+    b = run(prob, generic=generic, teams4=True, grid_cap=grid_cap, order=order)
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+        assert np.array_equal(a[f], b[f]), f
+
+
+def test_four_teams_sing_detect_and_pattern():
+    """The rare control paths under four teams per CTA: a team repeating the initial point (sing detected) and a team
+    skipping a problem that violates the row pattern, while the others iterate."""
+    n, p, cones = 20, 2, (sb.POC(0, 6), sb.SOC(6, 9), sb.SOC(15, 5))
+    prob = gen.random_feasible(6, n, p, cones, 0.1)
+    G = prob.G_cm.copy()
+    G[2, 5:, :] = G[2, :15, :]                    # problem 2: G has rank <= 15 < n  -> sing
+    prob2 = sb.BatchProblem(prob.c, prob.A_cm, prob.b, G, prob.h, prob.cones, sing=None, colmajor=True)
+    kw = dict(sing=None, sing_detect=True)
+    a = emu.solve(prob2.c, prob2.A_cm, prob2.b, prob2.G_cm, prob2.h, oc(prob2.cones), **kw)
+    b = emu.solve(prob2.c, prob2.A_cm, prob2.b, prob2.G_cm, prob2.h, oc(prob2.cones), teams4=True, grid_cap=1, order=2, **kw)
+    assert a["sing"][2] == 1
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj", "sing"):
+        assert np.array_equal(a[f], b[f]), f
+
+
 LAYOUTS = {
     # name: (n, p, cones): 4-warp teams with 3, 7 and 9 tiles per warp; p = 0, scalar p, p <= 8 (one warp), p > 8 (blocked)
     "mixed_p2": (20, 2, (sb.POC(0, 6), sb.SOC(6, 9), sb.SOC(15, 5))),
