@@ -158,6 +158,18 @@ int  socp_b200_solve_host(socp_handle* h, const socp_params* params,
                           double* x, double* y, double* z, double* s,
                           int32_t* status, int32_t* iters, double* pobj, double* dobj);
 
+/* The one-shot call for callers that hold A and G as the reference does
+ * (SparseMatrixCSC, src/Socp.jl:25,29): Problem(c, A, b, G, h, cones) +
+ * solve_socp(prob, ss) with the arguments of _set_data_csc followed by _solve.
+ * Pipelined like _solve_host; only the stored values cross PCIe, the dense
+ * operands of every chunk are assembled on the device before its solve, and
+ * the compressed-G plan of the fused kernel comes straight from the pattern. */
+int  socp_b200_solve_host_csc(socp_handle* h, const socp_params* params,
+                              const double* c, const socp_csc* A, const double* b, const socp_csc* G,
+                              const double* hvec, const uint8_t* sing, int32_t flags,
+                              double* x, double* y, double* z, double* s,
+                              int32_t* status, int32_t* iters, double* pobj, double* dobj);
+
 /* Same, but results stay on the device (inputs already resident after
  * set_data): the region bench.py times for `value`.  Fetch with _get_results. */
 int  socp_b200_solve_dev(socp_handle* h, const socp_params* params);

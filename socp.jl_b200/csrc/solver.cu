@@ -85,6 +85,10 @@ struct Shard {
     int* h_rowcol = nullptr;     // pinned, k + 1 ints
     bool sing_known = false;     // d_sing holds the flags (given by the caller, tested on the device, or found by the kernel)
     bool prepared = false;       // tiled-path prerequisites done (sing known, any_sing scanned, A'A when needed)
+    // staging of the CSC one-shot solve (socp_b200_solve_host_csc): stored values [batch][nnz] and the linear indices
+    double *d_valG = nullptr, *d_valA = nullptr;
+    int *d_linG = nullptr, *d_linA = nullptr;
+    size_t cap_valG = 0, cap_valA = 0, cap_linG = 0, cap_linA = 0;
 
     template <class T>
     T* alloc(size_t count, bool zero = true) {
@@ -820,13 +824,46 @@ bool can_pipeline(const socp_handle* h, const Shard& sh, const socp_params& prm,
     return true;
 }
 
+// CSC -> dense column-major on the device: dense[b][lin[j]] = val[b][j], lin = col * rows + row (host-validated, no
+// duplicates, so the scatter has no write conflicts).  One thread per (problem, stored entry).
+__global__ void __launch_bounds__(256)
+k_csc_scatter(const int* __restrict__ lin, const double* __restrict__ val, int64_t stride_val, int nnz,
+              double* __restrict__ dense, int64_t stride_dense, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / nnz;
+        const int j = (int)(i - b * nnz);
+        dense[b * stride_dense + lin[j]] = val[b * stride_val + j];
+    }
+}
+
+// A and G of the pipelined one-shot solve in the reference's own storage (SparseMatrixCSC): validated patterns as
+// linear indices into the dense column-major operands, and the row pattern of G for the fused_v3 plan
+struct CscSrc {
+    const socp_csc* A;
+    const socp_csc* G;
+    const std::vector<int>* linA;
+    const std::vector<int>* linG;
+    const std::vector<int>* rowcolG;
+};
+
 // returns false when the pipeline could not be used after all (the first chunk's pattern does not fit the fused
 // kernel): the caller falls back to set_data + solve
 bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const double* c, const double* A, const double* b,
                    const double* G, const double* hvec, const uint8_t* sing, int flags, double* x, double* y, double* z,
-                   double* s, int32_t* status, int32_t* iters, double* pobj, double* dobj) {
+                   double* s, int32_t* status, int32_t* iters, double* pobj, double* dobj, const CscSrc* csc = nullptr) {
     const int n = h->n, p = h->p, k = h->k, B = sh.batch;
     const int64_t f = sh.first;
+    const int64_t nnzG = csc ? csc->G->nnz : 0, nnzA = (csc && p > 0) ? csc->A->nnz : 0;
+    if (csc) {
+        auto grow_d = [&](double*& ptr, size_t& cap, size_t want) { if (want > cap) { ptr = sh.alloc<double>(want, false); cap = want; } };
+        auto grow_i = [&](int*& ptr, size_t& cap, size_t want) { if (want > cap) { ptr = sh.alloc<int>(want, false); cap = want; } };
+        grow_d(sh.d_valG, sh.cap_valG, (size_t)std::max<int64_t>(1, nnzG) * B);
+        grow_i(sh.d_linG, sh.cap_linG, (size_t)std::max<int64_t>(1, nnzG));
+        if (p > 0) {
+            grow_d(sh.d_valA, sh.cap_valA, (size_t)std::max<int64_t>(1, nnzA) * B);
+            grow_i(sh.d_linA, sh.cap_linA, (size_t)std::max<int64_t>(1, nnzA));
+        }
+    }
     if (!sh.up_stream) {
         CK(cudaStreamCreateWithFlags(&sh.up_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&sh.down_stream, cudaStreamNonBlocking));
@@ -874,13 +911,27 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         const int64_t g0 = f + lo;
         up(sh.d_c + (size_t)lo * n, c + g0 * n, sizeof(double) * cb * n);
         up(sh.d_h + (size_t)lo * k, hvec + g0 * k, sizeof(double) * cb * k);
-        if (p > 0) {
-            up(sh.d_b + (size_t)lo * p, b + g0 * p, sizeof(double) * cb * p);
-            if (sh.sharedA) { if (ci == 0) up(sh.d_A, A, sizeof(double) * p * n); }
-            else up(sh.d_A + (size_t)lo * p * n, A + g0 * p * n, sizeof(double) * cb * p * n);
+        if (p > 0) up(sh.d_b + (size_t)lo * p, b + g0 * p, sizeof(double) * cb * p);
+        if (csc) {
+            // only the stored values cross PCIe; the dense operands are assembled on the device (scatter_chunk)
+            if (ci == 0) {
+                up(sh.d_linG, csc->linG->data(), sizeof(int) * nnzG);
+                if (p > 0) up(sh.d_linA, csc->linA->data(), sizeof(int) * nnzA);
+            }
+            if (p > 0) {
+                if (sh.sharedA) { if (ci == 0) up(sh.d_valA, csc->A->nzval, sizeof(double) * nnzA); }
+                else up(sh.d_valA + (size_t)lo * nnzA, csc->A->nzval + g0 * nnzA, sizeof(double) * cb * nnzA);
+            }
+            if (sh.sharedG) { if (ci == 0) up(sh.d_valG, csc->G->nzval, sizeof(double) * nnzG); }
+            else up(sh.d_valG + (size_t)lo * nnzG, csc->G->nzval + g0 * nnzG, sizeof(double) * cb * nnzG);
+        } else {
+            if (p > 0) {
+                if (sh.sharedA) { if (ci == 0) up(sh.d_A, A, sizeof(double) * p * n); }
+                else up(sh.d_A + (size_t)lo * p * n, A + g0 * p * n, sizeof(double) * cb * p * n);
+            }
+            if (sh.sharedG) { if (ci == 0) up(sh.d_G, G, sizeof(double) * k * n); }
+            else up(sh.d_G + (size_t)lo * k * n, G + g0 * (int64_t)k * n, sizeof(double) * cb * k * n);
         }
-        if (sh.sharedG) { if (ci == 0) up(sh.d_G, G, sizeof(double) * k * n); }
-        else up(sh.d_G + (size_t)lo * k * n, G + g0 * (int64_t)k * n, sizeof(double) * cb * k * n);
         if (sing) up(sh.d_sing + lo, sing + g0, cb);
         CK(cudaEventRecord(sh.pipe_ev[2 * ci], sh.up_stream));
     };
@@ -899,8 +950,38 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         const int64_t g0 = f + lo;
         if (ci + 1 < nchunk) upload_chunk(ci + 1);        // the copy engine stays one chunk ahead
         CK(cudaStreamWaitEvent(cs, sh.pipe_ev[2 * ci], 0));
+        if (csc) {
+            // dense column-major operands of this chunk from the stored values (zero fill + scatter, on the chunk's
+            // compute stream: ordered after the upload, before the solve)
+            auto scatter_chunk = [&](double* dense, const double* val, const int* lin, int64_t nnz, int rows, bool shared) {
+                if (shared && ci > 0) return;
+                const int64_t nb = shared ? 1 : cb, off = shared ? 0 : lo;
+                CK(cudaMemsetAsync(dense + (size_t)off * rows * n, 0, sizeof(double) * nb * rows * n, cs));
+                const int64_t total = nb * nnz;
+                if (total == 0) return;
+                const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+                k_csc_scatter<<<grid, 256, 0, cs>>>(lin, val + (size_t)off * nnz, nnz, (int)nnz, dense + (size_t)off * rows * n,
+                                                    (int64_t)rows * n, total);
+                CK(cudaPeekAtLastError());
+                sh.launches += 1;
+            };
+            if (p > 0) scatter_chunk(sh.d_A, sh.d_valA, sh.d_linA, nnzA, p, sh.sharedA);
+            scatter_chunk(sh.d_G, sh.d_valG, sh.d_linG, nnzG, k, sh.sharedG);
+            if (nchunk > 1 && (sh.sharedA || sh.sharedG) && ci == 0) {
+                // later chunks run on the other stream as well: they must see the shared operand
+                CK(cudaEventRecord(sh.ev[2], cs));
+                CK(cudaStreamWaitEvent(sh.alt_stream, sh.ev[2], 0));
+            }
+        }
         if (v3) {
-            if (ci == 0) {
+            if (ci == 0 && csc) {
+                plan_fused3(h, sh, *csc->rowcolG, cs);          // the pattern is the CSC pattern: nothing to detect or verify
+                if (!sh.fused3.fits) {
+                    CK(cudaStreamSynchronize(sh.up_stream));
+                    CK(cudaStreamSynchronize(cs));
+                    return false;
+                }
+            } else if (ci == 0) {
                 // the row pattern of G is taken from the first chunk (one small kernel and a host round trip while the
                 // second chunk uploads); the later chunks are verified against it by the solve kernel itself
                 detect_and_plan_fused3(h, sh, 0, cb, cs);
@@ -909,7 +990,7 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
                     return false;
                 }
             }
-            solve_fused3_ext(sh.fused3, f3_glob(sh), lo, cb, lp, sing ? 0 : 1, ci > 0 && !sh.sharedG ? 1 : 0, cs, allow_static, ci & 15);
+            solve_fused3_ext(sh.fused3, f3_glob(sh), lo, cb, lp, sing ? 0 : 1, ci > 0 && !sh.sharedG && !csc ? 1 : 0, cs, allow_static, ci & 15);
         } else {
             solve_fused2_ext(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, cs, allow_static, ci & 15);
         }
@@ -978,18 +1059,6 @@ void finish_set_data(const socp_handle* h, Shard& sh, const uint8_t* sing, const
     if (f3_candidate(h)) {
         if (rowcol) plan_fused3(h, sh, *rowcol, sh.stream);
         else detect_and_plan_fused3(h, sh, 0, B, sh.stream);
-    }
-}
-
-// CSC -> dense column-major on the device: dense[b][lin[j]] = val[b][j], lin = col * rows + row (host-validated, no
-// duplicates, so the scatter has no write conflicts).  One thread per (problem, stored entry).
-__global__ void __launch_bounds__(256)
-k_csc_scatter(const int* __restrict__ lin, const double* __restrict__ val, int64_t stride_val, int nnz,
-              double* __restrict__ dense, int64_t stride_dense, int64_t total) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = i / nnz;
-        const int j = (int)(i - b * nnz);
-        dense[b * stride_dense + lin[j]] = val[b * stride_val + j];
     }
 }
 
@@ -1282,6 +1351,43 @@ int socp_b200_solve_host(socp_handle* h, const socp_params* params, const double
     });
     if (rc != 0 || pipelined) return rc;
     rc = socp_b200_set_data(h, c, A, b, G, hvec, sing, flags);
+    if (rc != 0) return rc;
+    return socp_b200_solve(h, &prm, x, y, z, s, status, iters, pobj, dobj);
+}
+
+int socp_b200_solve_host_csc(socp_handle* h, const socp_params* params, const double* c, const socp_csc* A,
+                             const double* b, const socp_csc* G, const double* hvec, const uint8_t* sing, int32_t flags,
+                             double* x, double* y, double* z, double* s, int32_t* status, int32_t* iters, double* pobj,
+                             double* dobj) {
+    if (!h) return SOCP_ERR_NULL;
+    socp_params prm;
+    socp_b200_default_params(&prm);
+    if (params) prm = *params;
+    bool pipelined = true;
+    int rc = guarded(h, [&]() {
+        need(c && G && hvec, SOCP_ERR_NULL, "c, G, h must not be null");
+        need(h->p == 0 || (A && b), SOCP_ERR_NULL, "A, b must not be null when p > 0");
+        need(prm.max_iter >= 0 && prm.max_iter <= 4000, SOCP_ERR_SIZE, "max_iter out of range");
+        for (auto& sh : h->shards) pipelined &= can_pipeline(h, sh, prm, sing, sh.first);
+        if (!pipelined) return;
+        const int n = h->n, p = h->p, k = h->k;
+        const std::vector<int> linG = csc_linear_index(*G, k, n, "G");
+        const std::vector<int> linA = p > 0 ? csc_linear_index(*A, p, n, "A") : std::vector<int>();
+        std::vector<int> rowcolG(k, -1);
+        for (int li : linG) {
+            const int i = li % k, j = li / k;
+            rowcolG[i] = rowcolG[i] == -1 ? j : -2;
+        }
+        const CscSrc src{A, G, &linA, &linG, &rowcolG};
+        std::vector<char> okv(h->shards.size(), 1);
+        for_each_shard(h, [&](Shard& sh) {
+            okv[&sh - h->shards.data()] = run_pipelined(h, sh, prm, c, nullptr, b, nullptr, hvec, sing, flags, x, y, z, s,
+                                                        status, iters, pobj, dobj, &src) ? 1 : 0;
+        });
+        for (char v : okv) pipelined &= (v != 0);
+    });
+    if (rc != 0 || pipelined) return rc;
+    rc = socp_b200_set_data_csc(h, c, A, b, G, hvec, sing, flags);
     if (rc != 0) return rc;
     return socp_b200_solve(h, &prm, x, y, z, s, status, iters, pobj, dobj);
 }

@@ -50,6 +50,9 @@ SYMBOLS = {
     "socp_b200_solve_host": (C.c_int, [H, C.POINTER(Params), c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                        c_uint8_p, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p,
                                        c_int32_p, c_int32_p, c_double_p, c_double_p]),
+    "socp_b200_solve_host_csc": (C.c_int, [H, C.POINTER(Params), c_double_p, C.POINTER(Csc), c_double_p, C.POINTER(Csc),
+                                           c_double_p, c_uint8_p, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                           c_double_p, c_int32_p, c_int32_p, c_double_p, c_double_p]),
     "socp_b200_solve_dev": (C.c_int, [H, C.POINTER(Params)]),
     "socp_b200_get_results": (C.c_int, [H, c_double_p, c_double_p, c_double_p, c_double_p,
                                         c_int32_p, c_int32_p, c_double_p, c_double_p]),

@@ -406,9 +406,20 @@ def solve_socp_batch(prob: BatchProblem, ss: BatchSolverState, params: Optional[
     pobj = np.empty(B)
     dobj = np.empty(B)
     prm = params if params is not None else default_params()
-    if prob.G_csc is not None:
-        ss.load(prob, force=reload)              # CSC in: assembled on the device, then the resident-data solve
-    if prob.G_csc is None and (reload or ss._loaded_id != id(prob)):
+    if prob.G_csc is not None and (reload or ss._loaded_id != id(prob)):
+        # the same from the reference's own storage (SparseMatrixCSC): only the stored values cross PCIe
+        assert (prob.n, prob.p, prob.B) == (h.n, h.p, h.batch) and prob.cones == h.cones
+        flags = (1 if prob.shared_A else 0) | (2 if prob.shared_G else 0)
+        sing = None if prob.sing is None else prob.sing.ctypes.data_as(L.c_uint8_p)
+        Gs = prob.G_csc.c_struct()
+        As = prob.A_csc.c_struct() if p else None
+        rc = h.lib.socp_b200_solve_host_csc(h.ptr, C.byref(prm), _dp(prob.c), C.byref(As) if p else None,
+                                            _dp(prob.b) if p else None, C.byref(Gs), _dp(prob.h), sing, flags,
+                                            _dp(x), _dp(y) if p else None, _dp(z), _dp(s),
+                                            _ip(status), _ip(iters), _dp(pobj), _dp(dobj))
+        h.check(rc, "socp_b200_solve_host_csc")
+        ss._loaded_id = id(prob)
+    elif prob.G_csc is None and (reload or ss._loaded_id != id(prob)):
         # Problem(...) + solve_socp(prob, ss) in one call: upload, solve and download overlap on the fused path
         assert (prob.n, prob.p, prob.B) == (h.n, h.p, h.batch) and prob.cones == h.cones
         flags = (1 if prob.shared_A else 0) | (2 if prob.shared_G else 0)

@@ -407,6 +407,31 @@ def test_solve_host_pipelined_matches_two_step():
     assert (one.status == sb.STATUS_CONVERGED).all()
 
 
+@pytest.mark.parametrize("sing_known", [True, False])
+def test_solve_host_csc_pipelined_matches_dense(sing_known):
+    """socp_b200_solve_host_csc -- Problem(...) + solve_socp from the reference's own SparseMatrixCSC storage in one
+    pipelined call (values of every chunk uploaded, scattered into the dense operands on the device, solved, downloaded)
+    -- must return exactly what the dense one-shot call and the two-step CSC path return."""
+    dense = gen.make_config("C2", batch=5000)          # several chunks on a 148-SM part
+    (Gp, Gv), (Ap, Av) = _csc_of(dense)
+    G = sb.CscMatrix(Gp.shape, Gp.indptr + 1, Gp.indices + 1, Gv, index_base=1)      # 1-based, as Julia hands them over
+    A = sb.CscMatrix(Ap.shape, Ap.indptr + 1, Ap.indices + 1, Av, index_base=1)
+    assert G.nnz == 2550
+    sing = dense.sing if sing_known else None
+    sparse = sb.BatchProblem(dense.c, A, dense.b, G, dense.h, dense.cones, sing=sing)
+    dense2 = sb.BatchProblem(dense.c, dense.A_cm, dense.b, dense.G_cm, dense.h, dense.cones, sing=sing, colmajor=True)
+    one = sb.solve_socp_batch(sparse, sb.SolverState(sparse))          # socp_b200_solve_host_csc
+    assert one.timings["path_used"] == sb.PATH_FUSED and one.timings["kernel_launches"] >= 4    # scatters + solves
+    ref = sb.solve_socp_batch(dense2, sb.SolverState(dense2))          # socp_b200_solve_host
+    ss2 = sb.SolverState(sparse)
+    ss2.load(sparse)                                                   # socp_b200_set_data_csc
+    two = sb.solve_socp_batch(sparse, ss2, reload=False)               # socp_b200_solve
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+        assert np.array_equal(getattr(one, f), getattr(ref, f)), f
+        assert np.array_equal(getattr(one, f), getattr(two, f)), f
+    assert (one.status == sb.STATUS_CONVERGED).all()
+
+
 def test_multi_device_handle_matches_single_device():
     """socp_b200_create(devices=[0, 1]) shards the batch contiguously over the devices of one process (no collective);
     results must equal the single-device ones bit for bit (same kernels, same problems).  On a box with one GPU the
