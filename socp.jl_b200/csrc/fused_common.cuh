@@ -120,6 +120,44 @@ __device__ __forceinline__ void gemv_cols_v(const double* __restrict__ M, int ld
         if (rl == 0 && ok) epi(c, acc);
     }
 }
+// The same product with the passes of a warp unrolled (at most MAXPASS passes: cols <= 4 NW MAXPASS): the loads, FMA
+// chains and shuffle rounds of the passes interleave instead of running one pass after the other -- one pass is a
+// dependent chain of ~250 cycles (LDS -> 4 DFMA -> 3 shuffle rounds -> epilogue) that keeps a warp scheduler idle.
+// The epilogues run after all the sums, so epi may overwrite x.
+template <int NW, int MAXPASS, class Epi>
+__device__ __forceinline__ void gemv_cols_vu(const double* __restrict__ M, int ld, int rows, int cols,
+                                             const double* __restrict__ x, int lane, int warp, Epi epi) {
+    const int cq = lane >> 3, rl = lane & 7;
+    const double2* xv = reinterpret_cast<const double2*>(x) + rl;
+    const int npair = (rows + 1) >> 1;
+    const int nq = (npair + 7) >> 3;
+    double acc[MAXPASS];
+#pragma unroll
+    for (int i = 0; i < MAXPASS; ++i) {
+        const int c = warp * 4 + i * NW * 4 + cq;
+        const double2* col = reinterpret_cast<const double2*>(M + (c < cols ? c : 0) * ld) + rl;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+        for (int m = 0; m < nq; ++m) {
+            if (rl + 8 * m < npair) {
+                const double2 g = col[8 * m], w = xv[8 * m];
+                a0 = fma(g.x, w.x, a0);
+                a1 = fma(g.y, w.y, a1);
+            }
+        }
+        acc[i] = a0 + a1;
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < MAXPASS; ++i) acc[i] += __shfl_xor_sync(FULL_MASK, acc[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < MAXPASS; ++i) {
+        const int c = warp * 4 + i * NW * 4 + cq;
+        if (rl == 0 && c < cols) epi(c, acc[i]);
+    }
+}
 // out(c) = sum_{r >= r_lo(c)} M[c*ld + r] * x[r], four lanes per column, scalar loads (triangular / small operands).
 template <int NW, bool TRI, class Epi>
 __device__ __forceinline__ void gemv_cols(const double* __restrict__ M, int ld, int rows, int cols,

@@ -524,22 +524,35 @@ template <int NW, class Epi>
 __device__ __forceinline__ void f3_symv(const double* Tt, int nb, const double* x, int lane, int warp, const T3Lane& TL,
                                         Epi epi) {
     const int fr = lane >> 2, fk = lane & 3;
-    for (int i = warp; i < nb; i += NW) {
-        double a0 = 0.0, a1 = 0.0;
-        const double* Trow = Tt + t3_idx(i, 0) * 64;
-        for (int j = 0; j <= i; ++j) {
-            a0 = fma(Trow[j * 64 + TL.a0], x[8 * j + fk], a0);
-            a1 = fma(Trow[j * 64 + TL.a1], x[8 * j + fk + 4], a1);
+    // nb <= 2 NW: a warp owns at most two block rows; their chains are interleaved (a missing second row re-does the
+    // first and drops the result)
+    for (int i0 = warp; i0 < nb; i0 += 2 * NW) {
+        const int i1 = i0 + NW;
+        const bool two = i1 < nb;
+        const int ib = two ? i1 : i0;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        const double* Ta = Tt + t3_idx(i0, 0) * 64;
+        const double* Tb = Tt + t3_idx(ib, 0) * 64;
+        for (int j = 0; j < nb; ++j) {
+            const double x0 = x[8 * j + fk], x1 = x[8 * j + fk + 4];
+            const double* pa = (j <= i0) ? Ta + j * 64 : Tt + t3_idx(j, i0) * 64;
+            const double* pb = (j <= ib) ? Tb + j * 64 : Tt + t3_idx(j, ib) * 64;
+            const int oa0 = (j <= i0) ? TL.a0 : TL.c0, oa1 = (j <= i0) ? TL.a1 : TL.c1;
+            const int ob0 = (j <= ib) ? TL.a0 : TL.c0, ob1 = (j <= ib) ? TL.a1 : TL.c1;
+            a0 = fma(pa[oa0], x0, a0);
+            a1 = fma(pa[oa1], x1, a1);
+            b0 = fma(pb[ob0], x0, b0);
+            b1 = fma(pb[ob1], x1, b1);
         }
-        for (int j = i + 1; j < nb; ++j) {
-            const double* Tc = Tt + t3_idx(j, i) * 64;
-            a0 = fma(Tc[TL.c0], x[8 * j + fk], a0);
-            a1 = fma(Tc[TL.c1], x[8 * j + fk + 4], a1);
-        }
-        double acc = a0 + a1;
+        double acc = a0 + a1, bcc = b0 + b1;
         acc += __shfl_xor_sync(FULL_MASK, acc, 1);
+        bcc += __shfl_xor_sync(FULL_MASK, bcc, 1);
         acc += __shfl_xor_sync(FULL_MASK, acc, 2);
-        if (fk == 0) epi(8 * i + fr, acc);
+        bcc += __shfl_xor_sync(FULL_MASK, bcc, 2);
+        if (fk == 0) {
+            epi(8 * i0 + fr, acc);
+            if (two) epi(8 * i1 + fr, bcc);
+        }
     }
 }
 
@@ -944,7 +957,7 @@ __global__ void __launch_bounds__(NW * 32 * TEAMS, MINB) k_fused3(const F3Args a
         double ll = 0.0;            // lambda'lambda of the current iteration
         for (;;) {
             // ---- n0 = G'u + sc*dx (+ sc*A'dy: sing, src/densesolver.jl:68-71)            src/densesolver.jl:66-67
-            gemv_cols_v<NW>(G, ldg, kd, n, u + d0, lane, warp, [&](int c, double acc) {
+            gemv_cols_vu<NW, 16 / NW>(G, ldg, kd, n, u + d0, lane, warp, [&](int c, double acc) {
                 double r = dx[c];
                 if (sing) r += atdy[c];
                 n0[c] = acc + sing_col(c, u) + sc * r;
@@ -1272,7 +1285,7 @@ __global__ void __launch_bounds__(NW * 32 * TEAMS, MINB) k_fused3(const F3Args a
                     r4[2] = fma(si, zi, r4[2]);
                     r4[3] = fma(lv, lv, r4[3]);
                 }
-                gemv_cols_v<NW>(G, ldg, kd, n, z + d0, lane, warp, [&](int c, double acc) {
+                gemv_cols_vu<NW, 16 / NW>(G, ldg, kd, n, z + d0, lane, warp, [&](int c, double acc) {
                     double v = -(acc + sing_col(c, z)) - cv[c];
                     for (int q = 0; q < p; ++q) v = fma(-A[c * p + q], y[q], v);
                     dx[c] = v;

@@ -13,7 +13,7 @@ module Socp
 using LinearAlgebra
 using SparseArrays
 
-export POC, SOC, Problem, BatchProblem, State, SolverState, B200Solver, B200Scaling,
+export POC, SOC, Problem, BatchProblem, SparseBatchProblem, State, SolverState, B200Solver, B200Scaling,
        solve_socp, solve_socp_batch, compute_scaling, setup_iter, solve_kkt, scale!, iscale!,
        vprod, iprod, make_e, max_step, compute_step, deg
 
@@ -88,7 +88,49 @@ struct BatchProblem{C<:Tuple{Vararg{Cone}}}
     end
 end
 
-"Problem(c, A, b, G, h, cones) -- reference src/Socp.jl:40-59; A and G may be sparse (densified once)."
+"""
+    SparseBatchProblem(c, A, b, G, h, cones; Avals, Gvals)
+
+The same batch with `A` and `G` held the way the reference holds them (`SparseMatrixCSC{Float64,Int64}`,
+src/Socp.jl:25,29): one sparsity pattern per matrix for the whole batch; `Avals` / `Gvals` (nnz x B) carry the
+per-problem values on that pattern (without them the one matrix is shared by every problem).  Nothing is densified on
+the host: colptr / rowval / nzval go to the library as they are (`socp_b200_solve_host_csc`).
+"""
+struct SparseBatchProblem{C<:Tuple{Vararg{Cone}}}
+    c::Matrix{Float64}
+    A::SparseMatrixCSC{Float64,Int64}
+    Avals::Union{Nothing,Matrix{Float64}}
+    b::Matrix{Float64}
+    G::SparseMatrixCSC{Float64,Int64}
+    Gvals::Union{Nothing,Matrix{Float64}}
+    h::Matrix{Float64}
+    cones::C
+    n::Int; m::Int; k::Int; B::Int
+    function SparseBatchProblem(c::AbstractMatrix, A::SparseMatrixCSC, b::AbstractMatrix, G::SparseMatrixCSC,
+                                h::AbstractMatrix, cones::C; Avals = nothing, Gvals = nothing) where {C<:Tuple{Vararg{Cone}}}
+        n, B = size(c)
+        m = size(b, 1)
+        k = size(h, 1)
+        @assert size(b, 2) == B && size(h, 2) == B
+        @assert size(G) == (k, n) && size(A) == (m, n)          # src/Socp.jl:43-47
+        @assert sum(conedim, cones) == k
+        @assert Gvals === nothing || size(Gvals) == (nnz(G), B)
+        @assert Avals === nothing || size(Avals) == (nnz(A), B)
+        new{C}(Matrix{Float64}(c), SparseMatrixCSC{Float64,Int64}(A), Avals, Matrix{Float64}(b),
+               SparseMatrixCSC{Float64,Int64}(G), Gvals, Matrix{Float64}(h), cones, n, m, k, B)
+    end
+end
+const AnyBatchProblem = Union{BatchProblem,SparseBatchProblem}
+
+"Problem(c, A, b, G, h, cones) -- reference src/Socp.jl:40-59.  Sparse A and G stay sparse (a batch of one on the CSC path)."
+function Problem(c::AbstractVector, A::SparseMatrixCSC, b::AbstractVector, G::SparseMatrixCSC,
+                 h::AbstractVector, cones::Tuple{Vararg{Cone}})
+    @assert length(b) == size(A, 1)
+    @assert size(A, 2) == length(c) && size(G, 2) == length(c)
+    @assert length(h) == size(G, 1)
+    SparseBatchProblem(reshape(Vector{Float64}(c), :, 1), A, reshape(Vector{Float64}(b), :, 1), G,
+                       reshape(Vector{Float64}(h), :, 1), cones)
+end
 function Problem(c::AbstractVector, A::AbstractMatrix, b::AbstractVector, G::AbstractMatrix,
                  h::AbstractVector, cones::Tuple{Vararg{Cone}})
     @assert length(b) == size(A, 1)
@@ -120,7 +162,7 @@ mutable struct SolverState{S<:KKTSolver}
     handle::Ptr{Cvoid}
     scaling::B200Scaling
     n::Int; m::Int; k::Int; B::Int; ncones::Int
-    function SolverState(pr::BatchProblem, solver::B200Solver)
+    function SolverState(pr::AnyBatchProblem, solver::B200Solver)
         kind = Int32[conekind(c) for c in pr.cones]
         offs = Int32[c.offs for c in pr.cones]
         dim = Int32[conedim(c) for c in pr.cones]
@@ -207,10 +249,33 @@ function solve_socp_batch(pr::BatchProblem, ss::SolverState; params = default_pa
     return (x = x, y = y, z = z, s = s, status = status, iters = iters, pobj = pobj, dobj = dobj)
 end
 
+# The same one-shot call from the reference's own storage: colptr / rowval / nzval (1-based) as they are.
+function solve_socp_batch(pr::SparseBatchProblem, ss::SolverState; params = default_params(),
+                          sing::Union{Nothing,Vector{UInt8}} = nothing)
+    x = zeros(pr.n, pr.B); y = zeros(pr.m, pr.B); z = zeros(pr.k, pr.B); s = zeros(pr.k, pr.B)
+    status = zeros(Int32, pr.B); iters = zeros(Int32, pr.B); pobj = zeros(pr.B); dobj = zeros(pr.B)
+    flags = Int32((pr.Avals === nothing && pr.m > 0 ? 1 : 0) | (pr.Gvals === nothing ? 2 : 0))
+    gv = pr.Gvals === nothing ? pr.G.nzval : pr.Gvals
+    av = pr.Avals === nothing ? pr.A.nzval : pr.Avals
+    rc = GC.@preserve pr gv av sing x y z s status iters pobj dobj begin
+        gs = Ref(CCsc(nnz(pr.G), pointer(pr.G.colptr), pointer(pr.G.rowval), pointer(gv), 1))
+        as = Ref(CCsc(nnz(pr.A), pointer(pr.A.colptr), pointer(pr.A.rowval), pr.m > 0 ? pointer(av) : Ptr{Float64}(C_NULL), 1))
+        ccall((:socp_b200_solve_host_csc, libsocp), Cint,
+              (Ptr{Cvoid}, Ref{CParams}, Ptr{Float64}, Ptr{CCsc}, Ptr{Float64}, Ptr{CCsc}, Ptr{Float64},
+               Ptr{UInt8}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+               Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+              ss.handle, params, pr.c, pr.m > 0 ? as : C_NULL, pr.m > 0 ? pointer(pr.b) : Ptr{Float64}(C_NULL), gs, pr.h,
+              sing === nothing ? Ptr{UInt8}(C_NULL) : pointer(sing), flags,
+              x, pr.m > 0 ? pointer(y) : Ptr{Float64}(C_NULL), z, s, status, iters, pobj, dobj)
+    end
+    check(ss, rc, "socp_b200_solve_host_csc")
+    return (x = x, y = y, z = z, s = s, status = status, iters = iters, pobj = pobj, dobj = dobj)
+end
+
 "solve_socp(prob, ss) -> State, reference src/solver.jl:40-152 (a batch of one)."
-function solve_socp(pr::BatchProblem, ss::SolverState)
+function solve_socp(pr::AnyBatchProblem, ss::SolverState; params = default_params())
     @assert pr.B == 1
-    r = solve_socp_batch(pr, ss)
+    r = solve_socp_batch(pr, ss; params = params)
     State(r.x[:, 1], r.y[:, 1], r.z[:, 1], r.s[:, 1], r.status[1], r.iters[1], r.pobj[1], r.dobj[1])
 end
 
