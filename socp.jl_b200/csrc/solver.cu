@@ -8,6 +8,7 @@
 #include "fused_v3.cuh"
 #include "cone_batch.cuh"
 #include "panel_mma.cuh"
+#include "syrk_tma.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -193,7 +194,13 @@ void syrk(Shard& sh, bool kmajor, const double* A, int64_t sA, int lda, int N, i
     const long long t128 = (long long)((N + 127) / 128) * ((N + 127) / 128 + 1) / 2 * sh.batch;
     const bool big = N > 256 && t128 >= 2 * 148;
     if (kmajor) {
-        if (big) syrk_launch<128, 4, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
+        if (big && syrk_tma_supported(A, sA, lda, N, K)) {
+            // operands fed by TMA (tensor map over A, mbarrier-signalled 4-stage ring): syrk_tma.cu
+            const int nt = (N + 127) / 128;
+            CK(syrk_tma_launch(sh.stream, batch_grid(nt * (nt + 1) / 2, sh.batch), A, sA, lda, N, K, C, sC, ldc, alpha, beta,
+                               addC, sAdd, ldadd, addFlag, active, sh.batch));
+            sh.launches++;
+        } else if (big) syrk_launch<128, 4, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
         else syrk_launch<64, 2, 16, true>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);
     } else {
         if (big) syrk_launch<128, 4, 16, false>(sh, A, sA, lda, N, K, C, sC, ldc, alpha, beta, addC, sAdd, ldadd, addFlag, active);

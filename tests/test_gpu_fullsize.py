@@ -131,6 +131,23 @@ def test_c4_batch():
     check_against_oracle(prob, res, np.arange(0, 48, 6))
 
 
+def test_syrk_tma_feed_bit_identical_to_cp_async_feed():
+    """The Gram product H = Gt'Gt of the tiled path is fed by TMA (tensor map + mbarrier ring, csrc/syrk_tma.cu); with
+    SOCP_B200_NO_TMA it runs the cp.async kernel of linalg.cuh.  Same tiles, same order of the k-blocks: the whole
+    solve must not change by a bit.  n = 500 and k = 1000 exercise the zero-filled out-of-bounds columns (500 = 3 x 128
+    + 116) and rows (1008 = 50 x 20 + 8) of the TMA boxes."""
+    prob = gen.make_config("C4", batch=40)
+    a = sb.solve_socp_batch(prob, sb.SolverState(prob))
+    os.environ["SOCP_B200_NO_TMA"] = "1"
+    try:
+        b = sb.solve_socp_batch(prob, sb.SolverState(prob))
+    finally:
+        del os.environ["SOCP_B200_NO_TMA"]
+    assert a.timings["path_used"] == sb.PATH_TILED and (a.status == sb.STATUS_CONVERGED).all()
+    for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
 GOLD_LARGE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "large_golden.npz")
 
 
