@@ -43,7 +43,7 @@ def plan(n, p, cones, rowcol):
 
 def solve(c, A_cm, b, G_cm, h, cones, sing=None, rowcol=None, generic=False, sing_detect=False, verify=False, order=0,
           max_iter=40, tol=1e-5, step_damp=0.99, init_eps=1e-10, dbg=None, grid_cap=4, shared_G=False, shared_A=False,
-          teams4=False):
+          teams4=False, align=False):
     """Same conventions as oracle.c_oracle.solve_batch.  dbg = (problem, iteration[, phase]) -> also returns the debug dump."""
     c = np.ascontiguousarray(c, dtype=np.float64)
     B, n = c.shape
@@ -64,7 +64,7 @@ def solve(c, A_cm, b, G_cm, h, cones, sing=None, rowcol=None, generic=False, sin
     sg = np.ascontiguousarray(sing, dtype=np.uint8) if sing is not None else None
     rc = np.ascontiguousarray(rowcol, dtype=np.int32) if rowcol is not None else None
     dbuf = np.zeros(2 * k + n * n + 2 * (n + p + 2 * k)) if dbg is not None else None
-    flags = (1 if generic else 0) | (2 if sing_detect else 0) | (4 if verify else 0) | (8 if teams4 else 0)
+    flags = (1 if generic else 0) | (2 if sing_detect else 0) | (4 if verify else 0) | (8 if teams4 else 0) | (16 if align else 0)
     r = lib().emu_fused3_solve(n, p, k, len(cones), _i(kind), _i(offs), _i(dim), B, _d(c), _d(A_cm),
                                C.c_int64(0 if shared_A else p * n), _d(b) if p else _d(np.zeros(1)), _d(G_cm),
                                C.c_int64(0 if shared_G else k * n), _d(h),

@@ -35,7 +35,8 @@ extern "C" int emu_fused3_plan(int n, int p, int k, int ncones, const int* kind,
     return 0;
 }
 
-// flags: bit 0 = generic kernel only, bit 1 = sing_detect, bit 2 = verify, bit 3 = four teams per CTA; rowcol_in may be
+// flags: bit 0 = generic kernel only, bit 1 = sing_detect, bit 2 = verify, bit 3 = four teams per CTA, bit 4 = re-align
+// the teams every iteration (the experiment switch of solve_fused3); rowcol_in may be
 // null (detected from G).
 // order: fibre schedule of the emulator (0 forward, 1 reverse, 2 random).  Returns 0, or -1 when the plan does not fit.
 extern "C" int emu_fused3_solve(int n, int p, int k, int ncones, const int* kind, const int* offs, const int* dim,
@@ -71,7 +72,7 @@ extern "C" int emu_fused3_solve(int n, int p, int k, int ncones, const int* kind
     a.counter = &counter;
     a.sing_detect = (flags >> 1) & 1;
     a.verify = (flags >> 2) & 1;
-    a.align = 1;
+    a.align = (flags >> 4) & 1;
     simt_emu::LaunchCfg cfg;
     const bool teams4 = (flags >> 3) & 1;
     if (teams4 && !P.teams4) return -1;

@@ -80,14 +80,17 @@ def test_c2_schedule_independent(order):
         assert np.array_equal(a[f], b[f]), f
 
 
-@pytest.mark.parametrize("generic,B,grid_cap,order", [(False, 7, 1, 0), (True, 6, 2, 2), (False, 3, 1, 1)])
-def test_c2_four_teams_per_cta(generic, B, grid_cap, order):
-    """Four teams (problems) per CTA, re-aligned at the top of every Mehrotra iteration by CTA-wide barriers: bit
-    identical to one team per CTA, whatever the number of problems per team (teams run out of work at different
-    times and keep the alignment barriers company; B = 3 leaves one team without any problem) and the schedule."""
+@pytest.mark.parametrize("generic,B,grid_cap,order,align", [(False, 7, 1, 0, True), (True, 6, 2, 2, True), (False, 3, 1, 1, True),
+                                                             (False, 7, 1, 2, False), (True, 5, 1, 1, False)])
+def test_c2_four_teams_per_cta(generic, B, grid_cap, order, align):
+    """Four teams (problems) per CTA, each with its own slice of shared memory and pair of hardware barriers, warp
+    numbering rotated per team: bit identical to one team per CTA, whatever the number of problems per team and the
+    schedule.  align=True also re-aligns the teams at the top of every Mehrotra iteration with CTA-wide barriers (the
+    experiment switch SOCP_B200_F3_ALIGN): teams run out of work at different times and keep the alignment barriers
+    company; B = 3 leaves one team without any problem."""
     prob = gen.make_config("C2", batch=B)
     a = run(prob, generic=generic)
-    b = run(prob, generic=generic, teams4=True, grid_cap=grid_cap, order=order)
+    b = run(prob, generic=generic, teams4=True, grid_cap=grid_cap, order=order, align=align)
     for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj"):
         assert np.array_equal(a[f], b[f]), f
 
@@ -102,7 +105,7 @@ def test_four_teams_sing_detect_and_pattern():
     prob2 = sb.BatchProblem(prob.c, prob.A_cm, prob.b, G, prob.h, prob.cones, sing=None, colmajor=True)
     kw = dict(sing=None, sing_detect=True)
     a = emu.solve(prob2.c, prob2.A_cm, prob2.b, prob2.G_cm, prob2.h, oc(prob2.cones), **kw)
-    b = emu.solve(prob2.c, prob2.A_cm, prob2.b, prob2.G_cm, prob2.h, oc(prob2.cones), teams4=True, grid_cap=1, order=2, **kw)
+    b = emu.solve(prob2.c, prob2.A_cm, prob2.b, prob2.G_cm, prob2.h, oc(prob2.cones), teams4=True, grid_cap=1, order=2, align=True, **kw)
     assert a["sing"][2] == 1
     for f in ("x", "y", "z", "s", "status", "iters", "pobj", "dobj", "sing"):
         assert np.array_equal(a[f], b[f]), f
