@@ -1,0 +1,691 @@
+// fused_lane.cuh -- whole-solve kernel for batches of TINY problems (n <= 16, p = 0: BASELINE.json C3, n = 12 with ten
+// second-order cones of dimension 4): ONE LANE PER PROBLEM.
+//
+// Reference path: the same Mehrotra predictor-corrector as the other whole-solve kernels (src/solver.jl:68-152 on
+// src/densesolver.jl:41-90, src/scalings.jl:22-141, src/mats.jl:1-86, src/vectors.jl:54-125), state machine of
+// fused_v2.cuh (initial point = one factor + solve with W = I; affine and combined directions share one code path).
+//
+// Why another kernel.  A problem of this size is ~13 kFLOP per iteration: a warp (let alone a team of warps) per
+// problem spends its instructions on shuffles, partial vectors and shared-memory round trips -- fused_v2 on C3 issues
+// ~5 000 warp instructions per problem-iteration for ~200 instructions' worth of FMAs, and its shared-memory pipe is
+// the busiest unit.  Here every lane runs the whole scalar algorithm on its own problem: no shuffles,
+// no barriers, no reductions; a warp instruction advances LPW problems at once.
+//
+//   * lane-interleaved storage everywhere: element e of the problem of lane l lives at base[e * LPW + l], so every
+//     warp access is one contiguous run (shared memory: conflict free; global: fully coalesced);
+//   * G, h, c and the Cholesky factor live in a per-warp global workspace (L2 resident: 148 SMs x 64 problems x 4.9 KB
+//     = 46 MB), the iterate / scaling / right-hand sides (9 k-vectors + 2 n-vectors + 4 scalars per cone) in shared
+//     memory (3.4 KB per problem -> 64 problems per SM); H (n(n+1)/2 packed) and the n-vectors of a solve in registers;
+//   * the reduced KKT matrix is accumulated row by row, H = sum_r d_r g_r g_r' + sum_c h_c h_c' (closed form of
+//     G'W^-2 G, src/densesolver.jl:42-43), factored in registers (LL', src/densesolver.jl:47) and solved by
+//     substitution; the factor of the affine direction is parked in the workspace for the combined direction;
+//   * lanes pull problems from an atomic counter as they finish (iteration counts vary 6..19 inside a batch); the
+//     warp copies a new problem into the lane's workspace slot cooperatively (coalesced reads);
+//   * slots alternate F (factor: initial point or affine direction) and N (no factor: combined direction), so lanes
+//     of one warp stay in step: a lane that has just taken a problem runs its initial point in an F slot, idles
+//     through the next N slot and joins the others at the following F slot;
+//   * LPW (lanes in use per warp) is a template parameter: 64 problems per SM are LPW-independent (shared memory),
+//     64 / LPW warps per SM share the four sub-partitions -- fewer lanes per warp = more independent instruction
+//     streams to hide the latency of each lane's dependent chains.
+//
+// Restrictions: p = 0, no `sing` problems (callers fall back to fused_v2 / the tiled path), layouts that have a
+// compile-time instantiation below (positive-orthant block first, then equal second-order cones).
+#pragma once
+#include "fused_common.cuh"
+#include <vector>
+#include <algorithm>
+
+namespace socp {
+
+template <int N_, int KPOC_, int NSOC_, int SDIM_>
+struct LaneDims {
+    static constexpr int N = N_, KPOC = KPOC_, NSOC = NSOC_, SDIM = SDIM_;
+    static constexpr int K = KPOC_ + NSOC_ * SDIM_;
+    static constexpr int NH = N_ * (N_ + 1) / 2;
+    // shared memory, doubles per lane: k-vectors, then iwb (orthant rows), cone scalars, x, dx
+    enum { V_S = 0, V_Z, V_LAM, V_WB, V_DZ, V_DSC, V_K0, V_K2, V_U, NVEC };
+    static constexpr int O_IWB = NVEC * K;
+    static constexpr int O_CS = O_IWB + KPOC_;            // 4 per cone: eta, 1/eta, 1/(1+w0), |lam_1|^2
+    static constexpr int O_X = O_CS + 4 * NSOC_;
+    static constexpr int O_DX = O_X + N_;
+    static constexpr int SM_PER_LANE = O_DX + N_;
+    // global workspace, doubles per lane: G (row-major k x n), h, c, the packed factor
+    static constexpr int W_G = 0, W_H = K * N_, W_C = W_H + K, W_L = W_C + N_;
+    static constexpr int WS_PER_LANE = W_L + NH;
+    static bool matches(int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
+                        const std::vector<int>& dim) {
+        if (n != N || p != 0 || k != K) return false;
+        int kpoc = 0, nsoc = 0;
+        for (size_t i = 0; i < kind.size(); ++i) {
+            if (kind[i] == KIND_POC) {
+                if (nsoc) return false;                   // orthant rows first
+                kpoc += dim[i];
+            } else {
+                if (dim[i] != SDIM || offs[i] != KPOC + nsoc * SDIM) return false;
+                ++nsoc;
+            }
+        }
+        return kpoc == KPOC && nsoc == NSOC;
+    }
+};
+
+using LaneC3 = LaneDims<12, 0, 10, 4>;      // BASELINE.json C3
+using LaneT1 = LaneDims<6, 5, 3, 3>;        // small mixed layout (orthant block + cones): keeps the generic code honest
+
+constexpr int FL_PROBLEMS_PER_SM = 64;
+constexpr int FL_WS_SETS = 2;               // launches that may overlap use different workspace sets
+
+struct FLPlan {
+    bool fits = false;
+    int shape = 0;          // 1: LaneC3, 2: LaneT1
+    int lpw = 8;            // lanes in use per warp
+    int num_sms = 148;
+    int deg = 0;
+    size_t smem = 0;
+    size_t ws_doubles = 0;  // per workspace set
+    double* d_ws = nullptr; // FL_WS_SETS sets
+    int* d_counter = nullptr;
+};
+
+inline void fl_plan(FLPlan& P, int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
+                    const std::vector<int>& dim, int dev_smem, int sms) {
+    P.fits = false;
+    P.shape = 0;
+    int spl = 0, wpl = 0;
+    if (LaneC3::matches(n, p, k, kind, offs, dim)) { P.shape = 1; spl = LaneC3::SM_PER_LANE; wpl = LaneC3::WS_PER_LANE; }
+    else if (LaneT1::matches(n, p, k, kind, offs, dim)) { P.shape = 2; spl = LaneT1::SM_PER_LANE; wpl = LaneT1::WS_PER_LANE; }
+    else return;
+    P.num_sms = sms;
+    P.deg = 0;
+    for (size_t i = 0; i < kind.size(); ++i) P.deg += kind[i] == KIND_POC ? dim[i] : 1;
+    P.smem = (size_t)spl * FL_PROBLEMS_PER_SM * sizeof(double);
+    if (P.smem > (size_t)dev_smem) return;
+    P.ws_doubles = (size_t)wpl * FL_PROBLEMS_PER_SM * sms;
+    P.fits = true;
+}
+
+struct FLArgs {
+    // problem data and results of the shard (batch slowest), as in Ws
+    const double *c, *G, *h;
+    int64_t sG;
+    double *x, *z, *s, *pobj, *dobj;
+    int *status, *iters, *active, *fail;
+    double* ws;
+    int* counter;
+    int first, batch, cap, deg;
+    LoopParams prm;
+};
+
+enum { FL_FREE = -1, FL_DONE = -2 };
+
+#ifdef SOCP_SIMT_EMU
+inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) {
+        const int v = __shfl_sync(0xffffffffu, pred, l);
+        if (v && l < simt_emu::cur_block()->warps[simt_emu::cur_thread()->warp].nlanes) r |= 1u << l;
+    }
+    return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+#define FL_SMEM() reinterpret_cast<double*>(emu_dyn_smem())
+#else
+#define FL_SMEM() fl_sm
+#endif
+
+template <class D, int LPW>
+__global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_lane(const FLArgs a) {
+#ifndef SOCP_SIMT_EMU
+    extern __shared__ __align__(16) double fl_sm[];
+#endif
+    constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NSOC = D::NSOC, SDIM = D::SDIM, NH = D::NH;
+    constexpr unsigned MASK = LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u);
+    constexpr int NWARP = FL_PROBLEMS_PER_SM / LPW;
+    const int tid = (int)(unsigned)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (lane >= LPW) return;
+    const int gwarp = (int)(unsigned)blockIdx.x * NWARP + warp;
+    double* const S = FL_SMEM() + (size_t)warp * D::SM_PER_LANE * LPW + lane;
+    double* const Wb = a.ws + (size_t)gwarp * D::WS_PER_LANE * LPW;
+    double* const W = Wb + lane;
+    const LoopParams prm = a.prm;
+#define SV(v, i) S[((v) * K + (i)) * LPW]
+#define SO(o, i) S[((o) + (i)) * LPW]
+#define WG(r, j) W[((r) * N + (j)) * LPW]
+#define WO(o, i) W[((o) + (i)) * LPW]
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+    int phase = FL_FREE, b = 0, iters = 0, status = ST_RUNNING;
+    bool need_top = false, dead = false, exhausted = false, fslot = true;
+    double sc = 1.0, ll = 0.0;
+
+    for (;;) {
+        if (fslot) {
+            // ------------------------------------------------ top of a Mehrotra iteration, src/solver.jl:105-126
+            if (phase == 1 && need_top) {
+                need_top = false;
+                if (iters >= prm.max_iter) { status = ST_MAXITER; phase = FL_DONE; }
+                else {
+                    double gap = 0.0, llacc = 0.0;
+                    int fl = 0;
+#pragma unroll 2
+                    for (int i = 0; i < KPOC; ++i) {                                    // src/scalings.jl:22-30
+                        const double si = SV(D::V_S, i), zi = SV(D::V_Z, i);
+                        const double q = si * fast_rcp(zi), qi = zi * fast_rcp(si), pz = si * zi;
+                        fl |= !(q >= 0.0) | !(pz >= 0.0);
+                        const double lv = fast_sqrt(pz);
+                        SV(D::V_WB, i) = fast_sqrt(q);
+                        SO(D::O_IWB, i) = fast_sqrt(qi);
+                        SV(D::V_LAM, i) = lv;
+                        gap = fma(si, zi, gap);
+                        llacc = fma(lv, lv, llacc);
+                    }
+#pragma unroll 2
+                    for (int c = 0; c < NSOC; ++c) {                                    // src/scalings.jl:32-99
+                        const int o = KPOC + c * SDIM;
+                        double sv[SDIM], zv[SDIM];
+#pragma unroll
+                        for (int e = 0; e < SDIM; ++e) { sv[e] = SV(D::V_S, o + e); zv[e] = SV(D::V_Z, o + e); }
+                        double ss = 0.0, zz = 0.0, sz = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) { ss = fma(sv[e], sv[e], ss); zz = fma(zv[e], zv[e], zz); sz = fma(sv[e], zv[e], sz); }
+                        const double onrms = sv[0] * sv[0] - ss, onrmz = zv[0] * zv[0] - zz;      // :39-45
+                        fl |= !(onrms >= 0.0) | !(onrmz >= 0.0);
+                        const double is = fast_rsqrt(onrms), iz = fast_rsqrt(onrmz);    // :46-49
+                        const double nrms = onrms * is, nrmz = onrmz * iz;
+                        const double sb0 = sv[0] * is, zb0 = zv[0] * iz;
+                        const double ns = sz * (is * iz) + zb0 * sb0;                   // :53-56
+                        const double g2 = (1.0 + ns) / 2.0;
+                        fl |= !(g2 >= 0.0);
+                        const double rg = fast_rsqrt(g2);
+                        const double gamma = g2 * rg, ig = 0.5 * rg;                    // :57, :64
+                        const double eta = fast_sqrt(nrms * iz);                        // :68
+                        const double ie = fast_rcp(eta);
+                        const double tmv1 = fast_sqrt(nrms * nrmz);                     // :91
+                        const double mult = tmv1 * fast_rcp(zb0 + sb0 + 2.0 * gamma);   // :92
+                        const double csf = gamma + zb0, czf = gamma + sb0;              // :93-94
+                        double llt = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) {
+                            const double sb = sv[e] * is, zb = zv[e] * iz;
+                            const double lv = (sb * csf + zb * czf) * mult;             // :95-97
+                            SV(D::V_WB, o + e) = (sb - zb) * ig;                        // :62, :64
+                            SV(D::V_LAM, o + e) = lv;
+                            llt = fma(lv, lv, llt);
+                        }
+                        const double w0 = (sb0 + zb0) * ig, l0 = gamma * tmv1;
+                        SV(D::V_WB, o) = w0;                                            // :60
+                        SV(D::V_LAM, o) = l0;                                           // :98
+                        SO(D::O_CS, 4 * c + 0) = eta;
+                        SO(D::O_CS, 4 * c + 1) = ie;
+                        SO(D::O_CS, 4 * c + 2) = fast_rcp(1.0 + w0);
+                        SO(D::O_CS, 4 * c + 3) = llt;
+                        gap += sv[0] * zv[0] + sz;
+                        llacc += l0 * l0 + llt;
+                    }
+                    // negated residuals (:110-118, :125) in one pass over G: dx = -G'z - c, dz = -G x - s + h
+                    double rx[N], xr[N];
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { rx[j] = -WO(D::W_C, j); xr[j] = SO(D::O_X, j); }
+#pragma unroll 4
+                    for (int r = 0; r < K; ++r) {
+                        const double zr = SV(D::V_Z, r);
+                        double g[N];
+#pragma unroll
+                        for (int j = 0; j < N; ++j) g[j] = WG(r, j);
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            rx[j] = fma(-g[j], zr, rx[j]);
+                            if (j & 1) a1 = fma(g[j], xr[j], a1); else a0 = fma(g[j], xr[j], a0);
+                        }
+                        SV(D::V_DZ, r) = -(a0 + a1) - SV(D::V_S, r) + WO(D::W_H, r);
+                    }
+                    double rxn = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { rxn = fma(rx[j], rx[j], rxn); SO(D::O_DX, j) = rx[j]; }
+                    if (fl) { status = ST_NUMERICAL; phase = FL_DONE; }                 // compute_scaling threw
+                    else if (sqrt(rxn) + gap < prm.tol) { status = ST_CONVERGED; phase = FL_DONE; }   // :122-124 (p = 0)
+                    else { ll = llacc; sc = 1.0; }
+                }
+            }
+            // ------------------------------------------------ a finished problem: iterate and objectives
+            if (phase == FL_DONE) {
+                double po = 0.0, dob = 0.0;
+                for (int j = 0; j < N; ++j) {
+                    const double xj = dead ? 0.0 : SO(D::O_X, j);
+                    a.x[(int64_t)b * N + j] = xj;
+                    po = fma(WO(D::W_C, j), xj, po);
+                }
+                for (int r = 0; r < K; ++r) {
+                    const double zr = dead ? 0.0 : SV(D::V_Z, r);
+                    a.z[(int64_t)b * K + r] = zr;
+                    a.s[(int64_t)b * K + r] = dead ? 0.0 : SV(D::V_S, r);
+                    dob = fma(-WO(D::W_H, r), zr, dob);
+                }
+                a.pobj[b] = po;
+                a.dobj[b] = dob;
+                a.status[b] = status;
+                a.iters[b] = iters;
+                a.active[b] = 0;
+                a.fail[b] = (status == ST_NUMERICAL);
+                phase = FL_FREE;
+            }
+            // ------------------------------------------------ free lanes take the next problems of the batch
+            {
+                const bool want = phase == FL_FREE && lane < a.cap && !exhausted;
+                const unsigned need = __ballot_sync(MASK, want);
+                if (need) {
+                    const int cnt = __popc(need);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(a.counter, cnt);
+                    base = __shfl_sync(MASK, base, 0);
+                    int myb = want ? base + __popc(need & ((1u << lane) - 1u)) : -1;
+                    if (base + cnt >= a.batch) exhausted = true;
+                    if (myb >= a.batch) myb = -1;
+                    unsigned m = need;
+                    while (m) {                                   // warp-uniform: copy the problem of lane l into its slot
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int pb = __shfl_sync(MASK, myb, l);
+                        if (pb < 0) continue;
+                        const int64_t gb = (int64_t)a.first + pb;
+                        const double* Gg = a.G + gb * a.sG;
+                        double* Wl = Wb + l;
+                        for (int e = lane; e < K * N; e += LPW) {
+                            const int j = e / K, r = e - j * K;
+                            Wl[(r * N + j) * LPW] = Gg[e];
+                        }
+                        for (int e = lane; e < K; e += LPW) Wl[(D::W_H + e) * LPW] = a.h[gb * K + e];
+                        for (int e = lane; e < N; e += LPW) Wl[(D::W_C + e) * LPW] = a.c[gb * N + e];
+                    }
+                    __syncwarp(MASK);
+                    if (myb >= 0) { b = a.first + myb; phase = 0; iters = 0; status = ST_RUNNING; need_top = false; dead = false; }
+                }
+            }
+            if (!__ballot_sync(MASK, phase != FL_FREE)) break;
+        }
+
+        const bool act = fslot ? (phase == 0 || phase == 1) : (phase == 2);
+        if (__ballot_sync(MASK, act) && act) {
+            // ------------------------------------------------ head of solve_kkt, src/densesolver.jl:61-66 (+ W^-2 of :86)
+            if (phase == 0) {
+                // initial point (src/solver.jl:68-104): W = I, u = h, k2 = h, dx = -c
+                for (int r = 0; r < K; ++r) {
+                    const double hr = WO(D::W_H, r);
+                    SV(D::V_U, r) = hr;
+                    SV(D::V_K2, r) = hr;
+                    SV(D::V_WB, r) = 0.0;
+                }
+                for (int i = 0; i < KPOC; ++i) { SV(D::V_WB, i) = 1.0; SO(D::O_IWB, i) = 1.0; }
+                for (int c = 0; c < NSOC; ++c) {
+                    SV(D::V_WB, KPOC + c * SDIM) = 1.0;
+                    SO(D::O_CS, 4 * c + 0) = 1.0; SO(D::O_CS, 4 * c + 1) = 1.0; SO(D::O_CS, 4 * c + 2) = 0.5; SO(D::O_CS, 4 * c + 3) = 0.0;
+                }
+                for (int j = 0; j < N; ++j) SO(D::O_DX, j) = -WO(D::W_C, j);
+                sc = 1.0;
+            } else {
+                const bool comb = phase == 2;          // ds = -lam o lam (:120) [+ sigma mu e - kt2 o kt3 (:137-139)]
+#pragma unroll 2
+                for (int i = 0; i < KPOC; ++i) {
+                    const double w = SV(D::V_WB, i), iw = SO(D::O_IWB, i), lv = SV(D::V_LAM, i);
+                    const double dsc = SV(D::V_DSC, i);
+                    const double dsv = -(lv * lv) + (comb ? dsc : 0.0);
+                    const double kk = dsv * fast_rcp(lv);
+                    const double kz = sc * SV(D::V_DZ, i) - w * kk;
+                    SV(D::V_K0, i) = kk; SV(D::V_K2, i) = kz; SV(D::V_U, i) = iw * iw * kz;
+                }
+#pragma unroll 2
+                for (int c = 0; c < NSOC; ++c) {
+                    const int o = KPOC + c * SDIM;
+                    const double eta = SO(D::O_CS, 4 * c + 0), ie = SO(D::O_CS, 4 * c + 1), r1w = SO(D::O_CS, 4 * c + 2),
+                                 llt = SO(D::O_CS, 4 * c + 3);
+                    const double ie2 = ie * ie;
+                    double lv[SDIM], wv[SDIM], dsv[SDIM], k0v[SDIM], k2v[SDIM];
+#pragma unroll
+                    for (int e = 0; e < SDIM; ++e) { lv[e] = SV(D::V_LAM, o + e); wv[e] = SV(D::V_WB, o + e); }
+                    const double l0 = lv[0], w0 = wv[0], aa = l0 * l0 - llt;
+                    {
+                        const double d0 = SV(D::V_DSC, o);
+                        dsv[0] = -(llt + l0 * l0) + (comb ? d0 : 0.0);                  // src/vectors.jl:66-69
+                    }
+                    double beta = 0.0;
+#pragma unroll
+                    for (int e = 1; e < SDIM; ++e) {
+                        const double de = SV(D::V_DSC, o + e);
+                        dsv[e] = -(l0 * lv[e] + l0 * lv[e]) + (comb ? de : 0.0);        // :73-75
+                        beta = fma(lv[e], dsv[e], beta);
+                    }
+                    const double ia = fast_rcp(aa), il0 = fast_rcp(l0);
+                    k0v[0] = (l0 * dsv[0] - beta) * ia;                                 // src/vectors.jl:105-125, O(d) form
+                    double dl = 0.0;
+#pragma unroll
+                    for (int e = 1; e < SDIM; ++e) {
+                        k0v[e] = (-dsv[0] * lv[e] + (aa * dsv[e] + beta * lv[e]) * il0) * ia;
+                        dl = fma(wv[e], k0v[e], dl);
+                    }
+                    const double cst = k0v[0] + dl * r1w;                               // src/scalings.jl:135
+                    k2v[0] = SV(D::V_DZ, o) * sc - eta * (w0 * k0v[0] + dl);            // :136, densesolver :65
+                    double qv = w0 * k2v[0];
+#pragma unroll
+                    for (int e = 1; e < SDIM; ++e) {
+                        k2v[e] = SV(D::V_DZ, o + e) * sc - eta * (k0v[e] + cst * wv[e]);        // :137-139
+                        qv = fma(-wv[e], k2v[e], qv);                                   // W^-2 = eta^-2 (2 q q' - J)
+                    }
+#pragma unroll
+                    for (int e = 1; e < SDIM; ++e) {
+                        SV(D::V_K0, o + e) = k0v[e];
+                        SV(D::V_K2, o + e) = k2v[e];
+                        SV(D::V_U, o + e) = ie2 * (k2v[e] - 2.0 * wv[e] * qv);
+                    }
+                    SV(D::V_K0, o) = k0v[0];
+                    SV(D::V_K2, o) = k2v[0];
+                    SV(D::V_U, o) = ie2 * (2.0 * w0 * qv - k2v[0]);
+                }
+            }
+            // ------------------------------------------------ n0 = G'u + sc dx                src/densesolver.jl:66-67
+            double n0[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) n0[j] = 0.0;
+#pragma unroll 4
+            for (int r = 0; r < K; ++r) {
+                const double ur = SV(D::V_U, r);
+#pragma unroll
+                for (int j = 0; j < N; ++j) n0[j] = fma(WG(r, j), ur, n0[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) n0[j] = fma(sc, SO(D::O_DX, j), n0[j]);
+
+            double Lr[NH];
+            bool ok = true;
+            if (fslot) {
+                // -------------------------------------------- KKT factor, src/densesolver.jl:41-47
+                const bool init = phase == 0;
+#pragma unroll
+                for (int e = 0; e < NH; ++e) Lr[e] = 0.0;
+#pragma unroll 1
+                for (int i = 0; i < KPOC; ++i) {
+                    const double iw = SO(D::O_IWB, i);
+                    const double d = iw * iw;
+                    double g[N];
+#pragma unroll
+                    for (int j = 0; j < N; ++j) g[j] = WG(i, j);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const double t = d * g[j];
+#pragma unroll
+                        for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(g[q], t, Lr[TRI(q, j)]);
+                    }
+                }
+#pragma unroll 1
+                for (int c = 0; c < NSOC; ++c) {
+                    const int o = KPOC + c * SDIM;
+                    const double ie = SO(D::O_CS, 4 * c + 1);
+                    const double ie2 = ie * ie;
+                    const double f = init ? 0.0 : 1.4142135623730951 * ie;          // h_c = sqrt(2)/eta G_c'q, q = J wbar
+                    double hq[N];
+#pragma unroll
+                    for (int j = 0; j < N; ++j) hq[j] = 0.0;
+#pragma unroll
+                    for (int e = 0; e < SDIM; ++e) {
+                        const double wq = e == 0 ? SV(D::V_WB, o) : -SV(D::V_WB, o + e);
+                        const double d = (e == 0 && !init) ? -ie2 : ie2;           // -eta^-2 on the head, eta^-2 on the tail
+                        double g[N];
+#pragma unroll
+                        for (int j = 0; j < N; ++j) g[j] = WG(o + e, j);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            hq[j] = fma(wq, g[j], hq[j]);
+                            const double t = d * g[j];
+#pragma unroll
+                            for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(g[q], t, Lr[TRI(q, j)]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < N; ++j) hq[j] *= f;
+#pragma unroll
+                    for (int j = 0; j < N; ++j)
+#pragma unroll
+                        for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(hq[q], hq[j], Lr[TRI(q, j)]);
+                }
+                // in-register LL' (src/densesolver.jl:47); the diagonal keeps 1 / l_jj
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double d = Lr[TRI(j, j)];
+                    ok = ok && (d > 0.0);
+                    const double rj = fast_rsqrt(d);
+                    Lr[TRI(j, j)] = rj;
+#pragma unroll
+                    for (int i = j + 1; i < N; ++i) Lr[TRI(i, j)] *= rj;
+#pragma unroll
+                    for (int i = j + 1; i < N; ++i)
+#pragma unroll
+                        for (int q = j + 1; q <= i; ++q) Lr[TRI(i, q)] = fma(-Lr[TRI(i, j)], Lr[TRI(q, j)], Lr[TRI(i, q)]);
+                }
+                if (!init) {
+#pragma unroll
+                    for (int e = 0; e < NH; ++e) WO(D::W_L, e) = Lr[e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NH; ++e) Lr[e] = WO(D::W_L, e);
+            }
+            if (!ok) { status = ST_NUMERICAL; dead = phase == 0; phase = FL_DONE; }     // cholesky! threw
+            else {
+                // -------------------------------------------- cx = H^-1 n0 by substitution     src/densesolver.jl:83
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    n0[j] *= Lr[TRI(j, j)];
+#pragma unroll
+                    for (int i = j + 1; i < N; ++i) n0[i] = fma(-Lr[TRI(i, j)], n0[j], n0[i]);
+                }
+#pragma unroll
+                for (int j = N - 1; j >= 0; --j) {
+                    n0[j] *= Lr[TRI(j, j)];
+#pragma unroll
+                    for (int m = 0; m < j; ++m) n0[m] = fma(-Lr[TRI(j, m)], n0[j], n0[m]);
+                }
+                // -------------------------------------------- u = G cx - k2                     :84-85
+#pragma unroll 4
+                for (int r = 0; r < K; ++r) {
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        if (j & 1) a1 = fma(WG(r, j), n0[j], a1); else a0 = fma(WG(r, j), n0[j], a0);
+                    }
+                    SV(D::V_U, r) = (a0 + a1) - SV(D::V_K2, r);
+                }
+
+                if (phase == 0) {
+                    // ---------------------------------------- initial iterate, src/solver.jl:86-101 (max_step: src/mats.jl:1-28)
+#pragma unroll
+                    for (int j = 0; j < N; ++j) SO(D::O_X, j) = n0[j];
+                    double mp = -INFINITY, md = -INFINITY;
+                    for (int i = 0; i < KPOC; ++i) { const double v = SV(D::V_U, i); mp = fmax(mp, v); md = fmax(md, -v); }
+                    for (int c = 0; c < NSOC; ++c) {
+                        const int o = KPOC + c * SDIM;
+                        double sq = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) { const double v = SV(D::V_U, o + e); sq = fma(v, v, sq); }
+                        const double nr = fast_sqrt(sq), z0 = SV(D::V_U, o);
+                        mp = fmax(mp, nr + z0);
+                        md = fmax(md, nr - z0);
+                    }
+                    const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(md) < prm.init_eps);
+                    for (int r = 0; r < K; ++r) { const double z0 = SV(D::V_U, r); SV(D::V_S, r) = -z0; SV(D::V_Z, r) = z0; }
+                    for (int i = 0; i < KPOC; ++i) {
+                        if (shp) SV(D::V_S, i) += 1.0 + mp;
+                        if (shd) SV(D::V_Z, i) += 1.0 + md;
+                    }
+                    for (int c = 0; c < NSOC; ++c) {
+                        const int o = KPOC + c * SDIM;
+                        if (shp) SV(D::V_S, o) += 1.0 + mp;
+                        if (shd) SV(D::V_Z, o) += 1.0 + md;
+                    }
+                    need_top = true;
+                    phase = 1;
+                } else {
+                    // ---------------------------------------- tail of solve_kkt (src/densesolver.jl:86-89), scale!/iscale!
+                    // (src/solver.jl:128-129), scmax of both results (src/mats.jl:53-86); u <- cz, k0 <- cs, dsc <- -(kt2 o kt3)
+                    const bool chk = phase == 2;
+                    double dotacc = 0.0, mx = -INFINITY;
+                    int fl = 0;
+#pragma unroll 2
+                    for (int i = 0; i < KPOC; ++i) {
+                        const double w = SV(D::V_WB, i), iw = SO(D::O_IWB, i), il = fast_rcp(SV(D::V_LAM, i));
+                        const double cz = iw * iw * SV(D::V_U, i);
+                        const double kt3 = w * cz;
+                        const double kk = SV(D::V_K0, i) - kt3;
+                        const double csx = w * kk;
+                        const double kt2 = iw * csx;
+                        mx = fmax(mx, fmax(-kt3 * il, -kt2 * il));
+                        dotacc = fma(kt2, kt3, dotacc);
+                        SV(D::V_U, i) = cz;
+                        SV(D::V_K0, i) = csx;
+                        SV(D::V_DSC, i) = -(kt2 * kt3);
+                        if (chk) fl |= !isfinite(cz) | !isfinite(csx);
+                    }
+#pragma unroll 2
+                    for (int c = 0; c < NSOC; ++c) {
+                        const int o = KPOC + c * SDIM;
+                        const double eta = SO(D::O_CS, 4 * c + 0), ie = SO(D::O_CS, 4 * c + 1), r1w = SO(D::O_CS, 4 * c + 2),
+                                     llt = SO(D::O_CS, 4 * c + 3);
+                        const double ie2 = ie * ie;
+                        double wv[SDIM], lv[SDIM], uv[SDIM], k0v[SDIM], czv[SDIM], csv[SDIM], kt2v[SDIM], kt3v[SDIM];
+#pragma unroll
+                        for (int e = 0; e < SDIM; ++e) {
+                            wv[e] = SV(D::V_WB, o + e); lv[e] = SV(D::V_LAM, o + e);
+                            uv[e] = SV(D::V_U, o + e); k0v[e] = SV(D::V_K0, o + e);
+                        }
+                        const double w0 = wv[0], l0 = lv[0], aa = l0 * l0 - llt;
+                        double qv = w0 * uv[0];                                         // cz = W^-2 u          :86
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) qv = fma(-wv[e], uv[e], qv);
+                        czv[0] = ie2 * (2.0 * w0 * qv - uv[0]);
+                        double dl = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) { czv[e] = ie2 * (uv[e] - 2.0 * wv[e] * qv); dl = fma(wv[e], czv[e], dl); }
+                        double cst = czv[0] + dl * r1w;                                 // kt3 = W cz           :87, solver :128
+                        kt3v[0] = eta * (w0 * czv[0] + dl);
+                        k0v[0] -= kt3v[0];                                              // k0 -= W cz           :88
+                        dl = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) {
+                            kt3v[e] = eta * (czv[e] + cst * wv[e]);
+                            k0v[e] -= kt3v[e];
+                            dl = fma(wv[e], k0v[e], dl);
+                        }
+                        cst = k0v[0] + dl * r1w;                                        // cs = W k0            :89
+                        csv[0] = eta * (w0 * k0v[0] + dl);
+                        dl = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) { csv[e] = eta * (k0v[e] + cst * wv[e]); dl = fma(wv[e], csv[e], dl); }
+                        cst = -csv[0] + dl * r1w;                                       // kt2 = W^-1 cs        solver :129
+                        kt2v[0] = ie * (w0 * csv[0] - dl);
+                        double lx3 = 0.0, lx2 = 0.0, dot = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) {
+                            kt2v[e] = ie * (csv[e] + cst * wv[e]);
+                            lx3 = fma(lv[e], kt3v[e], lx3);
+                            lx2 = fma(lv[e], kt2v[e], lx2);
+                            dot = fma(kt2v[e], kt3v[e], dot);
+                        }
+                        dot += kt2v[0] * kt3v[0];
+                        fl |= !(aa >= 0.0);
+                        const double as = fast_rsqrt(aa);                               // src/mats.jl:67-71
+                        const double r13 = as * l0 * kt3v[0] - as * lx3, r12 = as * l0 * kt2v[0] - as * lx2;   // :74-77
+                        const double den = fast_rcp(as * l0 + 1.0);
+                        const double c3 = (r13 + kt3v[0]) * den, c2 = (r12 + kt2v[0]) * den;      // :80
+                        double q3 = 0.0, q2 = 0.0;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) {
+                            const double v3 = as * (kt3v[e] - c3 * as * lv[e]);         // :83
+                            const double v2 = as * (kt2v[e] - c2 * as * lv[e]);
+                            q3 = fma(v3, v3, q3);
+                            q2 = fma(v2, v2, q2);
+                        }
+                        mx = fmax(mx, fmax(fast_sqrt(q3) - as * r13, fast_sqrt(q2) - as * r12));  // :85
+                        dotacc += dot;
+#pragma unroll
+                        for (int e = 1; e < SDIM; ++e) {
+                            SV(D::V_U, o + e) = czv[e];
+                            SV(D::V_K0, o + e) = csv[e];
+                            SV(D::V_DSC, o + e) = -(kt2v[0] * kt3v[e] + kt3v[0] * kt2v[e]);      // src/vectors.jl:73-75
+                            if (chk) fl |= !isfinite(czv[e]) | !isfinite(csv[e]);
+                        }
+                        SV(D::V_U, o) = czv[0];
+                        SV(D::V_K0, o) = csv[0];
+                        SV(D::V_DSC, o) = -dot;                                         // src/vectors.jl:66-69
+                        if (chk) fl |= !isfinite(czv[0]) | !isfinite(csv[0]);
+                    }
+                    const double tstep = step_from_t(mx);                               // src/solver.jl:130 / :145
+                    if (phase == 1) {
+                        // centering parameter (:130-134) and the combined right-hand side (:136-140)
+                        const double rho = 1.0 - tstep - tstep * tstep * dotacc * fast_rcp(ll);   // :132 (minus: reference quirk)
+                        const double cl = fmax(0.0, fmin(1.0, rho));
+                        const double sig = cl * cl * cl;                                // :133
+                        const double mu = ll / (double)a.deg;                           // :134
+                        if (fl) { status = ST_NUMERICAL; phase = FL_DONE; }
+                        else {
+                            const double smu = sig * mu;
+                            sc = 1.0 - sig;                                             // :136
+                            for (int i = 0; i < KPOC; ++i) SV(D::V_DSC, i) += smu;      // :137-139
+                            for (int c = 0; c < NSOC; ++c) SV(D::V_DSC, KPOC + c * SDIM) += smu;
+                            phase = 2;
+                        }
+                    } else {
+                        // step length (:143-146), iterate update (:147-150)
+                        const double step = tstep * prm.step_damp;
+#pragma unroll
+                        for (int j = 0; j < N; ++j) fl |= !isfinite(n0[j]);
+                        fl |= !isfinite(step);
+                        if (fl) { status = ST_NUMERICAL; phase = FL_DONE; }
+                        else {
+#pragma unroll
+                            for (int j = 0; j < N; ++j) SO(D::O_X, j) = fma(n0[j], step, SO(D::O_X, j));      // :147
+#pragma unroll 4
+                            for (int r = 0; r < K; ++r) {
+                                SV(D::V_Z, r) = fma(SV(D::V_U, r), step, SV(D::V_Z, r));                     // :149
+                                SV(D::V_S, r) = fma(SV(D::V_K0, r), step, SV(D::V_S, r));                    // :150
+                            }
+                            ++iters;
+                            need_top = true;
+                            phase = 1;
+                        }
+                    }
+                }
+            }
+        }
+        fslot = !fslot;
+    }
+#undef SV
+#undef SO
+#undef WG
+#undef WO
+#undef TRI
+}
+
+// grid and per-warp lane cap of a launch over `batch` problems: a small batch is spread over the SMs instead of
+// filling the first CTAs
+inline void fl_grid(const FLPlan& plan, int batch, int lpw, int& grid, int& cap) {
+    const int nwarp = FL_PROBLEMS_PER_SM / lpw;
+    grid = std::max(1, std::min(plan.num_sms, (batch + FL_PROBLEMS_PER_SM - 1) / FL_PROBLEMS_PER_SM));
+    cap = std::min(lpw, (batch + grid * nwarp - 1) / (grid * nwarp));
+}
+
+#ifndef SOCP_SIMT_EMU
+template <class D, int LPW>
+inline void fused_lane_launch(const FLPlan& plan, FLArgs args, cudaStream_t stream) {
+    int grid;
+    fl_grid(plan, args.batch, LPW, grid, args.cap);
+    cudaFuncSetAttribute(k_fused_lane<D, LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    k_fused_lane<D, LPW><<<grid, (FL_PROBLEMS_PER_SM / LPW) * 32, plan.smem, stream>>>(args);
+}
+
+// Solves problems [first, first + batch) of the shard.  ws_set: which workspace set / counter this launch uses
+// (launches that may overlap need different ones).
+void solve_fused_lane_ext(FLPlan& plan, const Ws& g, int first, int batch, const LoopParams& lp, cudaStream_t stream,
+                          int ws_set);
+#endif
+
+}  // namespace socp

@@ -6,6 +6,7 @@
 #include "tiled_kernels.cuh"
 #include "fused_v2.cuh"
 #include "fused_v3.cuh"
+#include "fused_lane.cuh"
 #include "cone_batch.cuh"
 #include "panel_mma.cuh"
 #include "syrk_tma.cuh"
@@ -78,6 +79,8 @@ struct Shard {
     F2Plan fused2{};
     // second-generation whole-solve kernel (fused_v3.cuh): planned per data set, from the row pattern of G
     F3Plan fused3{};
+    // lane-per-problem whole-solve kernel (fused_lane.cuh): tiny problems, large batches
+    FLPlan lane{};
     bool f3_planned = false;     // fused3 belongs to the data now resident
     bool f3_dense = false;       // ... and was planned with every row dense (fallback after a pattern violation)
     int* d_f3_tables = nullptr;  // capacity 2k + n + 1 ints
@@ -530,6 +533,13 @@ void build_shard(socp_handle* h, Shard& sh) {
     f2_plan(sh.fused2, n, p, k, h->kind, h->offs, h->dim, sh.device);
     sh.fused2.d_counter = sh.alloc<int>(16);
     sh.fused2.d_clk = sh.alloc<unsigned long long>(32);
+    {
+        int dev_smem = 0, sms = 148;
+        CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, sh.device));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+        fl_plan(sh.lane, n, p, k, h->kind, h->offs, h->dim, dev_smem, sms);
+        sh.lane.d_counter = sh.alloc<int>(FL_WS_SETS);
+    }
     sh.d_f3_tables = sh.alloc<int>((size_t)2 * k + n + 2);
     sh.d_rowcol = sh.alloc<int>(k);
     sh.d_npattern = sh.alloc<int>(1);
@@ -735,7 +745,19 @@ F3Glob f3_glob(const Shard& sh) {
     return g;
 }
 
-enum { FUSED_NONE = 0, FUSED_V2 = 2, FUSED_V3 = 3 };
+enum { FUSED_NONE = 0, FUSED_V2 = 2, FUSED_V3 = 3, FUSED_LANE = 4 };
+
+// The lane-per-problem kernel keeps 64 problems per SM in flight and a problem takes about as long as on a one-warp
+// team of fused_v2 (12 per SM): it pays from about two waves of fused_v2 teams on.  SOCP_B200_LANE=0 / 1 switches it
+// off / on regardless of the batch size (tests, experiments).
+bool lane_wanted(const Shard& sh, int batch) {
+    if (!sh.lane.fits) return false;
+    if (const char* e = getenv("SOCP_B200_LANE")) return atoi(e) != 0;
+    return batch >= 2 * sh.fused2.num_sms * sh.fused2.ctas_per_sm;
+}
+void ensure_lane_ws(Shard& sh) {
+    if (!sh.lane.d_ws) sh.lane.d_ws = sh.alloc<double>(sh.lane.ws_doubles * FL_WS_SETS, false);
+}
 
 // which whole-solve kernel can take the data now resident (plans fused_v3 on first use)
 int fused_kind(const socp_handle* h, Shard& sh) {
@@ -746,7 +768,7 @@ int fused_kind(const socp_handle* h, Shard& sh) {
     if (sh.fused2.fits) {
         if (!sh.sing_known) ensure_prepared(sh);       // fused_v2 cannot take sing problems: the flags must be known
         if (!sh.prepared) ensure_prepared(sh);
-        if (!sh.any_sing) return FUSED_V2;
+        if (!sh.any_sing) return lane_wanted(sh, sh.batch) ? FUSED_LANE : FUSED_V2;
     }
     return FUSED_NONE;
 }
@@ -775,6 +797,14 @@ void run_solve(const socp_handle* h, Shard& sh, const socp_params& prm) {
         solve_fused3_ext(sh.fused3, f3_glob(sh), 0, sh.batch, lp, detect ? 1 : 0, 0, sh.stream, allow_static, 0);
         CK(cudaGetLastError());
         if (detect) { sh.sing_known = true; sh.prepared = false; }      // the kernel left the flags in d_sing
+        sh.launches += 1;
+        sh.tim.path_used = SOCP_PATH_FUSED;
+        sh.tim.iterations_max = -1;
+    } else if (path == SOCP_PATH_FUSED && kind == FUSED_LANE) {
+        ensure_lane_ws(sh);
+        CK(cudaEventRecord(sh.ev[0], sh.stream));
+        solve_fused_lane_ext(sh.lane, sh.w, 0, sh.batch, LoopParams{prm.max_iter, prm.tol, prm.step_damp, prm.init_eps}, sh.stream, 0);
+        CK(cudaGetLastError());
         sh.launches += 1;
         sh.tim.path_used = SOCP_PATH_FUSED;
         sh.tim.iterations_max = -1;
@@ -877,6 +907,8 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
         CK(cudaStreamCreateWithFlags(&sh.alt_stream, cudaStreamNonBlocking));
     }
     const bool v3 = f3_candidate(h);
+    const bool lane = !v3 && lane_wanted(sh, B);
+    if (lane) ensure_lane_ws(sh);
     sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
     sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
     sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;
@@ -890,7 +922,8 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     // Chunk boundaries: two short chunks first (one wave of resident CTAs, then two: PCIe delivers problems about
     // twice as fast as the kernel retires them, so the upload of each next chunk ends before the previous one is
     // solved) so that the solve starts as soon as possible, then up to 8 equal chunks of at least 4 waves each.
-    const int slots = v3 ? sh.fused2.num_sms * 4 : sh.fused2.num_sms * sh.fused2.ctas_per_sm;
+    const int slots = v3 ? sh.fused2.num_sms * 4
+                         : (lane ? sh.lane.num_sms * FL_PROBLEMS_PER_SM : sh.fused2.num_sms * sh.fused2.ctas_per_sm);
     std::vector<int> bounds{0};
     if (B > 8 * slots) { bounds.push_back(slots); bounds.push_back(3 * slots); }
     {
@@ -998,6 +1031,8 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
                 }
             }
             solve_fused3_ext(sh.fused3, f3_glob(sh), lo, cb, lp, sing ? 0 : 1, ci > 0 && !sh.sharedG && !csc ? 1 : 0, cs, allow_static, ci & 15);
+        } else if (lane) {
+            solve_fused_lane_ext(sh.lane, sh.w, lo, cb, lp, cs, ci);      // adjacent chunks may overlap: alternate workspace sets
         } else {
             solve_fused2_ext(sh.fused2, sh.w, lo, cb, prm.max_iter, prm.tol, prm.step_damp, prm.init_eps, cs, allow_static, ci & 15);
         }

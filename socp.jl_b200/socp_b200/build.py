@@ -20,6 +20,7 @@ UNITS = {
     "fused2.cu": ["common.cuh", "fused_common.cuh", "fused_v2.cuh"],
     "fused3.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
     "fused3_dyn.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
+    "fused_lane.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh"],
     "syrk_tma.cu": ["common.cuh", "syrk_tma.cuh"],
 }
 

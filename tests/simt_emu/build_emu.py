@@ -12,8 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "socp.jl_b200", "csrc")
 OUT_DIR = os.path.join(ROOT, "tests", "_build")
 OUT = os.path.join(OUT_DIR, "libsocp_emu.so")
-DEPS = [os.path.join(HERE, f) for f in ("emu_fused3.cpp", "simt_emu.h")] + \
-       [os.path.join(CSRC, f) for f in ("common.cuh", "fused_common.cuh", "fused_v3.cuh")]
+SRCS = [os.path.join(HERE, f) for f in ("emu_fused3.cpp", "emu_fused_lane.cpp")]
+DEPS = SRCS + [os.path.join(HERE, "simt_emu.h")] + \
+       [os.path.join(CSRC, f) for f in ("common.cuh", "fused_common.cuh", "fused_v3.cuh", "fused_lane.cuh")]
 
 
 def build(force: bool = False) -> str:
@@ -21,7 +22,7 @@ def build(force: bool = False) -> str:
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     cmd = ["g++", "-O2", "-g", "-std=c++17", "-DSOCP_SIMT_EMU", "-I" + HERE, "-I" + CSRC, "-shared", "-fPIC",
-           "-o", OUT, os.path.join(HERE, "emu_fused3.cpp")]
+           "-o", OUT] + SRCS
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

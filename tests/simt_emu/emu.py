@@ -88,3 +88,27 @@ def solve(c, A_cm, b, G_cm, h, cones, sing=None, rowcol=None, generic=False, sin
         out["dbg"] = dict(s=take(k), z=take(k), H=take(n * n).reshape(n, n).T, dx=take(n), dy=take(p), dz=take(k),
                           ds=take(k), cx=take(n), cy=take(p), cz=take(k), cs=take(k))
     return out
+
+
+def solve_lane(c, G_cm, h, cones, lpw=8, order=0, grid_cap=0, max_iter=40, tol=1e-5, step_damp=0.99, init_eps=1e-10,
+               shared_G=False):
+    """The lane-per-problem kernel k_fused_lane (socp.jl_b200/csrc/fused_lane.cuh) on the emulator; p = 0 layouts."""
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    B, n = c.shape
+    kind = np.array([cn[0] for cn in cones], dtype=np.int32)
+    offs = np.array([cn[1] for cn in cones], dtype=np.int32)
+    dim = np.array([cn[2] for cn in cones], dtype=np.int32)
+    k = int(dim.sum())
+    G_cm = np.ascontiguousarray(G_cm, dtype=np.float64)
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    x, z, s = np.zeros((B, n)), np.zeros((B, k)), np.zeros((B, k))
+    status, iters = np.full(B, -99, dtype=np.int32), np.zeros(B, dtype=np.int32)
+    pobj, dobj = np.zeros(B), np.zeros(B)
+    f = lib().emu_fused_lane_solve
+    f.restype = C.c_int
+    r = f(n, k, len(cones), _i(kind), _i(offs), _i(dim), B, _d(c), _d(G_cm), C.c_int64(0 if shared_G else k * n), _d(h),
+          lpw, order, grid_cap, max_iter, C.c_double(tol), C.c_double(step_damp), C.c_double(init_eps), _d(x), _d(z),
+          _d(s), _i(status), _i(iters), _d(pobj), _d(dobj))
+    if r != 0:
+        raise RuntimeError("no lane-per-problem instantiation takes this layout")
+    return dict(x=x, y=np.zeros((B, 0)), z=z, s=s, status=status, iters=iters, pobj=pobj, dobj=dobj)

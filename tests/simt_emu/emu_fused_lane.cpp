@@ -1,0 +1,52 @@
+// emu_fused_lane.cpp -- host build of the lane-per-problem whole-solve kernel k_fused_lane
+// (socp.jl_b200/csrc/fused_lane.cuh) against the SIMT emulator.  TEST INFRASTRUCTURE ONLY (see emu_fused3.cpp).
+#define SOCP_SIMT_EMU 1
+#include "fused_lane.cuh"
+
+#include <vector>
+
+using namespace socp;
+
+template <class D, int LPW>
+static void run(const FLPlan& P, FLArgs a, int grid_cap, int order) {
+    int grid;
+    fl_grid(P, a.batch, LPW, grid, a.cap);
+    if (grid_cap > 0) grid = std::min(grid, grid_cap);
+    std::vector<double> ws((size_t)D::WS_PER_LANE * FL_PROBLEMS_PER_SM * grid, std::nan(""));
+    a.ws = ws.data();
+    simt_emu::LaunchCfg cfg;
+    cfg.grid = (unsigned)grid;
+    cfg.block = (FL_PROBLEMS_PER_SM / LPW) * 32;
+    cfg.smem = P.smem;
+    cfg.order = order;
+    simt_emu::launch(cfg, [&]() { k_fused_lane<D, LPW>(a); });
+}
+
+// Returns 0, -1 when no instantiation takes the layout.  grid_cap > 0 limits the number of CTAs (more problems per lane).
+extern "C" int emu_fused_lane_solve(int n, int k, int ncones, const int* kind, const int* offs, const int* dim, int batch,
+                                    const double* c, const double* G, int64_t sG, const double* h, int lpw, int order,
+                                    int grid_cap, int max_iter, double tol, double damp, double init_eps, double* x,
+                                    double* z, double* s, int* status, int* iters, double* pobj, double* dobj) {
+    FLPlan P;
+    fl_plan(P, n, 0, k, std::vector<int>(kind, kind + ncones), std::vector<int>(offs, offs + ncones),
+            std::vector<int>(dim, dim + ncones), 227 * 1024, 148);
+    if (!P.fits) return -1;
+    int counter = 0;
+    std::vector<int> active(batch, 1), fail(batch, 0);
+    FLArgs a;
+    a.c = c; a.G = G; a.h = h; a.sG = sG;
+    a.x = x; a.z = z; a.s = s; a.pobj = pobj; a.dobj = dobj;
+    a.status = status; a.iters = iters; a.active = active.data(); a.fail = fail.data();
+    a.ws = nullptr; a.counter = &counter;
+    a.first = 0; a.batch = batch; a.cap = 0; a.deg = P.deg;
+    a.prm = LoopParams{max_iter, tol, damp, init_eps};
+#define FL_RUN(D)                                              \
+    switch (lpw) {                                             \
+        case 32: run<D, 32>(P, a, grid_cap, order); break;     \
+        case 16: run<D, 16>(P, a, grid_cap, order); break;     \
+        case 4: run<D, 4>(P, a, grid_cap, order); break;       \
+        default: run<D, 8>(P, a, grid_cap, order); break;      \
+    }
+    if (P.shape == 1) { FL_RUN(LaneC3) } else { FL_RUN(LaneT1) }
+    return 0;
+}

@@ -154,6 +154,9 @@ struct Tramp {
         Thread* t = cur_thread();
         t->done = true;
         t->blk->progress++;
+        // a thread that has returned no longer takes part in the warp's collectives (kernels that retire lanes early)
+        Warp& w = t->blk->warps[t->warp];
+        if (--w.nlanes > 0 && w.bar_cnt == w.nlanes) { w.bar_cnt = 0; w.bar_gen++; }
         swapcontext(&t->ctx, &t->blk->sched);
     }
 };

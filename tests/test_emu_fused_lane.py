@@ -1,0 +1,84 @@
+"""The lane-per-problem whole-solve kernel k_fused_lane (socp.jl_b200/csrc/fused_lane.cuh: tiny problems, BASELINE.json
+C3) run on the SIMT emulator (tests/simt_emu/) and compared with the C oracle -- CPU-side coverage of the kernel's
+logic: every lanes-per-warp variant, lanes that take several problems one after the other (work queue, cooperative
+problem copy, the F / N slot alternation with lanes out of phase), a layout with a positive-orthant block, the
+iteration cap, infeasible data.  The emulator is test infrastructure; the product path is the CUDA build."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "simt_emu"))
+import emu  # noqa: E402
+import socp_b200 as sb  # noqa: E402
+from socp_b200 import generators as gen  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+
+oc = lambda cones: tuple((c.kind, c.offs, c.dim) for c in cones)
+rel = lambda a, b: np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+def check(prob, res, max_iter=40, tol_obj=1e-8, tol_x=1e-6):
+    B = prob.c.shape[0]
+    ref = co.solve_batch(prob.c, prob.A_cm, prob.b, prob.G_cm, prob.h, oc(prob.cones), sing=np.zeros(B, dtype=np.uint8),
+                         nthreads=4, max_iter=max_iter)
+    assert (res["status"] == ref["status"]).all(), (res["status"], ref["status"])
+    assert np.all(np.abs(res["iters"].astype(int) - ref["iters"].astype(int)) <= 1)
+    same = res["iters"] == ref["iters"]
+    assert same.sum() >= B - max(1, B // 10), (res["iters"], ref["iters"])
+    conv = same & (ref["status"] == sb.STATUS_CONVERGED)
+    cmp = conv if conv.any() else same          # iteration cap: compare the iterate the cap stopped at
+    d = np.maximum(rel(res["pobj"][cmp], ref["pobj"][cmp]), rel(res["dobj"][cmp], ref["dobj"][cmp]))
+    assert d.max() <= tol_obj, d.max()
+    assert np.abs(res["x"][cmp] - ref["x"][cmp]).max() <= tol_x
+    return ref
+
+
+@pytest.mark.parametrize("lpw", [4, 8, 16, 32])
+def test_c3_vs_c_oracle(lpw):
+    prob = gen.make_config("C3", batch=40)
+    res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=lpw)
+    check(prob, res)
+
+
+@pytest.mark.parametrize("lpw,order", [(8, 1), (16, 2)])
+def test_c3_lanes_take_several_problems(lpw, order):
+    """One CTA for 200 problems: every lane works through ~3 problems with different iteration counts, so lanes of a
+    warp sit in different phases (initial point next to affine directions, idle N slots); any schedule, same bits."""
+    prob = gen.make_config("C3", batch=200)
+    res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=lpw, grid_cap=1, order=order)
+    check(prob, res)
+    ref = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=32, grid_cap=0, order=0)
+    for key in ("x", "z", "s", "pobj", "dobj", "iters", "status"):
+        assert np.array_equal(res[key], ref[key]), key          # a problem's arithmetic does not depend on its lane
+
+
+def test_mixed_layout_with_orthant_block():
+    cones = [sb.POC(0, 5)] + [sb.SOC(5 + 3 * i, 3) for i in range(3)]
+    prob = gen.random_feasible(70, 6, 0, cones, 0.3, 0, 11)
+    res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=8, grid_cap=1)
+    # randomly generated mixed-cone family: the two oracles themselves differ by > 1e-8 on some of these problems
+    # (error growth ~1e3 per iteration near the end, see tests/test_emu_fused3.py::check_vs_c_oracle)
+    check(prob, res, tol_obj=1e-6, tol_x=1e-4)
+
+
+def test_iteration_cap_and_unknown_layout():
+    prob = gen.make_config("C3", batch=12)
+    res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=8, max_iter=3)
+    assert (res["status"] == sb.STATUS_MAXITER).all() and (res["iters"] == 3).all()
+    check(prob, res, max_iter=3)
+    other = gen.random_feasible(4, 12, 0, gen.soc_cones(8, 5), 0.3, 0, 3)
+    with pytest.raises(RuntimeError):
+        emu.solve_lane(other.c, other.G_cm, other.h, oc(other.cones))
+
+
+def test_rank_deficient_G_is_reported():
+    """G with a zero column: the initial factorisation fails (the reference's cholesky! throws) -> NUMERICAL, zeros."""
+    prob = gen.make_config("C3", batch=9)
+    G = prob.G_cm.copy().reshape(9, 12, 40)
+    G[4, 7, :] = 0.0
+    res = emu.solve_lane(prob.c, G.reshape(9, -1), prob.h, oc(prob.cones), lpw=8)
+    assert res["status"][4] == sb.STATUS_NUMERICAL and not res["x"][4].any()
+    assert (np.delete(res["status"], 4) == sb.STATUS_CONVERGED).all()

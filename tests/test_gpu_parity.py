@@ -678,3 +678,58 @@ def test_pattern_violation_in_a_later_chunk_falls_back():
     ref = so.solve_socp(pr, init="reduced", fast_iprod=True)
     assert ref.status == one.status[4100] and abs(ref.iters - int(one.iters[4100])) <= 1
     assert abs(ref.pobj - one.pobj[4100]) <= 1e-8 * max(1.0, abs(ref.pobj))
+
+
+# ---------------------------------------------------------------- lane-per-problem kernel (fused_lane.cuh)
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("lpw", ["8", "16", "32"])
+def test_lane_kernel_c3_vs_oracle_and_one_warp_kernel(lpw):
+    """C3 layout, 3000 problems (~20 per SM: lanes take problems one after the other through the work queue): the
+    lane-per-problem kernel against the numpy oracle on a sample and against fused_v2's one-warp teams on everything."""
+    prob = gen.make_config("C3", batch=3000)
+    run = lambda: sb.solve_socp_batch(prob, sb.SolverState(prob))
+    res = _with_env("SOCP_B200_LANE", "1", lambda: _with_env("SOCP_B200_LANE_LPW", lpw, run))
+    old = _with_env("SOCP_B200_LANE", "0", run)
+    assert res.timings["path_used"] == sb.PATH_FUSED
+    assert (res.status == sb.STATUS_CONVERGED).all()
+    _check_batch(prob, res, range(0, 3000, 100))
+    assert np.array_equal(res.status, old.status)
+    assert np.all(np.abs(res.iters.astype(int) - old.iters.astype(int)) <= 1)
+    same = res.iters == old.iters
+    assert same.mean() > 0.99
+    rel = lambda a, b: np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    d = np.maximum(rel(res.pobj[same], old.pobj[same]), rel(res.dobj[same], old.dobj[same]))
+    assert d.max() <= 1e-7 and (d <= 1e-8).mean() >= 0.99, (d.max(), (d <= 1e-8).mean())
+
+
+def test_lane_kernel_orthant_block_small_batch_and_solve_host():
+    """The second instantiation (orthant block + three SOC(3)), a batch smaller than one CTA's lanes, and the
+    pipelined one-shot entry (chunks on alternating streams use alternating workspace sets)."""
+    cones = [sb.POC(0, 5)] + [sb.SOC(5 + 3 * i, 3) for i in range(3)]
+    prob = gen.random_feasible(37, 6, 0, cones, 0.3, 0, 11)
+    res = _with_env("SOCP_B200_LANE", "1", lambda: sb.solve_socp_batch(prob, sb.SolverState(prob)))
+    old = _with_env("SOCP_B200_LANE", "0", lambda: sb.solve_socp_batch(prob, sb.SolverState(prob)))
+    assert np.array_equal(res.status, old.status)
+    same = res.iters == old.iters
+    assert same.sum() >= 33
+    assert np.max(np.abs(res.pobj[same] - old.pobj[same]) / np.maximum(1.0, np.abs(old.pobj[same]))) <= 1e-6
+    big = gen.make_config("C3", batch=90000)
+    one_shot = sb.solve_socp_batch(big, sb.SolverState(big))          # socp_b200_solve_host: 3 chunks
+    assert one_shot.timings["kernel_launches"] >= 2
+    ss2 = sb.SolverState(big)
+    ss2.load(big)
+    two_step = sb.solve_socp_batch(big, ss2, reload=False)             # set_data + solve: one launch
+    for key in ("status", "iters", "pobj", "dobj", "x", "z", "s"):
+        assert np.array_equal(getattr(one_shot, key), getattr(two_step, key)), key
