@@ -42,16 +42,22 @@ struct LaneDims {
     static constexpr int N = N_, KPOC = KPOC_, NSOC = NSOC_, SDIM = SDIM_;
     static constexpr int K = KPOC_ + NSOC_ * SDIM_;
     static constexpr int NH = N_ * (N_ + 1) / 2;
-    // shared memory, doubles per lane: k-vectors, then iwb (orthant rows), cone scalars, x, dx
-    enum { V_S = 0, V_Z, V_LAM, V_WB, V_DZ, V_DSC, V_K0, V_K2, V_U, NVEC };
+    static constexpr int NP = (N_ + 1) / 2 * 2;           // row stride of G in the workspace (rows are runs of double2)
+    static constexpr int RS = (K % 2 == 0) ? 2 : 1;       // rows per stage of the G ring
+    static constexpr int NS = 5;                          // stages of the G ring
+    // shared memory, doubles per lane: k-vectors, then iwb (orthant rows), cone scalars; then the lane's slice of the
+    // ring that G streams through (RS * NS rows of NP doubles)
+    enum { V_S = 0, V_Z, V_LAM, V_WB, V_K0, V_K2, V_U, NVEC };
     static constexpr int O_IWB = NVEC * K;
     static constexpr int O_CS = O_IWB + KPOC_;            // 4 per cone: eta, 1/eta, 1/(1+w0), |lam_1|^2
-    static constexpr int O_X = O_CS + 4 * NSOC_;
-    static constexpr int O_DX = O_X + N_;
-    static constexpr int SM_PER_LANE = O_DX + N_;
-    // global workspace, doubles per lane: G (row-major k x n), h, c, the packed factor
-    static constexpr int W_G = 0, W_H = K * N_, W_C = W_H + K, W_L = W_C + N_;
-    static constexpr int WS_PER_LANE = W_L + NH;
+    static constexpr int SM_STATE = O_CS + 4 * NSOC_;
+    static constexpr int SM_RING = RS * NS * NP;
+    static constexpr int SM_PER_LANE = SM_STATE + SM_RING;
+    // global workspace (L2 resident), doubles per lane: G (row-major k x NP, as double2 pairs), h, c, the packed factor,
+    // and the vectors touched once or twice per slot: x, dx, dz, the corrector term of ds
+    static constexpr int W_G = 0, W_H = K * NP, W_C = W_H + K, W_L = W_C + N_, W_X = W_L + NH, W_DX = W_X + N_,
+                         W_DZ = W_DX + N_, W_DSC = W_DZ + K;
+    static constexpr int WS_PER_LANE = W_DSC + K;
     static bool matches(int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
                         const std::vector<int>& dim) {
         if (n != N || p != 0 || k != K) return false;
@@ -78,7 +84,7 @@ constexpr int FL_WS_SETS = 2;               // launches that may overlap use dif
 struct FLPlan {
     bool fits = false;
     int shape = 0;          // 1: LaneC3, 2: LaneT1
-    int lpw = 8;            // lanes in use per warp
+    int lpw = 16;           // lanes in use per warp (measured on C3: 16 > 32 > 8, profiles/)
     int num_sms = 148;
     int deg = 0;
     size_t smem = 0;
@@ -134,12 +140,83 @@ inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 #define FL_SMEM() fl_sm
 #endif
 
+// 16-byte asynchronous copy global -> shared (LDGSTS): no registers in between, completion by commit groups
+__device__ __forceinline__ void fl_cp16(double2* dst, const double2* src) {
+#ifdef SOCP_SIMT_EMU
+    *dst = *src;
+#else
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void fl_commit() {
+#ifndef SOCP_SIMT_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void fl_wait() {
+#ifndef SOCP_SIMT_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+// block `blk` (RS rows) of this lane's G into stage blk % NS of its ring slice
+template <int NQ, int LPW, int RS, int NS>
+__device__ __forceinline__ void fl_ring_issue(const double2* __restrict__ G2, double2* ring, int blk, int stage) {
+#pragma unroll
+    for (int i = 0; i < RS; ++i)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) fl_cp16(ring + ((stage * RS + i) * NQ + q) * LPW, G2 + ((blk * RS + i) * NQ + q) * LPW);
+}
+// the first NS - 1 blocks of a pass: issued as early as possible (right after the previous pass) so that their latency
+// hides behind whatever runs between the passes
+template <int K, int NP, int LPW, int RS, int NS>
+__device__ __forceinline__ void fl_ring_prime(const double2* __restrict__ G2, double2* ring) {
+    constexpr int NQ = NP / 2, NBLK = K / RS;
+#pragma unroll
+    for (int blk = 0; blk < NS - 1; ++blk) {
+        if (blk < NBLK) fl_ring_issue<NQ, LPW, RS, NS>(G2, ring, blk, blk);
+        fl_commit();
+    }
+}
+// Streams the K rows of this lane's G (double2 pairs, element q of row r at G2[(r * NQ + q) * LPW]) through the lane's
+// slice of a shared-memory ring (NS stages of RS rows, cp.async): up to NS - 1 stages are in flight while f(r, g) runs
+// on the rows of the current one -- a lane has nobody to hide its L2 latency behind (one or two warps per SM
+// sub-partition), and the ring costs no registers (H alone takes 156 of the 255).  The ring slice is private to the
+// lane, so there is no synchronisation with other lanes.  The ring is primed on entry (by the previous pass, or by
+// the lane when it took its problem) and primed again on exit.
+template <int K, int NP, int LPW, int RS, int NS, class F>
+__device__ __forceinline__ void fl_stream_rows(const double2* __restrict__ G2, double2* ring, F f) {
+    static_assert(K % RS == 0, "stages must tile the rows");
+    constexpr int NQ = NP / 2, NBLK = K / RS;
+    int stage = 0, nstage = NS - 1;
+#pragma unroll 1
+    for (int blk = 0; blk < NBLK; ++blk) {
+        if (blk + NS - 1 < NBLK) fl_ring_issue<NQ, LPW, RS, NS>(G2, ring, blk + NS - 1, nstage);
+        fl_commit();
+        fl_wait<NS - 1>();
+#pragma unroll
+        for (int i = 0; i < RS; ++i) {
+            double g[NP];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double2 v = ring[((stage * RS + i) * NQ + q) * LPW];
+                g[2 * q] = v.x; g[2 * q + 1] = v.y;
+            }
+            f(blk * RS + i, g);
+        }
+        stage = stage + 1 == NS ? 0 : stage + 1;
+        nstage = nstage + 1 == NS ? 0 : nstage + 1;
+    }
+    fl_ring_prime<K, NP, LPW, RS, NS>(G2, ring);      // every pass starts at row 0: the next one is on its way
+}
+
 template <class D, int LPW>
 __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_lane(const FLArgs a) {
 #ifndef SOCP_SIMT_EMU
     extern __shared__ __align__(16) double fl_sm[];
 #endif
-    constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NSOC = D::NSOC, SDIM = D::SDIM, NH = D::NH;
+    constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NSOC = D::NSOC, SDIM = D::SDIM, NH = D::NH, NP = D::NP, RS = D::RS, NS = D::NS;
     constexpr unsigned MASK = LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u);
     constexpr int NWARP = FL_PROBLEMS_PER_SM / LPW;
     const int tid = (int)(unsigned)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -148,10 +225,11 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
     double* const S = FL_SMEM() + (size_t)warp * D::SM_PER_LANE * LPW + lane;
     double* const Wb = a.ws + (size_t)gwarp * D::WS_PER_LANE * LPW;
     double* const W = Wb + lane;
+    const double2* const G2 = reinterpret_cast<const double2*>(Wb) + lane;
+    double2* const ring = reinterpret_cast<double2*>(S - lane + D::SM_STATE * LPW) + lane;
     const LoopParams prm = a.prm;
 #define SV(v, i) S[((v) * K + (i)) * LPW]
 #define SO(o, i) S[((o) + (i)) * LPW]
-#define WG(r, j) W[((r) * N + (j)) * LPW]
 #define WO(o, i) W[((o) + (i)) * LPW]
 #define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
@@ -226,24 +304,20 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                     // negated residuals (:110-118, :125) in one pass over G: dx = -G'z - c, dz = -G x - s + h
                     double rx[N], xr[N];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) { rx[j] = -WO(D::W_C, j); xr[j] = SO(D::O_X, j); }
-#pragma unroll 4
-                    for (int r = 0; r < K; ++r) {
+                    for (int j = 0; j < N; ++j) { rx[j] = -WO(D::W_C, j); xr[j] = WO(D::W_X, j); }
+                    fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
                         const double zr = SV(D::V_Z, r);
-                        double g[N];
-#pragma unroll
-                        for (int j = 0; j < N; ++j) g[j] = WG(r, j);
                         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
                             rx[j] = fma(-g[j], zr, rx[j]);
                             if (j & 1) a1 = fma(g[j], xr[j], a1); else a0 = fma(g[j], xr[j], a0);
                         }
-                        SV(D::V_DZ, r) = -(a0 + a1) - SV(D::V_S, r) + WO(D::W_H, r);
-                    }
+                        WO(D::W_DZ, r) = -(a0 + a1) - SV(D::V_S, r) + WO(D::W_H, r);
+                    });
                     double rxn = 0.0;
 #pragma unroll
-                    for (int j = 0; j < N; ++j) { rxn = fma(rx[j], rx[j], rxn); SO(D::O_DX, j) = rx[j]; }
+                    for (int j = 0; j < N; ++j) { rxn = fma(rx[j], rx[j], rxn); WO(D::W_DX, j) = rx[j]; }
                     if (fl) { status = ST_NUMERICAL; phase = FL_DONE; }                 // compute_scaling threw
                     else if (sqrt(rxn) + gap < prm.tol) { status = ST_CONVERGED; phase = FL_DONE; }   // :122-124 (p = 0)
                     else { ll = llacc; sc = 1.0; }
@@ -252,11 +326,13 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
             // ------------------------------------------------ a finished problem: iterate and objectives
             if (phase == FL_DONE) {
                 double po = 0.0, dob = 0.0;
+#pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const double xj = dead ? 0.0 : SO(D::O_X, j);
+                    const double xj = dead ? 0.0 : WO(D::W_X, j);
                     a.x[(int64_t)b * N + j] = xj;
                     po = fma(WO(D::W_C, j), xj, po);
                 }
+#pragma unroll 8
                 for (int r = 0; r < K; ++r) {
                     const double zr = dead ? 0.0 : SV(D::V_Z, r);
                     a.z[(int64_t)b * K + r] = zr;
@@ -292,15 +368,44 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         const int64_t gb = (int64_t)a.first + pb;
                         const double* Gg = a.G + gb * a.sG;
                         double* Wl = Wb + l;
-                        for (int e = lane; e < K * N; e += LPW) {
-                            const int j = e / K, r = e - j * K;
-                            Wl[(r * N + j) * LPW] = Gg[e];
+                        // all the loads of a batch are issued before its first store: one memory latency per batch,
+                        // not one per element (the other lanes of the warp wait for this copy)
+                        constexpr int CH = 16, NHC = (K + N + LPW - 1) / LPW;
+                        double hc[NHC];
+#pragma unroll
+                        for (int i = 0; i < NHC; ++i) {
+                            const int e = i * LPW + lane;
+                            hc[i] = e < K ? a.h[gb * K + e] : (e < K + N ? a.c[gb * N + (e - K)] : 0.0);
                         }
-                        for (int e = lane; e < K; e += LPW) Wl[(D::W_H + e) * LPW] = a.h[gb * K + e];
-                        for (int e = lane; e < N; e += LPW) Wl[(D::W_C + e) * LPW] = a.c[gb * N + e];
+#pragma unroll 1
+                        for (int e0 = 0; e0 < K * N; e0 += CH * LPW) {
+                            double t[CH];
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                const int e = e0 + i * LPW + lane;
+                                t[i] = e < K * N ? Gg[e] : 0.0;
+                            }
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                const int e = e0 + i * LPW + lane;
+                                const int j = e / K, r = e - j * K;
+                                if (e < K * N) Wb[((r * (NP / 2) + (j >> 1)) * LPW + l) * 2 + (j & 1)] = t[i];
+                            }
+                        }
+                        if (NP != N)
+                            for (int r = lane; r < K; r += LPW) Wb[((r * (NP / 2) + (N >> 1)) * LPW + l) * 2 + 1] = 0.0;
+#pragma unroll
+                        for (int i = 0; i < NHC; ++i) {
+                            const int e = i * LPW + lane;
+                            if (e < K + N) Wl[(D::W_H + e) * LPW] = hc[i];      // h, then c (W_C = W_H + K)
+                        }
                     }
                     __syncwarp(MASK);
-                    if (myb >= 0) { b = a.first + myb; phase = 0; iters = 0; status = ST_RUNNING; need_top = false; dead = false; }
+                    if (myb >= 0) {
+                        b = a.first + myb; phase = 0; iters = 0; status = ST_RUNNING; need_top = false; dead = false;
+                        fl_wait<0>();                                   // whatever the previous problem left in flight
+                        fl_ring_prime<K, NP, LPW, RS, NS>(G2, ring);
+                    }
                 }
             }
             if (!__ballot_sync(MASK, phase != FL_FREE)) break;
@@ -311,6 +416,7 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
             // ------------------------------------------------ head of solve_kkt, src/densesolver.jl:61-66 (+ W^-2 of :86)
             if (phase == 0) {
                 // initial point (src/solver.jl:68-104): W = I, u = h, k2 = h, dx = -c
+#pragma unroll 8
                 for (int r = 0; r < K; ++r) {
                     const double hr = WO(D::W_H, r);
                     SV(D::V_U, r) = hr;
@@ -322,17 +428,18 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                     SV(D::V_WB, KPOC + c * SDIM) = 1.0;
                     SO(D::O_CS, 4 * c + 0) = 1.0; SO(D::O_CS, 4 * c + 1) = 1.0; SO(D::O_CS, 4 * c + 2) = 0.5; SO(D::O_CS, 4 * c + 3) = 0.0;
                 }
-                for (int j = 0; j < N; ++j) SO(D::O_DX, j) = -WO(D::W_C, j);
+#pragma unroll
+                for (int j = 0; j < N; ++j) WO(D::W_DX, j) = -WO(D::W_C, j);
                 sc = 1.0;
             } else {
                 const bool comb = phase == 2;          // ds = -lam o lam (:120) [+ sigma mu e - kt2 o kt3 (:137-139)]
 #pragma unroll 2
                 for (int i = 0; i < KPOC; ++i) {
                     const double w = SV(D::V_WB, i), iw = SO(D::O_IWB, i), lv = SV(D::V_LAM, i);
-                    const double dsc = SV(D::V_DSC, i);
+                    const double dsc = WO(D::W_DSC, i);
                     const double dsv = -(lv * lv) + (comb ? dsc : 0.0);
                     const double kk = dsv * fast_rcp(lv);
-                    const double kz = sc * SV(D::V_DZ, i) - w * kk;
+                    const double kz = sc * WO(D::W_DZ, i) - w * kk;
                     SV(D::V_K0, i) = kk; SV(D::V_K2, i) = kz; SV(D::V_U, i) = iw * iw * kz;
                 }
 #pragma unroll 2
@@ -346,13 +453,13 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                     for (int e = 0; e < SDIM; ++e) { lv[e] = SV(D::V_LAM, o + e); wv[e] = SV(D::V_WB, o + e); }
                     const double l0 = lv[0], w0 = wv[0], aa = l0 * l0 - llt;
                     {
-                        const double d0 = SV(D::V_DSC, o);
+                        const double d0 = WO(D::W_DSC, o);
                         dsv[0] = -(llt + l0 * l0) + (comb ? d0 : 0.0);                  // src/vectors.jl:66-69
                     }
                     double beta = 0.0;
 #pragma unroll
                     for (int e = 1; e < SDIM; ++e) {
-                        const double de = SV(D::V_DSC, o + e);
+                        const double de = WO(D::W_DSC, o + e);
                         dsv[e] = -(l0 * lv[e] + l0 * lv[e]) + (comb ? de : 0.0);        // :73-75
                         beta = fma(lv[e], dsv[e], beta);
                     }
@@ -365,11 +472,11 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         dl = fma(wv[e], k0v[e], dl);
                     }
                     const double cst = k0v[0] + dl * r1w;                               // src/scalings.jl:135
-                    k2v[0] = SV(D::V_DZ, o) * sc - eta * (w0 * k0v[0] + dl);            // :136, densesolver :65
+                    k2v[0] = WO(D::W_DZ, o) * sc - eta * (w0 * k0v[0] + dl);            // :136, densesolver :65
                     double qv = w0 * k2v[0];
 #pragma unroll
                     for (int e = 1; e < SDIM; ++e) {
-                        k2v[e] = SV(D::V_DZ, o + e) * sc - eta * (k0v[e] + cst * wv[e]);        // :137-139
+                        k2v[e] = WO(D::W_DZ, o + e) * sc - eta * (k0v[e] + cst * wv[e]);        // :137-139
                         qv = fma(-wv[e], k2v[e], qv);                                   // W^-2 = eta^-2 (2 q q' - J)
                     }
 #pragma unroll
@@ -387,14 +494,13 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
             double n0[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) n0[j] = 0.0;
-#pragma unroll 4
-            for (int r = 0; r < K; ++r) {
+            fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
                 const double ur = SV(D::V_U, r);
 #pragma unroll
-                for (int j = 0; j < N; ++j) n0[j] = fma(WG(r, j), ur, n0[j]);
-            }
+                for (int j = 0; j < N; ++j) n0[j] = fma(g[j], ur, n0[j]);
+            });
 #pragma unroll
-            for (int j = 0; j < N; ++j) n0[j] = fma(sc, SO(D::O_DX, j), n0[j]);
+            for (int j = 0; j < N; ++j) n0[j] = fma(sc, WO(D::W_DX, j), n0[j]);
 
             double Lr[NH];
             bool ok = true;
@@ -403,51 +509,45 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                 const bool init = phase == 0;
 #pragma unroll
                 for (int e = 0; e < NH; ++e) Lr[e] = 0.0;
-#pragma unroll 1
-                for (int i = 0; i < KPOC; ++i) {
-                    const double iw = SO(D::O_IWB, i);
-                    const double d = iw * iw;
-                    double g[N];
+                // rows [0, KPOC): d = iwb^2; cone rows: head -eta^-2, tail eta^-2, and after the cone's last row the
+                // rank-one term h_c h_c'
+                double hq[N];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) g[j] = WG(i, j);
+                for (int j = 0; j < N; ++j) hq[j] = 0.0;
+                fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
+                    double d, wq = 0.0, f = 0.0;
+                    int e = -1;
+                    if (r < KPOC) {
+                        const double iw = SO(D::O_IWB, r);
+                        d = iw * iw;
+                    } else {
+                        const int c = (r - KPOC) / SDIM;
+                        e = (r - KPOC) - c * SDIM;
+                        const double ie = SO(D::O_CS, 4 * c + 1);
+                        const double ie2 = ie * ie;
+                        const double wb = SV(D::V_WB, r);
+                        wq = e == 0 ? wb : -wb;
+                        d = (e == 0 && !init) ? -ie2 : ie2;                       // -eta^-2 on the head, eta^-2 on the tail
+                        f = init ? 0.0 : 1.4142135623730951 * ie;                 // h_c = sqrt(2)/eta G_c'q, q = J wbar
+                    }
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
+                        hq[j] = fma(wq, g[j], hq[j]);
                         const double t = d * g[j];
 #pragma unroll
                         for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(g[q], t, Lr[TRI(q, j)]);
                     }
-                }
-#pragma unroll 1
-                for (int c = 0; c < NSOC; ++c) {
-                    const int o = KPOC + c * SDIM;
-                    const double ie = SO(D::O_CS, 4 * c + 1);
-                    const double ie2 = ie * ie;
-                    const double f = init ? 0.0 : 1.4142135623730951 * ie;          // h_c = sqrt(2)/eta G_c'q, q = J wbar
-                    double hq[N];
+                    if (e == SDIM - 1) {
 #pragma unroll
-                    for (int j = 0; j < N; ++j) hq[j] = 0.0;
+                        for (int j = 0; j < N; ++j) hq[j] *= f;
 #pragma unroll
-                    for (int e = 0; e < SDIM; ++e) {
-                        const double wq = e == 0 ? SV(D::V_WB, o) : -SV(D::V_WB, o + e);
-                        const double d = (e == 0 && !init) ? -ie2 : ie2;           // -eta^-2 on the head, eta^-2 on the tail
-                        double g[N];
+                        for (int j = 0; j < N; ++j)
 #pragma unroll
-                        for (int j = 0; j < N; ++j) g[j] = WG(o + e, j);
+                            for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(hq[q], hq[j], Lr[TRI(q, j)]);
 #pragma unroll
-                        for (int j = 0; j < N; ++j) {
-                            hq[j] = fma(wq, g[j], hq[j]);
-                            const double t = d * g[j];
-#pragma unroll
-                            for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(g[q], t, Lr[TRI(q, j)]);
-                        }
+                        for (int j = 0; j < N; ++j) hq[j] = 0.0;
                     }
-#pragma unroll
-                    for (int j = 0; j < N; ++j) hq[j] *= f;
-#pragma unroll
-                    for (int j = 0; j < N; ++j)
-#pragma unroll
-                        for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(hq[q], hq[j], Lr[TRI(q, j)]);
-                }
+                });
                 // in-register LL' (src/densesolver.jl:47); the diagonal keeps 1 / l_jj
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
@@ -486,20 +586,19 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                     for (int m = 0; m < j; ++m) n0[m] = fma(-Lr[TRI(j, m)], n0[j], n0[m]);
                 }
                 // -------------------------------------------- u = G cx - k2                     :84-85
-#pragma unroll 4
-                for (int r = 0; r < K; ++r) {
+                fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
                     double a0 = 0.0, a1 = 0.0;
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
-                        if (j & 1) a1 = fma(WG(r, j), n0[j], a1); else a0 = fma(WG(r, j), n0[j], a0);
+                        if (j & 1) a1 = fma(g[j], n0[j], a1); else a0 = fma(g[j], n0[j], a0);
                     }
                     SV(D::V_U, r) = (a0 + a1) - SV(D::V_K2, r);
-                }
+                });
 
                 if (phase == 0) {
                     // ---------------------------------------- initial iterate, src/solver.jl:86-101 (max_step: src/mats.jl:1-28)
 #pragma unroll
-                    for (int j = 0; j < N; ++j) SO(D::O_X, j) = n0[j];
+                    for (int j = 0; j < N; ++j) WO(D::W_X, j) = n0[j];
                     double mp = -INFINITY, md = -INFINITY;
                     for (int i = 0; i < KPOC; ++i) { const double v = SV(D::V_U, i); mp = fmax(mp, v); md = fmax(md, -v); }
                     for (int c = 0; c < NSOC; ++c) {
@@ -542,7 +641,7 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         dotacc = fma(kt2, kt3, dotacc);
                         SV(D::V_U, i) = cz;
                         SV(D::V_K0, i) = csx;
-                        SV(D::V_DSC, i) = -(kt2 * kt3);
+                        WO(D::W_DSC, i) = -(kt2 * kt3);
                         if (chk) fl |= !isfinite(cz) | !isfinite(csx);
                     }
 #pragma unroll 2
@@ -610,12 +709,12 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         for (int e = 1; e < SDIM; ++e) {
                             SV(D::V_U, o + e) = czv[e];
                             SV(D::V_K0, o + e) = csv[e];
-                            SV(D::V_DSC, o + e) = -(kt2v[0] * kt3v[e] + kt3v[0] * kt2v[e]);      // src/vectors.jl:73-75
+                            WO(D::W_DSC, o + e) = -(kt2v[0] * kt3v[e] + kt3v[0] * kt2v[e]);      // src/vectors.jl:73-75
                             if (chk) fl |= !isfinite(czv[e]) | !isfinite(csv[e]);
                         }
                         SV(D::V_U, o) = czv[0];
                         SV(D::V_K0, o) = csv[0];
-                        SV(D::V_DSC, o) = -dot;                                         // src/vectors.jl:66-69
+                        WO(D::W_DSC, o) = -dot;                                         // src/vectors.jl:66-69
                         if (chk) fl |= !isfinite(czv[0]) | !isfinite(csv[0]);
                     }
                     const double tstep = step_from_t(mx);                               // src/solver.jl:130 / :145
@@ -629,8 +728,8 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         else {
                             const double smu = sig * mu;
                             sc = 1.0 - sig;                                             // :136
-                            for (int i = 0; i < KPOC; ++i) SV(D::V_DSC, i) += smu;      // :137-139
-                            for (int c = 0; c < NSOC; ++c) SV(D::V_DSC, KPOC + c * SDIM) += smu;
+                            for (int i = 0; i < KPOC; ++i) WO(D::W_DSC, i) += smu;      // :137-139
+                            for (int c = 0; c < NSOC; ++c) WO(D::W_DSC, KPOC + c * SDIM) += smu;
                             phase = 2;
                         }
                     } else {
@@ -642,7 +741,7 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         if (fl) { status = ST_NUMERICAL; phase = FL_DONE; }
                         else {
 #pragma unroll
-                            for (int j = 0; j < N; ++j) SO(D::O_X, j) = fma(n0[j], step, SO(D::O_X, j));      // :147
+                            for (int j = 0; j < N; ++j) WO(D::W_X, j) = fma(n0[j], step, WO(D::W_X, j));      // :147
 #pragma unroll 4
                             for (int r = 0; r < K; ++r) {
                                 SV(D::V_Z, r) = fma(SV(D::V_U, r), step, SV(D::V_Z, r));                     // :149
@@ -660,7 +759,6 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
     }
 #undef SV
 #undef SO
-#undef WG
 #undef WO
 #undef TRI
 }

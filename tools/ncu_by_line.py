@@ -7,8 +7,13 @@ rep, so, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+sass = []
+for f in sorted(os.listdir(tmp)):          # one cubin per translation unit: take the one that holds the kernel
+    if f.endswith(".cubin"):
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if kname in txt:
+            sass = txt.splitlines()
+            break
 # instruction list (in order) of the wanted kernel with (file, line)
 lines = []
 infn = False
