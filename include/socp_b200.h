@@ -201,6 +201,11 @@ int  socp_b200_scale(socp_handle* h, const double* in, double* out);
 int  socp_b200_iscale(socp_handle* h, const double* in, double* out);
 /* out = W^-2 in (the dense iWiW gemv of src/densesolver.jl:86 in closed form) */
 int  socp_b200_iwiw(socp_handle* h, const double* in, double* out);
+/* The SqrScaling form of the scaling computed last (compute_scaling(cones, ::SqrScaling, s, z), reference
+ * src/sqrscalings.jl:177-185; per cone :50-58 and :66-139): W^-2 = diag(D) + sum_c (u_c u_c' - v_c v_c').  D, u, v
+ * are [batch][k]; the reference keeps one k-vector u_c, v_c per cone with support on that cone only
+ * (src/sqrscalings.jl:119-128), here the supports are packed into one k-vector each (zero on orthant rows). */
+int  socp_b200_sqr_scaling(socp_handle* h, double* D, double* u, double* v);
 /* make_e!, vprod!, iprod!: reference src/vectors.jl:7-24, :58-81, :99-131 */
 int  socp_b200_make_e(socp_handle* h, double* out);
 int  socp_b200_vprod(socp_handle* h, const double* u, const double* v, double* out);

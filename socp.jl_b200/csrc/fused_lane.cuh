@@ -84,7 +84,8 @@ constexpr int FL_WS_SETS = 2;               // launches that may overlap use dif
 struct FLPlan {
     bool fits = false;
     int shape = 0;          // 1: LaneC3, 2: LaneT1
-    int lpw = 16;           // lanes in use per warp (measured on C3: 16 > 32 > 8, profiles/)
+    int lpw = 32;           // lanes in use per warp (measured on C3: 32 = 16 > 8 -- throughput follows the problems in
+                            // flight per SM, not the number of instruction streams; profiles/r02_lane_c3_lpw_sweep.txt)
     int num_sms = 148;
     int deg = 0;
     size_t smem = 0;
@@ -219,6 +220,9 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
     constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NSOC = D::NSOC, SDIM = D::SDIM, NH = D::NH, NP = D::NP, RS = D::RS, NS = D::NS;
     constexpr unsigned MASK = LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u);
     constexpr int NWARP = FL_PROBLEMS_PER_SM / LPW;
+    // measured on C3: interleaving five cones per loop body instead of two, and four partial sums per row instead of
+    // two, made the kernel slower (16.5M -> 13.4M problems/s at 16 lanes per warp): code size, not chain length
+    constexpr int CU = 2;
     const int tid = (int)(unsigned)threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (lane >= LPW) return;
     const int gwarp = (int)(unsigned)blockIdx.x * NWARP + warp;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
 
     int phase = FL_FREE, b = 0, iters = 0, status = ST_RUNNING;
     bool need_top = false, dead = false, exhausted = false, fslot = true;
-    double sc = 1.0, ll = 0.0;
+    double sc = 1.0, ll = 0.0, smu_l = 0.0;
 
     for (;;) {
         if (fslot) {
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         gap = fma(si, zi, gap);
                         llacc = fma(lv, lv, llacc);
                     }
-#pragma unroll 2
+#pragma unroll CU
                     for (int c = 0; c < NSOC; ++c) {                                    // src/scalings.jl:32-99
                         const int o = KPOC + c * SDIM;
                         double sv[SDIM], zv[SDIM];
@@ -326,18 +330,33 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
             // ------------------------------------------------ a finished problem: iterate and objectives
             if (phase == FL_DONE) {
                 double po = 0.0, dob = 0.0;
+                // workspace loads first, in batches (the compiler cannot move them above the stores to a.x / a.z / a.s)
+                {
+                    double xv[N], cv[N];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const double xj = dead ? 0.0 : WO(D::W_X, j);
-                    a.x[(int64_t)b * N + j] = xj;
-                    po = fma(WO(D::W_C, j), xj, po);
+                    for (int j = 0; j < N; ++j) { xv[j] = WO(D::W_X, j); cv[j] = WO(D::W_C, j); }
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const double xj = dead ? 0.0 : xv[j];
+                        a.x[(int64_t)b * N + j] = xj;
+                        po = fma(cv[j], xj, po);
+                    }
                 }
-#pragma unroll 8
-                for (int r = 0; r < K; ++r) {
-                    const double zr = dead ? 0.0 : SV(D::V_Z, r);
-                    a.z[(int64_t)b * K + r] = zr;
-                    a.s[(int64_t)b * K + r] = dead ? 0.0 : SV(D::V_S, r);
-                    dob = fma(-WO(D::W_H, r), zr, dob);
+#pragma unroll 1
+                for (int r0 = 0; r0 < K; r0 += 8) {
+                    double hv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) hv[q] = r0 + q < K ? WO(D::W_H, r0 + q) : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int r = r0 + q;
+                        if (r < K) {
+                            const double zr = dead ? 0.0 : SV(D::V_Z, r);
+                            a.z[(int64_t)b * K + r] = zr;
+                            a.s[(int64_t)b * K + r] = dead ? 0.0 : SV(D::V_S, r);
+                            dob = fma(-hv[q], zr, dob);
+                        }
+                    }
                 }
                 a.pobj[b] = po;
                 a.dobj[b] = dob;
@@ -433,16 +452,20 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                 sc = 1.0;
             } else {
                 const bool comb = phase == 2;          // ds = -lam o lam (:120) [+ sigma mu e - kt2 o kt3 (:137-139)]
-#pragma unroll 2
+                // dz and the corrector term live in the L2 workspace: all their loads go out before the first cone
+                double dzr[K], dscr[K];
+#pragma unroll
+                for (int r = 0; r < K; ++r) { dzr[r] = WO(D::W_DZ, r); dscr[r] = WO(D::W_DSC, r); }
+#pragma unroll
                 for (int i = 0; i < KPOC; ++i) {
                     const double w = SV(D::V_WB, i), iw = SO(D::O_IWB, i), lv = SV(D::V_LAM, i);
-                    const double dsc = WO(D::W_DSC, i);
+                    const double dsc = dscr[i] + smu_l;
                     const double dsv = -(lv * lv) + (comb ? dsc : 0.0);
                     const double kk = dsv * fast_rcp(lv);
-                    const double kz = sc * WO(D::W_DZ, i) - w * kk;
+                    const double kz = sc * dzr[i] - w * kk;
                     SV(D::V_K0, i) = kk; SV(D::V_K2, i) = kz; SV(D::V_U, i) = iw * iw * kz;
                 }
-#pragma unroll 2
+#pragma unroll
                 for (int c = 0; c < NSOC; ++c) {
                     const int o = KPOC + c * SDIM;
                     const double eta = SO(D::O_CS, 4 * c + 0), ie = SO(D::O_CS, 4 * c + 1), r1w = SO(D::O_CS, 4 * c + 2),
@@ -453,13 +476,13 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                     for (int e = 0; e < SDIM; ++e) { lv[e] = SV(D::V_LAM, o + e); wv[e] = SV(D::V_WB, o + e); }
                     const double l0 = lv[0], w0 = wv[0], aa = l0 * l0 - llt;
                     {
-                        const double d0 = WO(D::W_DSC, o);
+                        const double d0 = dscr[o] + smu_l;
                         dsv[0] = -(llt + l0 * l0) + (comb ? d0 : 0.0);                  // src/vectors.jl:66-69
                     }
                     double beta = 0.0;
 #pragma unroll
                     for (int e = 1; e < SDIM; ++e) {
-                        const double de = WO(D::W_DSC, o + e);
+                        const double de = dscr[o + e];
                         dsv[e] = -(l0 * lv[e] + l0 * lv[e]) + (comb ? de : 0.0);        // :73-75
                         beta = fma(lv[e], dsv[e], beta);
                     }
@@ -472,11 +495,11 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         dl = fma(wv[e], k0v[e], dl);
                     }
                     const double cst = k0v[0] + dl * r1w;                               // src/scalings.jl:135
-                    k2v[0] = WO(D::W_DZ, o) * sc - eta * (w0 * k0v[0] + dl);            // :136, densesolver :65
+                    k2v[0] = dzr[o] * sc - eta * (w0 * k0v[0] + dl);            // :136, densesolver :65
                     double qv = w0 * k2v[0];
 #pragma unroll
                     for (int e = 1; e < SDIM; ++e) {
-                        k2v[e] = WO(D::W_DZ, o + e) * sc - eta * (k0v[e] + cst * wv[e]);        // :137-139
+                        k2v[e] = dzr[o + e] * sc - eta * (k0v[e] + cst * wv[e]);        // :137-139
                         qv = fma(-wv[e], k2v[e], qv);                                   // W^-2 = eta^-2 (2 q q' - J)
                     }
 #pragma unroll
@@ -644,7 +667,7 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         WO(D::W_DSC, i) = -(kt2 * kt3);
                         if (chk) fl |= !isfinite(cz) | !isfinite(csx);
                     }
-#pragma unroll 2
+#pragma unroll CU
                     for (int c = 0; c < NSOC; ++c) {
                         const int o = KPOC + c * SDIM;
                         const double eta = SO(D::O_CS, 4 * c + 0), ie = SO(D::O_CS, 4 * c + 1), r1w = SO(D::O_CS, 4 * c + 2),
@@ -728,8 +751,8 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         else {
                             const double smu = sig * mu;
                             sc = 1.0 - sig;                                             // :136
-                            for (int i = 0; i < KPOC; ++i) WO(D::W_DSC, i) += smu;      // :137-139
-                            for (int c = 0; c < NSOC; ++c) WO(D::W_DSC, KPOC + c * SDIM) += smu;
+                            smu_l = smu;                // :137-139: added to the orthant rows and the cone heads of
+                                                        // the corrector term when the combined head reads it
                             phase = 2;
                         }
                     } else {

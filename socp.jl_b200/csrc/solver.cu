@@ -1546,6 +1546,61 @@ int socp_b200_scale(socp_handle* h, const double* in, double* out) { return appl
 int socp_b200_iscale(socp_handle* h, const double* in, double* out) { return apply_common(h, in, out, 1); }
 int socp_b200_iwiw(socp_handle* h, const double* in, double* out) { return apply_common(h, in, out, 2); }
 
+// SqrScaling form of the scaling now in the handle (reference src/sqrscalings.jl:50-58 positive orthant, :98-128
+// second-order cone): W^-2 restricted to one cone = diag(D) + u u' - v v'.  One thread per (problem, work cone); the
+// O(d) passes over a cone run on that thread (this is an interface of the reference's sparse assembly, not a hot
+// kernel: the dense path multiplies by W^-2 in closed form and never forms D, u, v).
+__global__ void k_sqr_scaling(ConeLayout L, int nbatch, const double* __restrict__ wb, const double* __restrict__ iwb,
+                              const double* __restrict__ eta, double* __restrict__ D, double* __restrict__ u,
+                              double* __restrict__ v) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = L.ncones;
+    if (t >= (int64_t)nbatch * nc) return;
+    const int b = (int)(t / nc), c = (int)(t - (int64_t)b * nc);
+    const int kind = L.kind[c], offs = L.offs[c], dim = L.dim[c];
+    const int64_t o = (int64_t)b * L.k + offs;
+    if (kind == KIND_POC) {
+        for (int i = 0; i < dim; ++i) {
+            const double iw = iwb[o + i];
+            D[o + i] = iw * iw;                                       // z / s                       :52
+            u[o + i] = 0.0;
+            v[o + i] = 0.0;
+        }
+        return;
+    }
+    const double* e4 = eta + (int64_t)b * 4 * nc;
+    const double inu = e4[nc + c], inusq = e4[2 * nc + c];             // 1/eta, 1/eta^2             :96-97
+    const double wb0 = wb[o];
+    double wb1sq = 0.0;
+    for (int i = 1; i < dim; ++i) wb1sq = fma(wb[o + i], wb[o + i], wb1sq);
+    const double cv = -(1.0 + wb0 + wb1sq / (1.0 + wb0));                                          // :101
+    const double d = 1.0 + 2.0 / (1.0 + wb0) + wb1sq / ((1.0 + wb0) * (1.0 + wb0));                // :102
+    const double a = (wb0 * wb0 + wb1sq - cv * cv * wb1sq / (1.0 + d * wb1sq)) / 2.0;              // :103
+    const double u0 = sqrt(wb0 * wb0 + wb1sq - a);                                                 // :104
+    const double u1 = cv / u0;                                                                     // :105
+    const double v1 = sqrt(cv * cv / (u0 * u0) - d);                                               // :106
+    D[o] = a * inusq;                                                                              // :108
+    u[o] = inu * u0;                                                                               // :120
+    v[o] = 0.0;
+    for (int i = 1; i < dim; ++i) {
+        const double wbv = inu * wb[o + i];
+        D[o + i] = inusq;                                                                          // :111-113
+        u[o + i] = u1 * wbv;                                                                       // :122-127
+        v[o + i] = v1 * wbv;
+    }
+}
+
+int socp_b200_sqr_scaling(socp_handle* h, double* D, double* u, double* v) {
+    if (h && (!D || !u || !v)) return SOCP_ERR_NULL;
+    STEP_PROLOGUE(sh.have_scaling, "sqr_scaling needs compute_scaling first")
+        const int64_t total = (int64_t)B * w.L.ncones;
+        LAUNCH(sh, k_sqr_scaling, (int)((total + 127) / 128), 128, 0, w.L, B, w.wb, w.iwb, w.eta, w.kt2, w.kt3, w.k0);
+        d2h(sh, D + f * k, w.kt2, sizeof(double) * B * k);
+        d2h(sh, u + f * k, w.kt3, sizeof(double) * B * k);
+        d2h(sh, v + f * k, w.k0, sizeof(double) * B * k);
+    STEP_EPILOGUE
+}
+
 int socp_b200_make_e(socp_handle* h, double* out) {
     if (h && !out) return SOCP_ERR_NULL;
     STEP_PROLOGUE(true, "")

@@ -7,7 +7,7 @@ vprod, iprod, make_e, max_step, compute_step (reference src/Socp.jl,
 src/solver.jl, src/densesolver.jl, src/scalings.jl, src/vectors.jl, src/mats.jl)."""
 from .api import (POC, SOC, Cone, Problem, State, B200Solver, B200Scaling, SolverState, solve_socp,
                   BatchProblem, CscMatrix, BatchSolverState, solve_socp_batch, BatchResult, SocpError,
-                  compute_scaling, setup_iter, solve_kkt, scale_, iscale_, iwiw, vprod, iprod, make_e,
+                  compute_scaling, setup_iter, solve_kkt, scale_, iscale_, iwiw, sqr_scaling, vprod, iprod, make_e,
                   max_step, compute_step, deg, default_params,
                   STATUS_CONVERGED, STATUS_MAXITER, STATUS_NUMERICAL, PATH_AUTO, PATH_TILED, PATH_FUSED)
 from . import generators

@@ -64,6 +64,7 @@ SYMBOLS = {
     "socp_b200_scale": (C.c_int, [H, c_double_p, c_double_p]),
     "socp_b200_iscale": (C.c_int, [H, c_double_p, c_double_p]),
     "socp_b200_iwiw": (C.c_int, [H, c_double_p, c_double_p]),
+    "socp_b200_sqr_scaling": (C.c_int, [H, c_double_p, c_double_p, c_double_p]),
     "socp_b200_make_e": (C.c_int, [H, c_double_p]),
     "socp_b200_vprod": (C.c_int, [H, c_double_p, c_double_p, c_double_p]),
     "socp_b200_iprod": (C.c_int, [H, c_double_p, c_double_p, c_double_p]),

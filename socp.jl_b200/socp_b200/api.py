@@ -536,6 +536,16 @@ def iwiw(cones, scaling: B200Scaling, inp, out):
     return _apply("socp_b200_iwiw", scaling, inp, out)
 
 
+def sqr_scaling(cones, scaling: B200Scaling):
+    """The SqrScaling vectors of the scaling computed last (compute_scaling(cones, ::SqrScaling, s, z), reference
+    src/sqrscalings.jl:177-185): returns (D, u, v), each (batch, k), with W^-2 = diag(D) + u u' - v v' cone by cone
+    (the per-cone u_c, v_c of the reference have disjoint supports and are packed into one k-vector each)."""
+    h = scaling.handle
+    D, u, v = np.empty((h.batch, h.k)), np.empty((h.batch, h.k)), np.empty((h.batch, h.k))
+    h.check(h.lib.socp_b200_sqr_scaling(h.ptr, _dp(D), _dp(u), _dp(v)), "socp_b200_sqr_scaling")
+    return D, u, v
+
+
 def make_e(cones, batch: int = 1):
     """make_e(cones), reference src/vectors.jl:7-38."""
     h = _cone_handle(cones, batch)

@@ -680,6 +680,68 @@ def test_pattern_violation_in_a_later_chunk_falls_back():
     assert abs(ref.pobj - one.pobj[4100]) <= 1e-8 * max(1.0, abs(ref.pobj))
 
 
+# ---------------------------------------------------------------- SqrScaling vectors (src/sqrscalings.jl)
+def _packed_to_dense(cones, D, u, v):
+    """diag(D) + sum_c (u_c u_c' - v_c v_c') from the packed [k] vectors (src/sqrscalings.jl:196-214)."""
+    k = so.total_dim(cones)
+    out = np.diag(np.asarray(D, dtype=np.float64))
+    for kind, offs, dim in cones:
+        if kind == so.SOC:
+            uc, vc = np.zeros(k), np.zeros(k)
+            uc[offs:offs + dim] = u[offs:offs + dim]
+            vc[offs:offs + dim] = v[offs:offs + dim]
+            out += np.outer(uc, uc) - np.outer(vc, vc)
+    return out
+
+
+@pytest.mark.parametrize("ocn,s,z", [(rc.NT_CONES, rc.NT_S, rc.NT_Z), (rc.SQ_CONES, rc.SQ_U1, rc.SQ_V1),
+                                     (rc.SQ_CONES, rc.SQ_U2, rc.SQ_V2)])
+def test_sqr_scaling_golden(ocn, s, z):
+    """The reference's own pins of the SqrScaling form, test/runtests.jl:51-90: D + uu' - vv' == iWiW, and the reduced
+    matrix G'(D + uu' - vv')G == G' iWiW G (:74-77), with D, u, v from the device."""
+    cones = bcones(ocn)
+    k = so.total_dim(ocn)
+    prob = sb.Problem(np.zeros(1), np.zeros((0, 1)), np.zeros(0), np.zeros((k, 1)), np.zeros(k), cones, sing=False)
+    ss = sb.SolverState(prob, sb.B200Solver(prob))
+    sc = sb.compute_scaling(cones, ss.scaling, s, z)
+    D, u, v = sb.sqr_scaling(cones, sc)
+    osc = so.Scaling.create(ocn)
+    so.compute_scaling(ocn, osc, s, z)
+    o2 = so.SqrScaling.create(ocn)
+    so.compute_sqr_scaling(ocn, o2, s, z)
+    assert relerr(D[0], o2.iWiW) < 1e-13
+    assert relerr(u[0], sum(o2.us)) < 1e-13 and relerr(v[0], sum(o2.vs)) < 1e-13
+    full = _packed_to_dense(ocn, D[0], u[0], v[0])
+    assert np.linalg.norm(full - osc.iWiW) < 1e-12                                            # :80, :89 (1e-2 there)
+    if ocn is rc.SQ_CONES:
+        H1, H2 = rc.SQ_G.T @ osc.iWiW @ rc.SQ_G, rc.SQ_G.T @ full @ rc.SQ_G                   # :74-77
+        assert np.linalg.norm(H2 - H1) < 1e-12
+
+
+def test_sqr_scaling_batch_vs_oracle_and_closed_form():
+    """A batch on the `mixed` layout (orthant chunks + cones up to 70): D, u, v against the oracle, and
+    (diag(D) + uu' - vv') x against the kernel's own closed-form W^-2 x (socp_b200_iwiw)."""
+    ocn = LAYOUTS["mixed"]
+    cones = bcones(ocn)
+    k = so.total_dim(ocn)
+    B = 9
+    rng = np.random.default_rng(5)
+    s, z = interior(ocn, rng, B), interior(ocn, rng, B)
+    prob = sb.BatchProblem(np.zeros((B, 1)), np.zeros((B, 0, 1)), np.zeros((B, 0)), np.zeros((B, k, 1)), np.zeros((B, k)),
+                           cones, sing=np.zeros(B, dtype=np.uint8))
+    ss = sb.SolverState(prob)
+    sc = sb.compute_scaling(cones, ss.scaling, s, z)
+    D, u, v = sb.sqr_scaling(cones, sc)
+    xin = rng.standard_normal((B, k))
+    ref = np.zeros((B, k))
+    sb.iwiw(cones, sc, xin, ref)
+    for b in range(B):
+        o2 = so.SqrScaling.create(ocn)
+        so.compute_sqr_scaling(ocn, o2, s[b], z[b])
+        assert relerr(D[b], o2.iWiW) < 1e-12 and relerr(u[b], sum(o2.us)) < 1e-12 and relerr(v[b], sum(o2.vs)) < 1e-12
+        assert relerr(_packed_to_dense(ocn, D[b], u[b], v[b]) @ xin[b], ref[b]) < 1e-11
+
+
 # ---------------------------------------------------------------- lane-per-problem kernel (fused_lane.cuh)
 def _with_env(name, value, fn):
     import os
