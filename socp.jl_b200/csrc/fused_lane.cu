@@ -5,13 +5,14 @@
 
 namespace socp {
 
-template <class D>
+// (lanes per warp, warps per CTA) of the instantiations: full warps by default; half and quarter warps with the
+// same number of problems per SM are experiment switches (SOCP_B200_LANE_LPW, profiles/)
+template <class D, int PPS>
 static void fl_dispatch(const FLPlan& plan, const FLArgs& args, int lpw, cudaStream_t stream) {
     switch (lpw) {
-        case 32: fused_lane_launch<D, 32>(plan, args, stream); break;
-        case 16: fused_lane_launch<D, 16>(plan, args, stream); break;
-        case 4: fused_lane_launch<D, 4>(plan, args, stream); break;
-        default: fused_lane_launch<D, 8>(plan, args, stream); break;
+        case 16: fused_lane_launch<D, 16, PPS / 16>(plan, args, stream); break;
+        case 8: if (PPS / 8 <= 8) { fused_lane_launch<D, 8, (PPS / 8 <= 8 ? PPS / 8 : 8)>(plan, args, stream); break; }
+        default: fused_lane_launch<D, 32, PPS / 32>(plan, args, stream); break;
     }
 }
 
@@ -29,8 +30,12 @@ void solve_fused_lane_ext(FLPlan& plan, const Ws& g, int first, int batch, const
     a.prm = lp;
     int lpw = plan.lpw;
     if (const char* e = getenv("SOCP_B200_LANE_LPW")) lpw = atoi(e);      // experiment switch (profiles/)
-    if (plan.shape == 1) fl_dispatch<LaneC3>(plan, a, lpw, stream);
-    else fl_dispatch<LaneT1>(plan, a, lpw, stream);
+    if (lpw != 16 && lpw != 8) lpw = 32;
+    if (lpw == 8 && plan.pps > 64) lpw = 16;             // 255 registers x 8 warps fill the register file
+    if (plan.shape == 1 && plan.pps == 96) fl_dispatch<LaneC3, 96>(plan, a, lpw, stream);
+    else if (plan.shape == 1) fl_dispatch<LaneC3, 64>(plan, a, lpw, stream);
+    else if (plan.shape == 2) fl_dispatch<LaneC3r2, 64>(plan, a, lpw, stream);
+    else fl_dispatch<LaneT1, 128>(plan, a, lpw, stream);
 }
 
 }  // namespace socp

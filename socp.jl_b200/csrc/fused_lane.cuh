@@ -34,30 +34,34 @@
 #include "fused_common.cuh"
 #include <vector>
 #include <algorithm>
+#include <cstdlib>
 
 namespace socp {
 
-template <int N_, int KPOC_, int NSOC_, int SDIM_>
+template <int N_, int KPOC_, int NSOC_, int SDIM_, int RS_>
 struct LaneDims {
     static constexpr int N = N_, KPOC = KPOC_, NSOC = NSOC_, SDIM = SDIM_;
     static constexpr int K = KPOC_ + NSOC_ * SDIM_;
     static constexpr int NH = N_ * (N_ + 1) / 2;
     static constexpr int NP = (N_ + 1) / 2 * 2;           // row stride of G in the workspace (rows are runs of double2)
-    static constexpr int RS = (K % 2 == 0) ? 2 : 1;       // rows per stage of the G ring
+    static constexpr int RS = RS_;                        // rows per stage of the G ring
+    static_assert(K % RS_ == 0, "ring stages must tile the rows of G");
     static constexpr int NS = 5;                          // stages of the G ring
     // shared memory, doubles per lane: k-vectors, then iwb (orthant rows), cone scalars; then the lane's slice of the
     // ring that G streams through (RS * NS rows of NP doubles)
-    enum { V_S = 0, V_Z, V_LAM, V_WB, V_K0, V_K2, V_U, NVEC };
+    enum { V_LAM = 0, V_WB, V_K0, V_K2, V_U, NVEC };
     static constexpr int O_IWB = NVEC * K;
     static constexpr int O_CS = O_IWB + KPOC_;            // 4 per cone: eta, 1/eta, 1/(1+w0), |lam_1|^2
     static constexpr int SM_STATE = O_CS + 4 * NSOC_;
     static constexpr int SM_RING = RS * NS * NP;
     static constexpr int SM_PER_LANE = SM_STATE + SM_RING;
     // global workspace (L2 resident), doubles per lane: G (row-major k x NP, as double2 pairs), h, c, the packed factor,
-    // and the vectors touched once or twice per slot: x, dx, dz, the corrector term of ds
+    // and the vectors touched once or twice per slot: x, dx, dz, the corrector term of ds, s, z
     static constexpr int W_G = 0, W_H = K * NP, W_C = W_H + K, W_L = W_C + N_, W_X = W_L + NH, W_DX = W_X + N_,
-                         W_DZ = W_DX + N_, W_DSC = W_DZ + K;
-    static constexpr int WS_PER_LANE = W_DSC + K;
+                         W_DZ = W_DX + N_, W_DSC = W_DZ + K, W_S = W_DSC + K, W_Z = W_S + K;
+    static constexpr int WS_PER_LANE = W_Z + K;
+    // problems in flight per SM: what the shared memory holds, in whole warps, at most four warps
+    static int pps(int dev_smem) { return std::min(128, (int)(dev_smem / (SM_PER_LANE * sizeof(double))) / 32 * 32); }
     static bool matches(int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
                         const std::vector<int>& dim) {
         if (n != N || p != 0 || k != K) return false;
@@ -75,15 +79,16 @@ struct LaneDims {
     }
 };
 
-using LaneC3 = LaneDims<12, 0, 10, 4>;      // BASELINE.json C3
-using LaneT1 = LaneDims<6, 5, 3, 3>;        // small mixed layout (orthant block + cones): keeps the generic code honest
+using LaneC3 = LaneDims<12, 0, 10, 4, 1>;   // BASELINE.json C3: 2400 B of shared memory per problem, 96 problems per SM
+using LaneC3r2 = LaneDims<12, 0, 10, 4, 2>; // the same with a ring of twice the depth: 2880 B, 64 (80) problems per SM
+using LaneT1 = LaneDims<6, 5, 3, 3, 2>;     // small mixed layout (orthant block + cones): keeps the generic code honest
 
-constexpr int FL_PROBLEMS_PER_SM = 64;
 constexpr int FL_WS_SETS = 2;               // launches that may overlap use different workspace sets
 
 struct FLPlan {
     bool fits = false;
-    int shape = 0;          // 1: LaneC3, 2: LaneT1
+    int shape = 0;          // 1: LaneC3, 2: LaneC3r2, 3: LaneT1
+    int pps = 64;           // problems in flight per SM (a multiple of 32)
     int lpw = 32;           // lanes in use per warp (measured on C3: 32 = 16 > 8 -- throughput follows the problems in
                             // flight per SM, not the number of instruction streams; profiles/r02_lane_c3_lpw_sweep.txt)
     int num_sms = 148;
@@ -99,15 +104,25 @@ inline void fl_plan(FLPlan& P, int n, int p, int k, const std::vector<int>& kind
     P.fits = false;
     P.shape = 0;
     int spl = 0, wpl = 0;
-    if (LaneC3::matches(n, p, k, kind, offs, dim)) { P.shape = 1; spl = LaneC3::SM_PER_LANE; wpl = LaneC3::WS_PER_LANE; }
-    else if (LaneT1::matches(n, p, k, kind, offs, dim)) { P.shape = 2; spl = LaneT1::SM_PER_LANE; wpl = LaneT1::WS_PER_LANE; }
-    else return;
+    const char* rs2 = getenv("SOCP_B200_LANE_RS2");      // experiment switch: the deeper ring, fewer problems per SM
+    if (LaneC3::matches(n, p, k, kind, offs, dim)) {
+        if (rs2 && atoi(rs2)) { P.shape = 2; spl = LaneC3r2::SM_PER_LANE; wpl = LaneC3r2::WS_PER_LANE; P.pps = LaneC3r2::pps(dev_smem); }
+        else { P.shape = 1; spl = LaneC3::SM_PER_LANE; wpl = LaneC3::WS_PER_LANE; P.pps = LaneC3::pps(dev_smem); }
+    } else if (LaneT1::matches(n, p, k, kind, offs, dim)) {
+        P.shape = 3; spl = LaneT1::SM_PER_LANE; wpl = LaneT1::WS_PER_LANE; P.pps = LaneT1::pps(dev_smem);
+    } else return;
+    // only what fused_lane.cu instantiates: 96 (or 64) problems per SM for C3, 64 with the deeper ring, 128 for T1
+    const char* pe = getenv("SOCP_B200_LANE_PPS");       // experiment switch: 64 problems per SM on the C3 layout
+    if (P.shape == 1) P.pps = (P.pps >= 96 && !(pe && atoi(pe) == 64)) ? 96 : (P.pps >= 64 ? 64 : 0);
+    else if (P.shape == 2) P.pps = P.pps >= 64 ? 64 : 0;
+    else P.pps = P.pps >= 128 ? 128 : 0;
+    if (P.pps == 0) return;
     P.num_sms = sms;
     P.deg = 0;
     for (size_t i = 0; i < kind.size(); ++i) P.deg += kind[i] == KIND_POC ? dim[i] : 1;
-    P.smem = (size_t)spl * FL_PROBLEMS_PER_SM * sizeof(double);
+    P.smem = (size_t)spl * P.pps * sizeof(double);
     if (P.smem > (size_t)dev_smem) return;
-    P.ws_doubles = (size_t)wpl * FL_PROBLEMS_PER_SM * sms;
+    P.ws_doubles = (size_t)wpl * P.pps * sms;
     P.fits = true;
 }
 
@@ -212,14 +227,13 @@ __device__ __forceinline__ void fl_stream_rows(const double2* __restrict__ G2, d
     fl_ring_prime<K, NP, LPW, RS, NS>(G2, ring);      // every pass starts at row 0: the next one is on its way
 }
 
-template <class D, int LPW>
-__global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_lane(const FLArgs a) {
+template <class D, int LPW, int NWARP>
+__global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
 #ifndef SOCP_SIMT_EMU
     extern __shared__ __align__(16) double fl_sm[];
 #endif
     constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NSOC = D::NSOC, SDIM = D::SDIM, NH = D::NH, NP = D::NP, RS = D::RS, NS = D::NS;
     constexpr unsigned MASK = LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u);
-    constexpr int NWARP = FL_PROBLEMS_PER_SM / LPW;
     // measured on C3: interleaving five cones per loop body instead of two, and four partial sums per row instead of
     // two, made the kernel slower (16.5M -> 13.4M problems/s at 16 lanes per warp): code size, not chain length
     constexpr int CU = 2;
@@ -252,7 +266,9 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                     int fl = 0;
 #pragma unroll 2
                     for (int i = 0; i < KPOC; ++i) {                                    // src/scalings.jl:22-30
-                        const double si = SV(D::V_S, i), zi = SV(D::V_Z, i);
+                        const double si = WO(D::W_S, i), zi = WO(D::W_Z, i);
+                        SV(D::V_U, i) = zi;                           // z and h - s for the residual pass below
+                        SV(D::V_K2, i) = WO(D::W_H, i) - si;
                         const double q = si * fast_rcp(zi), qi = zi * fast_rcp(si), pz = si * zi;
                         fl |= !(q >= 0.0) | !(pz >= 0.0);
                         const double lv = fast_sqrt(pz);
@@ -262,12 +278,29 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         gap = fma(si, zi, gap);
                         llacc = fma(lv, lv, llacc);
                     }
+                    // s, z and h come from the L2 workspace: the loads of the next cone are in flight under this one
+                    double sn[SDIM], zn[SDIM], hn[SDIM];
+#pragma unroll
+                    for (int e = 0; e < SDIM; ++e) {
+                        sn[e] = NSOC ? WO(D::W_S, KPOC + e) : 0.0; zn[e] = NSOC ? WO(D::W_Z, KPOC + e) : 0.0;
+                        hn[e] = NSOC ? WO(D::W_H, KPOC + e) : 0.0;
+                    }
 #pragma unroll CU
                     for (int c = 0; c < NSOC; ++c) {                                    // src/scalings.jl:32-99
                         const int o = KPOC + c * SDIM;
                         double sv[SDIM], zv[SDIM];
 #pragma unroll
-                        for (int e = 0; e < SDIM; ++e) { sv[e] = SV(D::V_S, o + e); zv[e] = SV(D::V_Z, o + e); }
+                        for (int e = 0; e < SDIM; ++e) {
+                            sv[e] = sn[e]; zv[e] = zn[e];
+                            SV(D::V_U, o + e) = zn[e];                 // z and h - s for the residual pass below
+                            SV(D::V_K2, o + e) = hn[e] - sn[e];
+                        }
+                        if (c + 1 < NSOC) {
+#pragma unroll
+                            for (int e = 0; e < SDIM; ++e) {
+                                sn[e] = WO(D::W_S, o + SDIM + e); zn[e] = WO(D::W_Z, o + SDIM + e); hn[e] = WO(D::W_H, o + SDIM + e);
+                            }
+                        }
                         double ss = 0.0, zz = 0.0, sz = 0.0;
 #pragma unroll
                         for (int e = 1; e < SDIM; ++e) { ss = fma(sv[e], sv[e], ss); zz = fma(zv[e], zv[e], zz); sz = fma(sv[e], zv[e], sz); }
@@ -310,14 +343,14 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
 #pragma unroll
                     for (int j = 0; j < N; ++j) { rx[j] = -WO(D::W_C, j); xr[j] = WO(D::W_X, j); }
                     fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
-                        const double zr = SV(D::V_Z, r);
+                        const double zr = SV(D::V_U, r);
                         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
                             rx[j] = fma(-g[j], zr, rx[j]);
                             if (j & 1) a1 = fma(g[j], xr[j], a1); else a0 = fma(g[j], xr[j], a0);
                         }
-                        WO(D::W_DZ, r) = -(a0 + a1) - SV(D::V_S, r) + WO(D::W_H, r);
+                        WO(D::W_DZ, r) = SV(D::V_K2, r) - (a0 + a1);
                     });
                     double rxn = 0.0;
 #pragma unroll
@@ -344,17 +377,21 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                 }
 #pragma unroll 1
                 for (int r0 = 0; r0 < K; r0 += 8) {
-                    double hv[8];
+                    double hv[8], zv[8], sv[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) hv[q] = r0 + q < K ? WO(D::W_H, r0 + q) : 0.0;
+                    for (int q = 0; q < 8; ++q) {
+                        const bool in = r0 + q < K;
+                        hv[q] = in ? WO(D::W_H, r0 + q) : 0.0;
+                        zv[q] = in && !dead ? WO(D::W_Z, r0 + q) : 0.0;
+                        sv[q] = in && !dead ? WO(D::W_S, r0 + q) : 0.0;
+                    }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int r = r0 + q;
                         if (r < K) {
-                            const double zr = dead ? 0.0 : SV(D::V_Z, r);
-                            a.z[(int64_t)b * K + r] = zr;
-                            a.s[(int64_t)b * K + r] = dead ? 0.0 : SV(D::V_S, r);
-                            dob = fma(-hv[q], zr, dob);
+                            a.z[(int64_t)b * K + r] = zv[q];
+                            a.s[(int64_t)b * K + r] = sv[q];
+                            dob = fma(-hv[q], zv[q], dob);
                         }
                     }
                 }
@@ -634,15 +671,20 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         md = fmax(md, nr - z0);
                     }
                     const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(md) < prm.init_eps);
-                    for (int r = 0; r < K; ++r) { const double z0 = SV(D::V_U, r); SV(D::V_S, r) = -z0; SV(D::V_Z, r) = z0; }
+                    const double shs = shp ? 1.0 + mp : 0.0, shz = shd ? 1.0 + md : 0.0;
                     for (int i = 0; i < KPOC; ++i) {
-                        if (shp) SV(D::V_S, i) += 1.0 + mp;
-                        if (shd) SV(D::V_Z, i) += 1.0 + md;
+                        const double z0 = SV(D::V_U, i);
+                        WO(D::W_S, i) = shp ? -z0 + shs : -z0;
+                        WO(D::W_Z, i) = shd ? z0 + shz : z0;
                     }
                     for (int c = 0; c < NSOC; ++c) {
                         const int o = KPOC + c * SDIM;
-                        if (shp) SV(D::V_S, o) += 1.0 + mp;
-                        if (shd) SV(D::V_Z, o) += 1.0 + md;
+#pragma unroll
+                        for (int e = 0; e < SDIM; ++e) {
+                            const double z0 = SV(D::V_U, o + e);
+                            WO(D::W_S, o + e) = (e == 0 && shp) ? -z0 + shs : -z0;
+                            WO(D::W_Z, o + e) = (e == 0 && shd) ? z0 + shz : z0;
+                        }
                     }
                     need_top = true;
                     phase = 1;
@@ -765,10 +807,22 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
                         else {
 #pragma unroll
                             for (int j = 0; j < N; ++j) WO(D::W_X, j) = fma(n0[j], step, WO(D::W_X, j));      // :147
-#pragma unroll 4
-                            for (int r = 0; r < K; ++r) {
-                                SV(D::V_Z, r) = fma(SV(D::V_U, r), step, SV(D::V_Z, r));                     // :149
-                                SV(D::V_S, r) = fma(SV(D::V_K0, r), step, SV(D::V_S, r));                    // :150
+#pragma unroll 1
+                            for (int r0 = 0; r0 < K; r0 += 8) {        // workspace loads of a batch before its stores
+                                double zv[8], sv[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    zv[q] = r0 + q < K ? WO(D::W_Z, r0 + q) : 0.0;
+                                    sv[q] = r0 + q < K ? WO(D::W_S, r0 + q) : 0.0;
+                                }
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const int r = r0 + q;
+                                    if (r < K) {
+                                        WO(D::W_Z, r) = fma(SV(D::V_U, r), step, zv[q]);                     // :149
+                                        WO(D::W_S, r) = fma(SV(D::V_K0, r), step, sv[q]);                    // :150
+                                    }
+                                }
                             }
                             ++iters;
                             need_top = true;
@@ -789,18 +843,18 @@ __global__ void __launch_bounds__((FL_PROBLEMS_PER_SM / LPW) * 32, 1) k_fused_la
 // grid and per-warp lane cap of a launch over `batch` problems: a small batch is spread over the SMs instead of
 // filling the first CTAs
 inline void fl_grid(const FLPlan& plan, int batch, int lpw, int& grid, int& cap) {
-    const int nwarp = FL_PROBLEMS_PER_SM / lpw;
-    grid = std::max(1, std::min(plan.num_sms, (batch + FL_PROBLEMS_PER_SM - 1) / FL_PROBLEMS_PER_SM));
+    const int nwarp = plan.pps / lpw;
+    grid = std::max(1, std::min(plan.num_sms, (batch + plan.pps - 1) / plan.pps));
     cap = std::min(lpw, (batch + grid * nwarp - 1) / (grid * nwarp));
 }
 
 #ifndef SOCP_SIMT_EMU
-template <class D, int LPW>
+template <class D, int LPW, int NWARP>
 inline void fused_lane_launch(const FLPlan& plan, FLArgs args, cudaStream_t stream) {
     int grid;
     fl_grid(plan, args.batch, LPW, grid, args.cap);
-    cudaFuncSetAttribute(k_fused_lane<D, LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-    k_fused_lane<D, LPW><<<grid, (FL_PROBLEMS_PER_SM / LPW) * 32, plan.smem, stream>>>(args);
+    cudaFuncSetAttribute(k_fused_lane<D, LPW, NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    k_fused_lane<D, LPW, NWARP><<<grid, NWARP * 32, plan.smem, stream>>>(args);
 }
 
 // Solves problems [first, first + batch) of the shard.  ws_set: which workspace set / counter this launch uses

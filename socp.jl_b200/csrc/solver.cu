@@ -923,7 +923,7 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     // twice as fast as the kernel retires them, so the upload of each next chunk ends before the previous one is
     // solved) so that the solve starts as soon as possible, then up to 8 equal chunks of at least 4 waves each.
     const int slots = v3 ? sh.fused2.num_sms * 4
-                         : (lane ? sh.lane.num_sms * FL_PROBLEMS_PER_SM : sh.fused2.num_sms * sh.fused2.ctas_per_sm);
+                         : (lane ? sh.lane.num_sms * sh.lane.pps : sh.fused2.num_sms * sh.fused2.ctas_per_sm);
     std::vector<int> bounds{0};
     if (B > 8 * slots) { bounds.push_back(slots); bounds.push_back(3 * slots); }
     {

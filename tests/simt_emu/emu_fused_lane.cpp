@@ -7,19 +7,19 @@
 
 using namespace socp;
 
-template <class D, int LPW>
+template <class D, int LPW, int NWARP>
 static void run(const FLPlan& P, FLArgs a, int grid_cap, int order) {
     int grid;
     fl_grid(P, a.batch, LPW, grid, a.cap);
     if (grid_cap > 0) grid = std::min(grid, grid_cap);
-    std::vector<double> ws((size_t)D::WS_PER_LANE * FL_PROBLEMS_PER_SM * grid, std::nan(""));
+    std::vector<double> ws((size_t)D::WS_PER_LANE * P.pps * grid, std::nan(""));
     a.ws = ws.data();
     simt_emu::LaunchCfg cfg;
     cfg.grid = (unsigned)grid;
-    cfg.block = (FL_PROBLEMS_PER_SM / LPW) * 32;
+    cfg.block = NWARP * 32;
     cfg.smem = P.smem;
     cfg.order = order;
-    simt_emu::launch(cfg, [&]() { k_fused_lane<D, LPW>(a); });
+    simt_emu::launch(cfg, [&]() { k_fused_lane<D, LPW, NWARP>(a); });
 }
 
 // Returns 0, -1 when no instantiation takes the layout.  grid_cap > 0 limits the number of CTAs (more problems per lane).
@@ -40,13 +40,15 @@ extern "C" int emu_fused_lane_solve(int n, int k, int ncones, const int* kind, c
     a.ws = nullptr; a.counter = &counter;
     a.first = 0; a.batch = batch; a.cap = 0; a.deg = P.deg;
     a.prm = LoopParams{max_iter, tol, damp, init_eps};
-#define FL_RUN(D)                                              \
-    switch (lpw) {                                             \
-        case 32: run<D, 32>(P, a, grid_cap, order); break;     \
-        case 16: run<D, 16>(P, a, grid_cap, order); break;     \
-        case 4: run<D, 4>(P, a, grid_cap, order); break;       \
-        default: run<D, 8>(P, a, grid_cap, order); break;      \
+#define FL_RUN(D, PPS)                                                     \
+    switch (lpw) {                                                         \
+        case 16: run<D, 16, PPS / 16>(P, a, grid_cap, order); break;       \
+        case 8: run<D, 8, PPS / 8>(P, a, grid_cap, order); break;          \
+        default: run<D, 32, PPS / 32>(P, a, grid_cap, order); break;       \
     }
-    if (P.shape == 1) { FL_RUN(LaneC3) } else { FL_RUN(LaneT1) }
+    if (P.shape == 1 && P.pps == 96) { FL_RUN(LaneC3, 96) }
+    else if (P.shape == 1) { FL_RUN(LaneC3, 64) }
+    else if (P.shape == 2) { FL_RUN(LaneC3r2, 64) }
+    else { FL_RUN(LaneT1, 128) }
     return 0;
 }

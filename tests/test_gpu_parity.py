@@ -787,8 +787,8 @@ def test_lane_kernel_orthant_block_small_batch_and_solve_host():
     same = res.iters == old.iters
     assert same.sum() >= 33
     assert np.max(np.abs(res.pobj[same] - old.pobj[same]) / np.maximum(1.0, np.abs(old.pobj[same]))) <= 1e-6
-    big = gen.make_config("C3", batch=90000)
-    one_shot = sb.solve_socp_batch(big, sb.SolverState(big))          # socp_b200_solve_host: 3 chunks
+    big = gen.make_config("C3", batch=120000)                          # > 8 waves of 148 x 96 lanes: three chunks
+    one_shot = sb.solve_socp_batch(big, sb.SolverState(big))          # socp_b200_solve_host
     assert one_shot.timings["kernel_launches"] >= 2
     ss2 = sb.SolverState(big)
     ss2.load(big)
