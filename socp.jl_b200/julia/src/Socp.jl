@@ -14,7 +14,7 @@ using LinearAlgebra
 using SparseArrays
 
 export POC, SOC, Problem, BatchProblem, SparseBatchProblem, State, SolverState, B200Solver, B200Scaling,
-       solve_socp, solve_socp_batch, compute_scaling, setup_iter, solve_kkt, scale!, iscale!,
+       solve_socp, solve_socp_batch, compute_scaling, sqr_scaling, setup_iter, solve_kkt, scale!, iscale!,
        vprod, iprod, make_e, max_step, compute_step, deg
 
 const libsocp = get(ENV, "SOCP_B200_LIB", joinpath(@__DIR__, "..", "..", "lib", "libsocp_b200.so"))
@@ -309,6 +309,19 @@ for (jl, cfn) in ((:scale!, :socp_b200_scale), (:iscale!, :socp_b200_iscale))   
                         ss.handle, inp, out), $(string(cfn)))
         return out
     end
+end
+"""
+    sqr_scaling(ss) -> (D, u, v)
+
+The SqrScaling form of the scaling computed last (`compute_scaling(cones, ::SqrScaling, s, z)`, reference
+src/sqrscalings.jl:177-185; per cone :50-58, :98-128): `W^-2 = Diagonal(D) + u u' - v v'` cone by cone.  Each result is
+k x B; the reference's per-cone vectors `us[c]`, `vs[c]` (support on cone c only) are packed into one k-vector.
+"""
+function sqr_scaling(ss::SolverState)
+    D = zeros(ss.k, ss.B); u = zeros(ss.k, ss.B); v = zeros(ss.k, ss.B)
+    check(ss, ccall((:socp_b200_sqr_scaling, libsocp), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    ss.handle, D, u, v), "socp_b200_sqr_scaling")
+    return D, u, v
 end
 function vprod(ss::SolverState, u::Matrix{Float64}, v::Matrix{Float64})          # src/vectors.jl:58-81
     out = similar(u)
