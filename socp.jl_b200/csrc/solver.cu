@@ -58,6 +58,7 @@ struct Shard {
     cudaStream_t alt_stream = nullptr;                           // second compute stream: consecutive chunks backfill
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t split_ev[2] = {nullptr, nullptr};                // fork / join of the two-stream factor
     std::vector<void*> allocs;
     Ws w{};
     // layout (device copies)
@@ -112,6 +113,8 @@ struct Shard {
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         for (auto& e : pipe_ev) cudaEventDestroy(e);
+        for (auto& e : split_ev)
+            if (e) cudaEventDestroy(e);
         if (up_stream) cudaStreamDestroy(up_stream);
         if (alt_stream) cudaStreamDestroy(alt_stream);
         if (down_stream) cudaStreamDestroy(down_stream);
@@ -358,8 +361,59 @@ void launch_compute_step(Shard& sh, const double* lam, const double* ds, const d
     else LAUNCH(sh, k_compute_step, sh.batch, sh.threads, 0, sh.w.L, lam, ds, dz, out);
 }
 
+void factor_one(Shard& sh, bool identity, bool add_aa, const int* active);
+
+// The factor of a large batch without equality rows, as two half batches on two streams: the Gram product of one
+// half (DMMA bound) runs under the Cholesky panels of the other (short latency-bound kernels: diagonal blocks,
+// triangular panel solves), which on their own leave most of the machine idle.  Same kernels, same per-problem
+// arithmetic: results are bit-identical to the single-stream order.
+bool factor_split_ok(const Shard& sh) {
+    static const bool off = getenv("SOCP_B200_NO_SPLIT_FACTOR") != nullptr;
+    return !off && sh.w.L.p == 0 && sh.batch >= 256 && sh.w.L.n >= 128;
+}
+void factor_split(Shard& sh, bool identity, const int* active) {
+    Ws& w = sh.w;
+    const int n = w.L.n, k = w.L.k, nc = w.L.ncones;
+    if (!sh.alt_stream) CK(cudaStreamCreateWithFlags(&sh.alt_stream, cudaStreamNonBlocking));
+    if (!sh.split_ev[0]) {
+        CK(cudaEventCreateWithFlags(&sh.split_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sh.split_ev[1], cudaEventDisableTiming));
+    }
+    const int B = sh.batch, h0 = B / 2;
+    const Ws saved = w;
+    cudaStream_t main_stream = sh.stream;
+    CK(cudaEventRecord(sh.split_ev[0], main_stream));
+    CK(cudaStreamWaitEvent(sh.alt_stream, sh.split_ev[0], 0));
+    const int nblk = (n + CHOL_NB - 1) / CHOL_NB;
+    for (int part = 0; part < 2; ++part) {
+        const int64_t off = part ? h0 : 0;
+        sh.batch = part ? B - h0 : h0;
+        sh.stream = part ? sh.alt_stream : main_stream;
+        w = saved;
+        w.G = saved.G + off * saved.sG;
+        w.wb = saved.wb + off * k;
+        w.iwb = saved.iwb + off * k;
+        w.eta = saved.eta + off * 4 * nc;
+        w.Gt = saved.Gt + off * (int64_t)saved.ldgt * n;
+        w.H = saved.H + off * (int64_t)saved.ldh * n;
+        w.XH = saved.XH + off * (int64_t)nblk * 4096;
+        w.fail = saved.fail + off;
+        w.sing = saved.sing ? saved.sing + off : nullptr;
+        factor_one(sh, identity, false, active ? active + off : nullptr);
+    }
+    w = saved;
+    sh.batch = B;
+    sh.stream = main_stream;
+    CK(cudaEventRecord(sh.split_ev[1], sh.alt_stream));
+    CK(cudaStreamWaitEvent(main_stream, sh.split_ev[1], 0));
+}
+
 // KKT factor, reference src/densesolver.jl:41-52.  identity: W = I (initial point, sing test).
 void factor(Shard& sh, bool identity, bool add_aa, const int* active) {
+    if (factor_split_ok(sh)) factor_split(sh, identity, active);
+    else factor_one(sh, identity, add_aa, active);
+}
+void factor_one(Shard& sh, bool identity, bool add_aa, const int* active) {
     Ws& w = sh.w;
     const int n = w.L.n, p = w.L.p;
     launch_build_gt(sh, identity, active);
@@ -901,11 +955,9 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
             grow_i(sh.d_linA, sh.cap_linA, (size_t)std::max<int64_t>(1, nnzA));
         }
     }
-    if (!sh.up_stream) {
-        CK(cudaStreamCreateWithFlags(&sh.up_stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&sh.down_stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&sh.alt_stream, cudaStreamNonBlocking));
-    }
+    if (!sh.up_stream) CK(cudaStreamCreateWithFlags(&sh.up_stream, cudaStreamNonBlocking));
+    if (!sh.down_stream) CK(cudaStreamCreateWithFlags(&sh.down_stream, cudaStreamNonBlocking));
+    if (!sh.alt_stream) CK(cudaStreamCreateWithFlags(&sh.alt_stream, cudaStreamNonBlocking));
     const bool v3 = f3_candidate(h);
     const bool lane = !v3 && lane_wanted(sh, B);
     if (lane) ensure_lane_ws(sh);
