@@ -248,7 +248,11 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
             if (m > 0) {   // rows >= jm, columns [jm, jm + 64): first block column of what is left
                 const double* P = H + (int64_t)j * ld + jm;
                 double* T = H + (int64_t)jm * ld + jm;
-                syrk_launch<64, 2, 16, false>(sh, P, sH, ld, nn - jm, m * CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active, true);
+                // few tiles (a handful of large problems: C5 has at most 64 of them per update): sixteen warps per tile
+                // instead of four -- the update is a serial link of the panel chain and one CTA's DMMA rate sets its length
+                const long long tiles = (long long)((nn - jm + 63) / 64) * sh.batch;
+                if (tiles <= 148) syrk_launch<64, 4, 16, false>(sh, P, sH, ld, nn - jm, m * CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active, true);
+                else syrk_launch<64, 2, 16, false>(sh, P, sH, ld, nn - jm, m * CHOL_NB, T, sH, ld, -1.0, 1.0, nullptr, 0, 0, nullptr, active, true);
             }
             panel(jm);
         }
@@ -976,11 +980,14 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     // solved) so that the solve starts as soon as possible, then up to 8 equal chunks of at least 4 waves each.
     const int slots = v3 ? sh.fused2.num_sms * 4
                          : (lane ? sh.lane.num_sms * sh.lane.pps : sh.fused2.num_sms * sh.fused2.ctas_per_sm);
+    // (the lane-per-problem kernel holds 96 problems per SM and fills partial waves evenly: one short chunk, then
+    // chunks of two waves)
     std::vector<int> bounds{0};
-    if (B > 8 * slots) { bounds.push_back(slots); bounds.push_back(3 * slots); }
+    if (lane) { if (B > 3 * slots) bounds.push_back(slots); }
+    else if (B > 8 * slots) { bounds.push_back(slots); bounds.push_back(3 * slots); }
     {
         const int rest = B - bounds.back();
-        const int nrest = std::max(1, std::min(8, rest / std::max(1, 4 * slots)));
+        const int nrest = std::max(1, std::min(8, rest / std::max(1, (lane ? 2 : 4) * slots)));
         const int per = (rest + nrest - 1) / nrest;
         for (int lo = bounds.back(); lo < B; lo += per) bounds.push_back(std::min(B, lo + per));
     }
