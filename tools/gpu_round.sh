@@ -10,6 +10,7 @@ for cfg in C3 C4 C5; do
   python bench.py --config $cfg --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/${tag}_bench_${cfg}.json 2> gpurun_out/${tag}_bench_${cfg}.err
 done
 bash tools/gpu_ncu_c2.sh ${tag}_fused3_c2
+bash tools/gpu_ncu_c3.sh ${tag}_lane_c3
 python tools/bench_steps.py C4 --reps 3 > gpurun_out/${tag}_steps_C4.txt 2>&1
 python tools/bench_steps.py C5 --reps 3 > gpurun_out/${tag}_steps_C5.txt 2>&1
 python tools/bench_steps.py C2 --batch 100000 --reps 3 > gpurun_out/${tag}_steps_C2_100k.txt 2>&1
