@@ -242,8 +242,14 @@ def main():
 
     n, p, k, batch_cfg, desc = workload_meta(args.config)
     B = args.batch or batch_cfg
-    # every rank generates its own shard: problems [rank*B, (rank+1)*B) of the seeded sequence
     from socp_b200 import sharding
+    numa_node = -1
+    if world > 1 and not os.environ.get("SOCP_B200_NO_NUMA_BIND"):
+        # one process per GPU: its host thread and the pinned staging buffers allocated below go to the GPU's NUMA node
+        # (N = 1 is left alone: the cpu_baseline leg of that run needs every host core)
+        pr_ = torch.cuda.get_device_properties(local)
+        numa_node = sharding.bind_host_to_pci_device(f"{pr_.pci_domain_id:04x}:{pr_.pci_bus_id:02x}:{pr_.pci_device_id:02x}.0")
+    # every rank generates its own shard: problems [rank*B, (rank+1)*B) of the seeded sequence
     first, _last = sharding.weak_shard(B, rank)
     prob = gen.make_config(args.config, batch=B, first=first)
 
@@ -425,7 +431,8 @@ def main():
                               "stored" % (csc["G"].nnz, k * n)) if csc else "A and G dense column-major",
                     "how": ("socp_b200_solve_host_csc" if csc else "socp_b200_solve_host") +
                            ": pinned host buffers -> chunked H2D / (CSC scatter) / solve / D2H (overlapped on three "
-                           "streams) -> pinned host results; wall clock between barriers, max over ranks"},
+                           "streams) -> pinned host results; wall clock between barriers, max over ranks",
+                    "host_numa_node_rank0": numa_node},
             "gpu_launches": int(total_launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,

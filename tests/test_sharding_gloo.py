@@ -79,3 +79,28 @@ def test_two_rank_gloo_reduction(tmp_path):
         want = zlib.crc32(full.G_cm[first:last].tobytes()) ^ zlib.crc32(full.c[first:last].tobytes())
         assert crc == want
     assert [c[:2] for c in crcs] == [(0, 6), (6, 12)]
+
+
+def test_numa_binding_helpers(tmp_path):
+    """bind_host_to_pci_device on a fake sysfs tree: cpulist parsing, unknown devices / nodes leave the process alone."""
+    import os
+    from socp_b200 import sharding
+    assert sharding._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    dev = tmp_path / "bus" / "pci" / "devices" / "0000:3b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices" / "system" / "node" / "node1"
+    node.mkdir(parents=True)
+    mine = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text(",".join(str(c) for c in mine) + "\n")
+    assert sharding.numa_node_of_pci_device("0000:3B:00.0", str(tmp_path)) == 1
+    assert sharding.numa_node_of_pci_device("0000:00:00.0", str(tmp_path)) == -1
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_host_to_pci_device("0000:3b:00.0", str(tmp_path)) == 1
+    assert os.sched_getaffinity(0) == before                    # the node's CPUs are exactly the allowed ones here
+    (dev / "numa_node").write_text("-1\n")
+    assert sharding.bind_host_to_pci_device("0000:3b:00.0", str(tmp_path)) == -1
+    (dev / "numa_node").write_text("1\n")
+    (node / "cpulist").write_text("100000\n")                   # no overlap with the allowed CPUs: nothing changes
+    assert sharding.bind_host_to_pci_device("0000:3b:00.0", str(tmp_path)) == -1
+    assert os.sched_getaffinity(0) == before
