@@ -816,7 +816,7 @@ bool lane_wanted(const Shard& sh, int batch) {
     return (long long)batch * 5 >= 3LL * sh.lane.num_sms * sh.lane.pps;
 }
 void ensure_lane_ws(Shard& sh) {
-    if (!sh.lane.d_ws) sh.lane.d_ws = sh.alloc<double>(sh.lane.ws_doubles * FL_WS_SETS, false);
+    if (!sh.lane.d_ws) sh.lane.d_ws = sh.alloc<double>(sh.lane.ws_doubles * FL_WS_SETS, true);
 }
 
 // which whole-solve kernel can take the data now resident (plans fused_v3 on first use)
