@@ -141,12 +141,11 @@ struct FLArgs {
 enum { FL_FREE = -1, FL_DONE = -2 };
 
 #ifdef SOCP_SIMT_EMU
-inline unsigned __ballot_sync(unsigned, int pred) {
-    unsigned r = 0;
-    for (int l = 0; l < 32; ++l) {
-        const int v = __shfl_sync(0xffffffffu, pred, l);
-        if (v && l < simt_emu::cur_block()->warps[simt_emu::cur_thread()->warp].nlanes) r |= 1u << l;
-    }
+inline unsigned __ballot_sync(unsigned, int pred) {      // a lane that has returned reads back as the caller's own value:
+    unsigned r = 0;                                      // every lane votes with its own number so that it cannot pass
+    const int mine = pred ? simt_emu::cur_thread()->lane + 1 : 0;      // for another lane's vote
+    for (int l = 0; l < 32; ++l)
+        if (__shfl_sync(0xffffffffu, mine, l) == l + 1) r |= 1u << l;
     return r;
 }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

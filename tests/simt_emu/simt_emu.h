@@ -36,7 +36,10 @@ struct Warp {
     double ma[2][32], mb[2][32];
     int bar_cnt = 0;
     unsigned bar_gen = 0;
-    int nlanes = 32;
+    int nlanes = 32;               // lanes the warp was launched with
+    int nlive = 32;                // ... that have not returned yet: what a warp collective waits for
+    unsigned xseq[2][32] = {};     // which collective (per-lane running count) wrote xbuf[par][lane]: a lane that
+                                   // returned before this collective holds a stale entry and does not take part
 };
 
 struct Block;
@@ -75,7 +78,7 @@ inline void warp_barrier(const char* where) {
     Thread* t = cur_thread();
     Warp& w = t->blk->warps[t->warp];
     const unsigned gen = w.bar_gen;
-    if (++w.bar_cnt == w.nlanes) {
+    if (++w.bar_cnt == w.nlive) {
         w.bar_cnt = 0;
         w.bar_gen++;
         t->blk->progress++;
@@ -104,10 +107,11 @@ inline T exchange(T v, int src_lane_xor, int src_lane_abs, const char* where) {
     uint64_t bits = 0;
     memcpy(&bits, &v, sizeof(T));
     w.xbuf[par][t->lane] = bits;
+    w.xseq[par][t->lane] = t->xpar;
     warp_barrier(where);
     const int src = src_lane_abs >= 0 ? (src_lane_abs & 31) : (t->lane ^ src_lane_xor);
     T r;
-    const uint64_t got = (src < w.nlanes) ? w.xbuf[par][src] : bits;
+    const uint64_t got = (src < w.nlanes && w.xseq[par][src] == t->xpar) ? w.xbuf[par][src] : bits;
     memcpy(&r, &got, sizeof(T));
     return r;
 }
@@ -116,9 +120,11 @@ inline int vote_any(int pred) {
     Warp& w = t->blk->warps[t->warp];
     const unsigned par = (t->xpar++) & 1u;
     w.xbuf[par][t->lane] = pred ? 1 : 0;
+    w.xseq[par][t->lane] = t->xpar;
     warp_barrier("__any_sync");
     int r = 0;
-    for (int l = 0; l < w.nlanes; ++l) r |= (int)w.xbuf[par][l];
+    for (int l = 0; l < w.nlanes; ++l)
+        if (w.xseq[par][l] == t->xpar) r |= (int)w.xbuf[par][l];
     return r;
 }
 // D(8x8) += A(8x4, row) * B(4x8, col): lane l holds A[l>>2][l&3], B[l&3][l>>2], C[l>>2][2*(l&3) + {0,1}]
@@ -155,8 +161,10 @@ struct Tramp {
         t->done = true;
         t->blk->progress++;
         // a thread that has returned no longer takes part in the warp's collectives (kernels that retire lanes early)
+        // (lanes that have passed their last collective return one after the other while their neighbours may not
+        // even have read the result of that collective yet: the launch width stays what it was)
         Warp& w = t->blk->warps[t->warp];
-        if (--w.nlanes > 0 && w.bar_cnt == w.nlanes) { w.bar_cnt = 0; w.bar_gen++; }
+        if (--w.nlive > 0 && w.bar_cnt == w.nlive) { w.bar_cnt = 0; w.bar_gen++; }
         swapcontext(&t->ctx, &t->blk->sched);
     }
 };
@@ -179,7 +187,7 @@ inline void launch(const LaunchCfg& cfg, Fn body) {
         blk.smem = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
         const int nwarp = (cfg.block + 31) / 32;
         blk.warps.resize(nwarp);
-        for (int w = 0; w < nwarp; ++w) blk.warps[w].nlanes = (int)std::min<unsigned>(32, cfg.block - 32 * w);
+        for (int w = 0; w < nwarp; ++w) blk.warps[w].nlanes = blk.warps[w].nlive = (int)std::min<unsigned>(32, cfg.block - 32 * w);
         blk.th.resize(cfg.block);
         cur_block() = &blk;
         for (unsigned i = 0; i < cfg.block; ++i) {
