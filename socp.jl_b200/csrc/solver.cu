@@ -808,12 +808,12 @@ enum { FUSED_NONE = 0, FUSED_V2 = 2, FUSED_V3 = 3, FUSED_LANE = 4 };
 // The lane-per-problem kernel keeps 96 problems per SM in flight, but a problem occupies its lane for about 0.1 ms per
 // iteration: a launch lasts at least as long as its slowest problem (~1 ms at 19 iterations) however small the batch,
 // while fused_v2's one-warp teams (12 per SM, ~0.02 ms per iteration) retire 8.6M problems/s from the first wave on.
-// Measured crossover on C3: ~8.6k problems, i.e. 0.6 of the lane slots.  SOCP_B200_LANE=0 / 1 switches the kernel
-// off / on regardless of the batch size (tests, experiments).
+// Measured crossover on C3 (profiles/r02_lane_c3_batch_sweep.txt): between 6k and 9k problems, i.e. about half of the
+// lane slots.  SOCP_B200_LANE=0 / 1 switches the kernel off / on regardless of the batch size (tests, experiments).
 bool lane_wanted(const Shard& sh, int batch) {
     if (!sh.lane.fits) return false;
     if (const char* e = getenv("SOCP_B200_LANE")) return atoi(e) != 0;
-    return (long long)batch * 5 >= 3LL * sh.lane.num_sms * sh.lane.pps;
+    return 2LL * batch >= (long long)sh.lane.num_sms * sh.lane.pps;
 }
 void ensure_lane_ws(Shard& sh) {
     if (!sh.lane.d_ws) sh.lane.d_ws = sh.alloc<double>(sh.lane.ws_doubles * FL_WS_SETS, true);
