@@ -13,9 +13,13 @@
 //
 //   * lane-interleaved storage everywhere: element e of the problem of lane l lives at base[e * LPW + l], so every
 //     warp access is one contiguous run (shared memory: conflict free; global: fully coalesced);
-//   * G, h, c and the Cholesky factor live in a per-warp global workspace (L2 resident: 148 SMs x 64 problems x 4.9 KB
-//     = 46 MB), the iterate / scaling / right-hand sides (9 k-vectors + 2 n-vectors + 4 scalars per cone) in shared
-//     memory (3.4 KB per problem -> 64 problems per SM); H (n(n+1)/2 packed) and the n-vectors of a solve in registers;
+//   * shared memory holds what every phase touches (lam, wbar, k0, k2, u, four scalars per cone: 240 doubles for C3)
+//     plus the lane's slice of the ring below; everything touched once or twice per slot lives in a per-warp global
+//     workspace that stays L2 resident (G, h, c, the Cholesky factor, x, dx, dz, s, z, the corrector term: 6.4 KB per
+//     problem, 148 SMs x 96 problems = 90 MB) and is read with batched loads; H (n(n+1)/2 packed) and the n-vectors of
+//     a solve live in registers;
+//   * G streams through a per-lane cp.async ring in shared memory (fl_stream_rows): a lane has nobody to hide its L2
+//     latency behind, and the ring costs no registers;
 //   * the reduced KKT matrix is accumulated row by row, H = sum_r d_r g_r g_r' + sum_c h_c h_c' (closed form of
 //     G'W^-2 G, src/densesolver.jl:42-43), factored in registers (LL', src/densesolver.jl:47) and solved by
 //     substitution; the factor of the affine direction is parked in the workspace for the combined direction;
@@ -24,9 +28,9 @@
 //   * slots alternate F (factor: initial point or affine direction) and N (no factor: combined direction), so lanes
 //     of one warp stay in step: a lane that has just taken a problem runs its initial point in an F slot, idles
 //     through the next N slot and joins the others at the following F slot;
-//   * LPW (lanes in use per warp) is a template parameter: 64 problems per SM are LPW-independent (shared memory),
-//     64 / LPW warps per SM share the four sub-partitions -- fewer lanes per warp = more independent instruction
-//     streams to hide the latency of each lane's dependent chains.
+//   * throughput follows the number of problems in flight per SM (measured: two full warps = four half warps at 64
+//     problems per SM), which shared memory sets: 2400 B per problem -> 96 problems per SM, three full warps.  LPW
+//     (lanes in use per warp) and the ring depth stay template parameters for the measurements in profiles/.
 //
 // Restrictions: p = 0, no `sing` problems (callers fall back to fused_v2 / the tiled path), layouts that have a
 // compile-time instantiation below (positive-orthant block first, then equal second-order cones).
