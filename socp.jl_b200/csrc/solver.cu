@@ -59,6 +59,8 @@ struct Shard {
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t split_ev[2] = {nullptr, nullptr};                // fork / join of the two-stream factor
+    int* d_panel_flags = nullptr;                                // [batch] release flags of k_panel_fused
+    int panel_gen = 0;                                           // ... and the value the next launch releases with
     std::vector<void*> allocs;
     Ws w{};
     // layout (device copies)
@@ -221,6 +223,7 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
     if (!configured[sh.device]) {
         CK(cudaFuncSetAttribute(k_potrf_diag_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_MMA_SMEM));
         CK(cudaFuncSetAttribute(k_trsm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_MMA_SMEM));
+        CK(cudaFuncSetAttribute(k_panel_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PANEL_FUSED_SMEM));
         CK(cudaFuncSetAttribute(k_trsv_blk_fwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_trsv_blk_bwd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2048 + 64) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_trsv_blk_fwd<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((5 * 1024 + 64) * sizeof(double))));
@@ -241,10 +244,24 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
     // thin product, K = 64 m); after the group the rest of the matrix receives all of them at once (K = 64 CHOL_GROUP) --
     // 1/CHOL_GROUP of the read-modify-write passes over the trailing matrix at CHOL_GROUP times the arithmetic intensity.
     constexpr int CHOL_GROUP = 4;
+    // A handful of large problems (C5): the factorisation is a serial chain of panel steps, and each step is ONE launch
+    // (k_panel_fused: pending update + diagonal block + panel solve, the row CTAs spinning on a flag until the
+    // diagonal CTA is done) -- possible only when every CTA of the launch is resident, one per SM.
+    static const bool no_fused_panels = getenv("SOCP_B200_NO_FUSED_PANELS") != nullptr;
+    const long long panel_ctas = (long long)(1 + std::max(0, (nn - CHOL_NB + 127) / 128)) * sh.batch;
+    const bool fused_panels = !no_fused_panels && nn >= 4 * CHOL_NB && panel_ctas <= sh.fused2.num_sms;
+    if (fused_panels && !sh.d_panel_flags) sh.d_panel_flags = sh.alloc<int>(sh.batch);
     for (int j = 0; j < nn; j += CHOL_GROUP * CHOL_NB) {
         for (int m = 0; m < CHOL_GROUP; ++m) {
             const int jm = j + m * CHOL_NB;
             if (jm >= nn) break;
+            if (fused_panels) {
+                const int below = nn - jm - CHOL_NB;
+                dim3 grid = batch_grid(1 + std::max(0, (below + 127) / 128), sh.batch);
+                LAUNCH(sh, k_panel_fused, grid, 256, PANEL_FUSED_SMEM, H, sH, ld, nn, j, jm, Xinv, nblk, fail, active,
+                       sh.d_panel_flags, ++sh.panel_gen, sh.batch);
+                continue;
+            }
             if (m > 0) {   // rows >= jm, columns [jm, jm + 64): first block column of what is left
                 const double* P = H + (int64_t)j * ld + jm;
                 double* T = H + (int64_t)jm * ld + jm;

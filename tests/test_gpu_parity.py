@@ -795,3 +795,35 @@ def test_lane_kernel_orthant_block_small_batch_and_solve_host():
     two_step = sb.solve_socp_batch(big, ss2, reload=False)             # set_data + solve: one launch
     for key in ("status", "iters", "pobj", "dobj", "x", "z", "s"):
         assert np.array_equal(getattr(one_shot, key), getattr(two_step, key)), key
+
+
+def test_fused_panel_steps_small_batch_large_n():
+    """A handful of n = 500 problems (n not a multiple of the 64-wide panels, a partial last row block): the blocked
+    Cholesky takes its panel steps through k_panel_fused (pending update + diagonal block + panel solve in one launch,
+    row CTAs released by a flag).  Whole solves against the numpy oracle; the factor against L L' = H at step level."""
+    prob = gen.make_config("C4", batch=6)
+    ss = sb.SolverState(prob)
+    res = sb.solve_socp_batch(prob, ss, sb.default_params(path=sb.PATH_TILED))
+    assert (res.status == sb.STATUS_CONVERGED).all()
+    _check_batch(prob, res, [0, 5])
+    # step level: factor at a strictly interior scaling point, then solve_kkt against the oracle's DenseSolver
+    rng = np.random.default_rng(3)
+    oc_ = ocones(prob.cones)
+    s, z = interior(oc_, rng, prob.B), interior(oc_, rng, prob.B)
+    solver = sb.B200Solver(prob)
+    ss2 = sb.SolverState(prob, solver)
+    ss2.load(prob)
+    sc = sb.compute_scaling(prob.cones, ss2.scaling, s, z)
+    assert not sb.setup_iter(solver, prob, None, sc).any()
+    n, k, B = prob.n, prob.k, prob.B
+    dx, dz, ds = rng.standard_normal((B, n)), rng.standard_normal((B, k)), rng.standard_normal((B, k))
+    cx, cy, cz, cs = np.zeros((B, n)), np.zeros((B, 0)), np.zeros((B, k)), np.zeros((B, k))
+    sb.solve_kkt(solver, prob, None, sc, dx, np.zeros((B, 0)), dz, ds, cx, cy, cz, cs)
+    for q in (1, 4):
+        pr = so.Problem.create(prob.c[q], prob.A_dense(q), prob.b[q], prob.G_dense(q), prob.h[q], oc_, sing=False)
+        osc = so.Scaling.create(oc_)
+        so.compute_scaling(oc_, osc, s[q], z[q])
+        dsv = so.DenseSolver(pr)
+        dsv.setup_iter(pr, osc)
+        ox, oy, oz, os_ = dsv.solve_kkt(pr, osc, dx[q], np.zeros(0), dz[q], ds[q], fast_iprod=True)
+        assert relerr(cx[q], ox) < 1e-9 and relerr(cz[q], oz) < 1e-9 and relerr(cs[q], os_) < 1e-9
