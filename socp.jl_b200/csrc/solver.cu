@@ -249,6 +249,8 @@ void potrf(Shard& sh, double* H, int64_t sH, int ld, int nn, double* Xinv, int* 
     // diagonal CTA is done) -- possible only when every CTA of the launch is resident, one per SM.
     static const bool no_fused_panels = getenv("SOCP_B200_NO_FUSED_PANELS") != nullptr;
     const long long panel_ctas = (long long)(1 + std::max(0, (nn - CHOL_NB + 127) / 128)) * sh.batch;
+    // (for a large batch the spinning row CTAs only take SMs away from other problems' diagonal blocks: C4 at batch
+    // 1000 factors in 6.7 ms this way against 3.7 ms with the three batch-wide kernels)
     const bool fused_panels = !no_fused_panels && nn >= 4 * CHOL_NB && panel_ctas <= sh.fused2.num_sms;
     if (fused_panels && !sh.d_panel_flags) sh.d_panel_flags = sh.alloc<int>(sh.batch);
     for (int j = 0; j < nn; j += CHOL_GROUP * CHOL_NB) {
