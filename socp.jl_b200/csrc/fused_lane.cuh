@@ -557,13 +557,13 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
             double n0[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) n0[j] = 0.0;
-            fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
-                const double ur = SV(D::V_U, r);
+            if (!fslot) {          // (in an F slot the SYRK pass below accumulates G'u as well: one pass over G less)
+                fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
+                    const double ur = SV(D::V_U, r);
 #pragma unroll
-                for (int j = 0; j < N; ++j) n0[j] = fma(g[j], ur, n0[j]);
-            });
-#pragma unroll
-            for (int j = 0; j < N; ++j) n0[j] = fma(sc, WO(D::W_DX, j), n0[j]);
+                    for (int j = 0; j < N; ++j) n0[j] = fma(g[j], ur, n0[j]);
+                });
+            }
 
             double Lr[NH];
             bool ok = true;
@@ -593,8 +593,10 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         d = (e == 0 && !init) ? -ie2 : ie2;                       // -eta^-2 on the head, eta^-2 on the tail
                         f = init ? 0.0 : 1.4142135623730951 * ie;                 // h_c = sqrt(2)/eta G_c'q, q = J wbar
                     }
+                    const double ur = SV(D::V_U, r);
 #pragma unroll
                     for (int j = 0; j < N; ++j) {
+                        n0[j] = fma(g[j], ur, n0[j]);
                         hq[j] = fma(wq, g[j], hq[j]);
                         const double t = d * g[j];
 #pragma unroll
@@ -635,6 +637,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
             }
             if (!ok) { status = ST_NUMERICAL; dead = phase == 0; phase = FL_DONE; }     // cholesky! threw
             else {
+#pragma unroll
+                for (int j = 0; j < N; ++j) n0[j] = fma(sc, WO(D::W_DX, j), n0[j]);
                 // -------------------------------------------- cx = H^-1 n0 by substitution     src/densesolver.jl:83
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
