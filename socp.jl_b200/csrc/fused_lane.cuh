@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
             // ------------------------------------------------ head of solve_kkt, src/densesolver.jl:61-66 (+ W^-2 of :86)
             if (phase == 0) {
                 // initial point (src/solver.jl:68-104): W = I, u = h, k2 = h, dx = -c
-#pragma unroll 8
+#pragma unroll 20
                 for (int r = 0; r < K; ++r) {
                     const double hr = WO(D::W_H, r);
                     SV(D::V_U, r) = hr;
@@ -565,8 +565,12 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                 });
             }
 
-            double Lr[NH];
+            double Lr[NH], dxv[N];
             bool ok = true;
+            if (!fslot) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) dxv[j] = WO(D::W_DX, j);
+            }
             if (fslot) {
                 // -------------------------------------------- KKT factor, src/densesolver.jl:41-47
                 const bool init = phase == 0;
@@ -613,6 +617,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         for (int j = 0; j < N; ++j) hq[j] = 0.0;
                     }
                 });
+#pragma unroll
+                for (int j = 0; j < N; ++j) dxv[j] = WO(D::W_DX, j);        // in flight under the factorisation below
                 // in-register LL' (src/densesolver.jl:47); the diagonal keeps 1 / l_jj
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
             if (!ok) { status = ST_NUMERICAL; dead = phase == 0; phase = FL_DONE; }     // cholesky! threw
             else {
 #pragma unroll
-                for (int j = 0; j < N; ++j) n0[j] = fma(sc, WO(D::W_DX, j), n0[j]);
+                for (int j = 0; j < N; ++j) n0[j] = fma(sc, dxv[j], n0[j]);
                 // -------------------------------------------- cx = H^-1 n0 by substitution     src/densesolver.jl:83
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
@@ -815,15 +821,16 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
 #pragma unroll
                             for (int j = 0; j < N; ++j) WO(D::W_X, j) = fma(n0[j], step, WO(D::W_X, j));      // :147
 #pragma unroll 1
-                            for (int r0 = 0; r0 < K; r0 += 8) {        // workspace loads of a batch before its stores
-                                double zv[8], sv[8];
+                            constexpr int UB = 20;
+                            for (int r0 = 0; r0 < K; r0 += UB) {       // workspace loads of a batch before its stores
+                                double zv[UB], sv[UB];
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
+                                for (int q = 0; q < UB; ++q) {
                                     zv[q] = r0 + q < K ? WO(D::W_Z, r0 + q) : 0.0;
                                     sv[q] = r0 + q < K ? WO(D::W_S, r0 + q) : 0.0;
                                 }
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
+                                for (int q = 0; q < UB; ++q) {
                                     const int r = r0 + q;
                                     if (r < K) {
                                         WO(D::W_Z, r) = fma(SV(D::V_U, r), step, zv[q]);                     // :149
