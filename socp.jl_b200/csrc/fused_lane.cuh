@@ -378,18 +378,19 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         po = fma(cv[j], xj, po);
                     }
                 }
+                constexpr int FB = 20;
 #pragma unroll 1
-                for (int r0 = 0; r0 < K; r0 += 8) {
-                    double hv[8], zv[8], sv[8];
+                for (int r0 = 0; r0 < K; r0 += FB) {
+                    double hv[FB], zv[FB], sv[FB];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < FB; ++q) {
                         const bool in = r0 + q < K;
                         hv[q] = in ? WO(D::W_H, r0 + q) : 0.0;
                         zv[q] = in && !dead ? WO(D::W_Z, r0 + q) : 0.0;
                         sv[q] = in && !dead ? WO(D::W_S, r0 + q) : 0.0;
                     }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < FB; ++q) {
                         const int r = r0 + q;
                         if (r < K) {
                             a.z[(int64_t)b * K + r] = zv[q];
@@ -418,45 +419,67 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                     int myb = want ? base + __popc(need & ((1u << lane) - 1u)) : -1;
                     if (base + cnt >= a.batch) exhausted = true;
                     if (myb >= a.batch) myb = -1;
+                    // warp-uniform: the problems of up to NF lanes are copied into their slots together -- all the loads
+                    // of the group are issued before its first store, so the warp waits one memory latency per group
+                    // and not one per element or per problem (the data comes from DRAM: first touch)
+                    constexpr int NF = 4, CH = 16, NHC = (K + N + LPW - 1) / LPW;
                     unsigned m = need;
-                    while (m) {                                   // warp-uniform: copy the problem of lane l into its slot
-                        const int l = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int pb = __shfl_sync(MASK, myb, l);
-                        if (pb < 0) continue;
-                        const int64_t gb = (int64_t)a.first + pb;
-                        const double* Gg = a.G + gb * a.sG;
-                        double* Wl = Wb + l;
-                        // all the loads of a batch are issued before its first store: one memory latency per batch,
-                        // not one per element (the other lanes of the warp wait for this copy)
-                        constexpr int CH = 16, NHC = (K + N + LPW - 1) / LPW;
-                        double hc[NHC];
+                    while (m) {
+                        int ls[NF], nf = 0;
+                        int64_t gbs[NF];
 #pragma unroll
-                        for (int i = 0; i < NHC; ++i) {
-                            const int e = i * LPW + lane;
-                            hc[i] = e < K ? a.h[gb * K + e] : (e < K + N ? a.c[gb * N + (e - K)] : 0.0);
+                        for (int f = 0; f < NF; ++f) { ls[f] = 0; gbs[f] = 0; }
+                        while (m && nf < NF) {
+                            const int l = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int pb = __shfl_sync(MASK, myb, l);
+                            if (pb < 0) continue;
+#pragma unroll
+                            for (int f = 0; f < NF; ++f)
+                                if (f == nf) { ls[f] = l; gbs[f] = (int64_t)a.first + pb; }
+                            ++nf;
                         }
+                        double hc[NF][NHC];
+#pragma unroll
+                        for (int f = 0; f < NF; ++f)
+#pragma unroll
+                            for (int i = 0; i < NHC; ++i) {
+                                const int e = i * LPW + lane;
+                                hc[f][i] = (f < nf && e < K) ? a.h[gbs[f] * K + e]
+                                                             : ((f < nf && e < K + N) ? a.c[gbs[f] * N + (e - K)] : 0.0);
+                            }
 #pragma unroll 1
                         for (int e0 = 0; e0 < K * N; e0 += CH * LPW) {
-                            double t[CH];
+                            double t[NF][CH];
 #pragma unroll
-                            for (int i = 0; i < CH; ++i) {
-                                const int e = e0 + i * LPW + lane;
-                                t[i] = e < K * N ? Gg[e] : 0.0;
+                            for (int f = 0; f < NF; ++f) {
+                                const double* Gg = a.G + gbs[f] * a.sG;
+#pragma unroll
+                                for (int i = 0; i < CH; ++i) {
+                                    const int e = e0 + i * LPW + lane;
+                                    t[f][i] = (f < nf && e < K * N) ? Gg[e] : 0.0;
+                                }
                             }
 #pragma unroll
-                            for (int i = 0; i < CH; ++i) {
-                                const int e = e0 + i * LPW + lane;
-                                const int j = e / K, r = e - j * K;
-                                if (e < K * N) Wb[((r * (NP / 2) + (j >> 1)) * LPW + l) * 2 + (j & 1)] = t[i];
-                            }
+                            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                                for (int i = 0; i < CH; ++i) {
+                                    const int e = e0 + i * LPW + lane;
+                                    const int j = e / K, r = e - j * K;
+                                    if (f < nf && e < K * N) Wb[((r * (NP / 2) + (j >> 1)) * LPW + ls[f]) * 2 + (j & 1)] = t[f][i];
+                                }
                         }
-                        if (NP != N)
-                            for (int r = lane; r < K; r += LPW) Wb[((r * (NP / 2) + (N >> 1)) * LPW + l) * 2 + 1] = 0.0;
 #pragma unroll
-                        for (int i = 0; i < NHC; ++i) {
-                            const int e = i * LPW + lane;
-                            if (e < K + N) Wl[(D::W_H + e) * LPW] = hc[i];      // h, then c (W_C = W_H + K)
+                        for (int f = 0; f < NF; ++f) {
+                            if (f < nf) {
+                                if (NP != N)
+                                    for (int r = lane; r < K; r += LPW) Wb[((r * (NP / 2) + (N >> 1)) * LPW + ls[f]) * 2 + 1] = 0.0;
+#pragma unroll
+                                for (int i = 0; i < NHC; ++i) {
+                                    const int e = i * LPW + lane;
+                                    if (e < K + N) Wb[(D::W_H + e) * LPW + ls[f]] = hc[f][i];      // h, then c (W_C = W_H + K)
+                                }
+                            }
                         }
                     }
                     __syncwarp(MASK);
