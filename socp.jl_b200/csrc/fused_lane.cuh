@@ -281,12 +281,14 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         gap = fma(si, zi, gap);
                         llacc = fma(lv, lv, llacc);
                     }
-                    // s, z and h come from the L2 workspace: the loads of the next cone are in flight under this one
-                    double sn[SDIM], zn[SDIM], hn[SDIM];
+                    // s, z and h come from the L2 workspace: the loads of the next two cones are in flight under this one
+                    double sn[SDIM], zn[SDIM], hn[SDIM], sm2[SDIM], zm2[SDIM], hm2[SDIM];
 #pragma unroll
                     for (int e = 0; e < SDIM; ++e) {
                         sn[e] = NSOC ? WO(D::W_S, KPOC + e) : 0.0; zn[e] = NSOC ? WO(D::W_Z, KPOC + e) : 0.0;
                         hn[e] = NSOC ? WO(D::W_H, KPOC + e) : 0.0;
+                        sm2[e] = NSOC > 1 ? WO(D::W_S, KPOC + SDIM + e) : 0.0; zm2[e] = NSOC > 1 ? WO(D::W_Z, KPOC + SDIM + e) : 0.0;
+                        hm2[e] = NSOC > 1 ? WO(D::W_H, KPOC + SDIM + e) : 0.0;
                     }
 #pragma unroll CU
                     for (int c = 0; c < NSOC; ++c) {                                    // src/scalings.jl:32-99
@@ -297,11 +299,13 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                             sv[e] = sn[e]; zv[e] = zn[e];
                             SV(D::V_U, o + e) = zn[e];                 // z and h - s for the residual pass below
                             SV(D::V_K2, o + e) = hn[e] - sn[e];
+                            sn[e] = sm2[e]; zn[e] = zm2[e]; hn[e] = hm2[e];
                         }
-                        if (c + 1 < NSOC) {
+                        if (c + 2 < NSOC) {
 #pragma unroll
                             for (int e = 0; e < SDIM; ++e) {
-                                sn[e] = WO(D::W_S, o + SDIM + e); zn[e] = WO(D::W_Z, o + SDIM + e); hn[e] = WO(D::W_H, o + SDIM + e);
+                                sm2[e] = WO(D::W_S, o + 2 * SDIM + e); zm2[e] = WO(D::W_Z, o + 2 * SDIM + e);
+                                hm2[e] = WO(D::W_H, o + 2 * SDIM + e);
                             }
                         }
                         double ss = 0.0, zz = 0.0, sz = 0.0;
