@@ -1,5 +1,15 @@
 // common.cuh -- shared definitions for the socp_b200 CUDA sources (sm_100a).
 #pragma once
+#if defined(__CUDACC_RTC__)
+// run-time compilation of a layout-specialised kernel (lane_jit.cu): NVRTC has the CUDA built-ins but no host headers
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned char uint8_t;
+typedef unsigned long long uintptr_t;
+#ifndef INFINITY
+#define INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#endif
+#else
 #ifdef SOCP_SIMT_EMU
 // host build of the kernels for CPU-side tests (tests/simt_emu/, test infrastructure -- never part of libsocp_b200)
 #include "simt_emu.h"
@@ -8,6 +18,7 @@
 #endif
 #include <stdint.h>
 #include <math.h>
+#endif
 
 namespace socp {
 

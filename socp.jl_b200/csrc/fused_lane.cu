@@ -32,6 +32,7 @@ void solve_fused_lane_ext(FLPlan& plan, const Ws& g, int first, int batch, const
     if (const char* e = getenv("SOCP_B200_LANE_LPW")) lpw = atoi(e);      // experiment switch (profiles/)
     if (lpw != 16 && lpw != 8) lpw = 32;
     if (lpw == 8 && plan.pps > 64) lpw = 16;             // 255 registers x 8 warps fill the register file
+    if (plan.shape == 100) { lane_jit_launch(plan.jit_fn, plan, a, stream); return; }      // full warps only
     if (plan.shape == 1 && plan.pps == 96) fl_dispatch<LaneC3, 96>(plan, a, lpw, stream);
     else if (plan.shape == 1) fl_dispatch<LaneC3, 64>(plan, a, lpw, stream);
     else if (plan.shape == 2) fl_dispatch<LaneC3r2, 64>(plan, a, lpw, stream);

@@ -1,0 +1,148 @@
+// lane_jit.cu -- run-time specialisation of the lane-per-problem kernel (fused_lane_dev.cuh) for layouts that have no
+// compile-time instantiation in fused_lane.cu: the kernel template is instantiated for the caller's (n, orthant rows,
+// cone count, cone dimension) with NVRTC the first time a handle with that layout wants it, and cached per process
+// and device.  This is the GPU analogue of what the reference gets from Julia: `solve_socp` is specialised on the cone
+// tuple's type parameters (src/Socp.jl:8-18, `@unroll` over cones) the first time it is called with a new layout.
+// libnvrtc and libcuda are loaded lazily with dlopen, so the library has no link-time dependency on either; when they
+// are missing, or the compilation fails, the caller falls back to fused_v2's one-warp teams.
+#include "fused_lane.cuh"
+#include <dlfcn.h>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace socp {
+namespace {
+
+typedef int nvrtcResult_t;
+typedef struct _nvrtcProgram* nvrtcProgram_t;
+typedef int CUresult_t;
+typedef struct CUmod_st* CUmodule_t;
+typedef struct CUfunc_st* CUfunction_t;
+
+struct Api {
+    bool ok = false;
+    nvrtcResult_t (*CreateProgram)(nvrtcProgram_t*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult_t (*CompileProgram)(nvrtcProgram_t, int, const char* const*) = nullptr;
+    nvrtcResult_t (*AddNameExpression)(nvrtcProgram_t, const char*) = nullptr;
+    nvrtcResult_t (*GetLoweredName)(nvrtcProgram_t, const char*, const char**) = nullptr;
+    nvrtcResult_t (*GetCUBINSize)(nvrtcProgram_t, size_t*) = nullptr;
+    nvrtcResult_t (*GetCUBIN)(nvrtcProgram_t, char*) = nullptr;
+    nvrtcResult_t (*GetProgramLogSize)(nvrtcProgram_t, size_t*) = nullptr;
+    nvrtcResult_t (*GetProgramLog)(nvrtcProgram_t, char*) = nullptr;
+    nvrtcResult_t (*DestroyProgram)(nvrtcProgram_t*) = nullptr;
+    CUresult_t (*ModuleLoadData)(CUmodule_t*, const void*) = nullptr;
+    CUresult_t (*ModuleGetFunction)(CUfunction_t*, CUmodule_t, const char*) = nullptr;
+    CUresult_t (*FuncSetAttribute)(CUfunction_t, int, int) = nullptr;
+    CUresult_t (*LaunchKernel)(CUfunction_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**) = nullptr;
+};
+
+template <class F>
+bool sym(void* lib, const char* name, F& f) {
+    f = reinterpret_cast<F>(dlsym(lib, name));
+    return f != nullptr;
+}
+
+Api& api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* rtc = nullptr;
+        for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+            if ((rtc = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+        void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!rtc || !cu) return;
+        a.ok = sym(rtc, "nvrtcCreateProgram", a.CreateProgram) && sym(rtc, "nvrtcCompileProgram", a.CompileProgram) &&
+               sym(rtc, "nvrtcAddNameExpression", a.AddNameExpression) && sym(rtc, "nvrtcGetLoweredName", a.GetLoweredName) &&
+               sym(rtc, "nvrtcGetCUBINSize", a.GetCUBINSize) && sym(rtc, "nvrtcGetCUBIN", a.GetCUBIN) &&
+               sym(rtc, "nvrtcGetProgramLogSize", a.GetProgramLogSize) && sym(rtc, "nvrtcGetProgramLog", a.GetProgramLog) &&
+               sym(rtc, "nvrtcDestroyProgram", a.DestroyProgram) && sym(cu, "cuModuleLoadData", a.ModuleLoadData) &&
+               sym(cu, "cuModuleGetFunction", a.ModuleGetFunction) && sym(cu, "cuFuncSetAttribute", a.FuncSetAttribute) &&
+               sym(cu, "cuLaunchKernel", a.LaunchKernel);
+    });
+    return a;
+}
+
+// directory of the kernel sources: next to the library (.../lib/libsocp_b200.so -> .../csrc), or SOCP_B200_CSRC
+std::string csrc_dir() {
+    if (const char* e = getenv("SOCP_B200_CSRC")) return e;
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void*>(&csrc_dir), &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        const size_t s1 = p.rfind('/');
+        if (s1 != std::string::npos) {
+            const size_t s2 = p.rfind('/', s1 - 1);
+            if (s2 != std::string::npos) return p.substr(0, s2) + "/csrc";
+        }
+    }
+    return "csrc";
+}
+
+using Key = std::tuple<int, int, int, int, int, int, int>;      // device, n, kpoc, nsoc, sdim, rs, nwarp
+std::map<Key, CUfunction_t>& cache() { static std::map<Key, CUfunction_t> c; return c; }
+std::mutex& cache_mutex() { static std::mutex m; return m; }
+
+}  // namespace
+
+// Compiles (once per process and device) and returns the kernel for the plan's layout; nullptr when NVRTC / the driver
+// API are not available or the compilation fails (the reason goes to stderr when SOCP_B200_JIT_VERBOSE is set).
+void* lane_jit_get(const FLPlan& P, int device) {
+    Api& a = api();
+    if (!a.ok) return nullptr;
+    const Key key{device, P.jn, P.jkpoc, P.jnsoc, P.jsdim, P.jrs, P.pps / 32};
+    std::lock_guard<std::mutex> lock(cache_mutex());
+    auto it = cache().find(key);
+    if (it != cache().end()) return it->second;
+    CUfunction_t fn = nullptr;
+    const bool verbose = getenv("SOCP_B200_JIT_VERBOSE") != nullptr;
+    char inst[256];
+    snprintf(inst, sizeof inst, "socp::k_fused_lane<socp::LaneDims<%d, %d, %d, %d, %d>, 32, %d>", P.jn, P.jkpoc, P.jnsoc, P.jsdim,
+             P.jrs, P.pps / 32);
+    const std::string src = "#include \"fused_lane_dev.cuh\"\n";
+    nvrtcProgram_t prog = nullptr;
+    if (a.CreateProgram(&prog, src.c_str(), "lane_jit_instance.cu", 0, nullptr, nullptr) == 0) {
+        const std::string inc = "-I" + csrc_dir();
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-diag-suppress=607", inc.c_str()};
+        const char* lowered = nullptr;
+        std::vector<char> cubin;
+        if (a.AddNameExpression(prog, inst) == 0 && a.CompileProgram(prog, 5, opts) == 0 &&
+            a.GetLoweredName(prog, inst, &lowered) == 0 && lowered) {
+            size_t sz = 0;
+            if (a.GetCUBINSize(prog, &sz) == 0 && sz > 0) {
+                cubin.resize(sz);
+                CUmodule_t mod = nullptr;
+                cudaFree(0);                                     // the primary context of the current device
+                if (a.GetCUBIN(prog, cubin.data()) == 0 && a.ModuleLoadData(&mod, cubin.data()) == 0 &&
+                    a.ModuleGetFunction(&fn, mod, lowered) == 0 && fn) {
+                    // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
+                    if (a.FuncSetAttribute(fn, 8, (int)P.smem) != 0) fn = nullptr;
+                }
+            }
+        } else if (verbose) {
+            size_t n = 0;
+            a.GetProgramLogSize(prog, &n);
+            std::vector<char> log(n + 1, 0);
+            a.GetProgramLog(prog, log.data());
+            fprintf(stderr, "socp_b200: NVRTC could not build %s:\n%s\n", inst, log.data());
+        }
+        a.DestroyProgram(&prog);
+    }
+    if (verbose) fprintf(stderr, "socp_b200: lane kernel for %s %s\n", inst, fn ? "compiled at run time" : "NOT available");
+    cache()[key] = fn;
+    return fn;
+}
+
+bool lane_jit_launch(void* fn, const FLPlan& plan, FLArgs args, cudaStream_t stream) {
+    Api& a = api();
+    if (!a.ok || !fn) return false;
+    int grid;
+    fl_grid(plan, args.batch, 32, grid, args.cap);
+    void* params[] = {&args};
+    return a.LaunchKernel(reinterpret_cast<CUfunction_t>(fn), (unsigned)grid, 1, 1, (unsigned)(plan.pps / 32) * 32, 1, 1,
+                          (unsigned)plan.smem, stream, params, nullptr) == 0;
+}
+
+}  // namespace socp

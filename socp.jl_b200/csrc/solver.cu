@@ -829,10 +829,20 @@ enum { FUSED_NONE = 0, FUSED_V2 = 2, FUSED_V3 = 3, FUSED_LANE = 4 };
 // while fused_v2's one-warp teams (12 per SM, ~0.02 ms per iteration) retire 8.6M problems/s from the first wave on.
 // Measured crossover on C3 (profiles/r02_lane_c3_batch_sweep.txt): between 6k and 9k problems, i.e. about half of the
 // lane slots.  SOCP_B200_LANE=0 / 1 switches the kernel off / on regardless of the batch size (tests, experiments).
-bool lane_wanted(const Shard& sh, int batch) {
+bool lane_wanted(Shard& sh, int batch) {
     if (!sh.lane.fits) return false;
-    if (const char* e = getenv("SOCP_B200_LANE")) return atoi(e) != 0;
-    return 2LL * batch >= (long long)sh.lane.num_sms * sh.lane.pps;
+    bool want = 2LL * batch >= (long long)sh.lane.num_sms * sh.lane.pps;
+    if (const char* e = getenv("SOCP_B200_LANE")) want = atoi(e) != 0;
+    if (want && sh.lane.shape == 100 && !sh.lane.jit_fn) {
+        // a layout without a compile-time instantiation: specialise the kernel now (once per process and device; the
+        // callers are outside their timed regions); one-warp teams when that is not possible
+        if (!sh.lane.jit_tried) {
+            sh.lane.jit_tried = true;
+            sh.lane.jit_fn = lane_jit_get(sh.lane, sh.device);
+        }
+        if (!sh.lane.jit_fn) { sh.lane.fits = false; return false; }
+    }
+    return want;
 }
 void ensure_lane_ws(Shard& sh) {
     if (!sh.lane.d_ws) sh.lane.d_ws = sh.alloc<double>(sh.lane.ws_doubles * FL_WS_SETS, true);

@@ -20,7 +20,8 @@ UNITS = {
     "fused2.cu": ["common.cuh", "fused_common.cuh", "fused_v2.cuh"],
     "fused3.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
     "fused3_dyn.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
-    "fused_lane.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh"],
+    "fused_lane.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh", "fused_lane_dev.cuh"],
+    "lane_jit.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh", "fused_lane_dev.cuh"],
     "syrk_tma.cu": ["common.cuh", "syrk_tma.cuh"],
 }
 
@@ -60,7 +61,7 @@ def _compile(out_path: str, extra, verbose: bool = False, force: bool = False) -
             raise RuntimeError("nvcc failed compiling " + u)
         if verbose:
             sys.stderr.write(err)
-    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path] + objs,
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path] + objs + ["-ldl"],
                          capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -14,7 +14,7 @@ OUT_DIR = os.path.join(ROOT, "tests", "_build")
 OUT = os.path.join(OUT_DIR, "libsocp_emu.so")
 SRCS = [os.path.join(HERE, f) for f in ("emu_fused3.cpp", "emu_fused_lane.cpp")]
 DEPS = SRCS + [os.path.join(HERE, "simt_emu.h")] + \
-       [os.path.join(CSRC, f) for f in ("common.cuh", "fused_common.cuh", "fused_v3.cuh", "fused_lane.cuh")]
+       [os.path.join(CSRC, f) for f in ("common.cuh", "fused_common.cuh", "fused_v3.cuh", "fused_lane.cuh", "fused_lane_dev.cuh")]
 
 
 def build(force: bool = False) -> str:

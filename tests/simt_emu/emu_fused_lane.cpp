@@ -30,7 +30,7 @@ extern "C" int emu_fused_lane_solve(int n, int k, int ncones, const int* kind, c
     FLPlan P;
     fl_plan(P, n, 0, k, std::vector<int>(kind, kind + ncones), std::vector<int>(offs, offs + ncones),
             std::vector<int>(dim, dim + ncones), 227 * 1024, 148);
-    if (!P.fits) return -1;
+    if (!P.fits || P.shape == 100) return -1;      // (shape 100: specialised at run time with NVRTC on the device only)
     int counter = 0;
     std::vector<int> active(batch, 1), fail(batch, 0);
     FLArgs a;

@@ -827,3 +827,27 @@ def test_fused_panel_steps_small_batch_large_n():
         dsv.setup_iter(pr, osc)
         ox, oy, oz, os_ = dsv.solve_kkt(pr, osc, dx[q], np.zeros(0), dz[q], ds[q], fast_iprod=True)
         assert relerr(cx[q], ox) < 1e-9 and relerr(cz[q], oz) < 1e-9 and relerr(cs[q], os_) < 1e-9
+
+
+def test_lane_kernel_specialised_at_run_time():
+    """A tiny layout without a compile-time instantiation (n = 8, two orthant rows + six SOC(3)): the lane-per-problem
+    kernel is specialised for it with NVRTC on first use (csrc/lane_jit.cu) -- against the numpy oracle on a sample and
+    against the one-warp teams on the whole batch; a second handle with the same layout reuses the compiled kernel."""
+    cones = [sb.POC(0, 2)] + [sb.SOC(2 + 3 * i, 3) for i in range(6)]
+    prob = gen.random_feasible(2500, 8, 0, cones, 0.3, 0, 21)
+    run = lambda: sb.solve_socp_batch(prob, sb.SolverState(prob))
+    res = _with_env("SOCP_B200_LANE", "1", lambda: _with_env("SOCP_B200_JIT_VERBOSE", "1", run))
+    old = _with_env("SOCP_B200_LANE", "0", run)
+    again = _with_env("SOCP_B200_LANE", "1", run)
+    assert res.timings["path_used"] == sb.PATH_FUSED and res.timings["kernel_launches"] >= 1
+    assert np.array_equal(res.status, old.status)
+    for key in ("status", "iters", "pobj", "dobj", "x"):
+        assert np.array_equal(getattr(res, key), getattr(again, key)), key
+    conv = res.status == sb.STATUS_CONVERGED
+    assert conv.mean() > 0.9
+    assert np.all(np.abs(res.iters.astype(int) - old.iters.astype(int))[conv] <= 1)
+    same = conv & (res.iters == old.iters)
+    rel = lambda a, b: np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    d = np.maximum(rel(res.pobj[same], old.pobj[same]), rel(res.dobj[same], old.dobj[same]))
+    assert same.mean() > 0.9 and np.quantile(d, 0.99) <= 1e-6, (same.mean(), d.max())
+    _check_batch(prob, res, [q for q in range(0, 2500, 250) if conv[q]][:6])

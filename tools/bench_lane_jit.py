@@ -1,0 +1,23 @@
+#!/usr/bin/env python
+"""Device-resident solve time of a tiny layout WITHOUT a compile-time instantiation of the lane-per-problem kernel: the
+kernel specialised at run time (NVRTC, csrc/lane_jit.cu) against fused_v2's one-warp teams.
+usage: python tools/bench_lane_jit.py [batch]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "socp.jl_b200"))
+import numpy as np
+import socp_b200 as sb
+from socp_b200 import generators as gen
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+layouts = {"n=8: POC 2 + 6 x SOC(3)": (8, [sb.POC(0, 2)] + [sb.SOC(2 + 3 * i, 3) for i in range(6)]),
+           "n=10: 8 x SOC(5)": (10, [sb.SOC(5 * i, 5) for i in range(8)])}
+for name, (n, cones) in layouts.items():
+    prob = gen.random_feasible(B, n, 0, cones, 0.3, 0, 21)
+    for lane in ("1", "0"):
+        os.environ["SOCP_B200_LANE"] = lane
+        ss = sb.SolverState(prob)
+        t0 = time.time(); ss.load(prob); sb.solve_socp_batch(prob, ss, reload=False); first = time.time() - t0
+        ms = min(sb.solve_socp_batch(prob, ss, reload=False).timings["solve_ms"] for _ in range(3))
+        res = sb.solve_socp_batch(prob, ss, reload=False)
+        print(f"{name:28s} batch {B} {'lane kernel (run-time specialised)' if lane == '1' else 'one-warp teams (fused_v2)          '}: "
+              f"{ms:8.3f} ms = {B / ms / 1e3:6.2f}M problems/s, converged {(res.status == 0).mean():.4f}, first call {first:.1f} s")
