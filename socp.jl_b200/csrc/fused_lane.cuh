@@ -34,7 +34,7 @@
 //
 // Restrictions: p = 0, no `sing` problems (callers fall back to fused_v2 / the tiled path); layouts of the family
 // "positive-orthant block first, then equal second-order cones".  BASELINE.json's C3 (and a small test layout) are
-// instantiated at compile time in fused_lane.cu; any other layout of the family with n <= 12 is specialised at run
+// instantiated at compile time in fused_lane.cu; any other layout of the family (n <= 16) is specialised at run
 // time with NVRTC on first use (lane_jit.cu: the device code lives in fused_lane_dev.cuh, free of host headers).
 #pragma once
 #include "fused_lane_dev.cuh"
@@ -103,8 +103,8 @@ inline void fl_plan(FLPlan& P, int n, int p, int k, const std::vector<int>& kind
         P.shape = 3; spl = LaneT1::SM_PER_LANE; wpl = LaneT1::WS_PER_LANE; P.pps = lane_pps(LaneT1::SM_PER_LANE, dev_smem);
     } else {
         // no compile-time instantiation: a layout of the same family (orthant rows first, then equal second-order cones,
-        // p = 0, n <= 12 so that the packed H fits the registers) is specialised at run time with NVRTC (lane_jit.cu)
-        if (getenv("SOCP_B200_NO_LANE_JIT") || p != 0 || n < 1 || n > 12 || k > 96) return;
+        // p = 0, n <= 16; up to n = 12 the packed H fits the registers) is specialised at run time with NVRTC (lane_jit.cu)
+        if (getenv("SOCP_B200_NO_LANE_JIT") || p != 0 || n < 1 || n > 16 || k > 96) return;
         int kpoc = 0, nsoc = 0, sdim = 0;
         for (size_t i = 0; i < kind.size(); ++i) {
             if (kind[i] == KIND_POC) { if (nsoc) return; kpoc += dim[i]; }
