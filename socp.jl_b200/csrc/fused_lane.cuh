@@ -33,14 +33,16 @@
 //     (lanes in use per warp) and the ring depth stay template parameters for the measurements in profiles/.
 //
 // Restrictions: p = 0, no `sing` problems (callers fall back to fused_v2 / the tiled path); layouts of the family
-// "positive-orthant block first, then equal second-order cones".  BASELINE.json's C3 (and a small test layout) are
-// instantiated at compile time in fused_lane.cu; any other layout of the family (n <= 16) is specialised at run
-// time with NVRTC on first use (lane_jit.cu: the device code lives in fused_lane_dev.cuh, free of host headers).
+// "positive-orthant rows first, then second-order cones back to back" (n <= 16, cone dimensions 2..8, at most six runs of
+// equal cones).  BASELINE.json's C3 (and a small test layout) are instantiated at compile time in fused_lane.cu; any
+// other layout of the family is specialised at run time with NVRTC on first use (lane_jit.cu: the device code lives in
+// fused_lane_dev.cuh, free of host headers).
 #pragma once
 #include "fused_lane_dev.cuh"
 #include <vector>
 #include <algorithm>
 #include <cstdlib>
+#include <utility>
 
 namespace socp {
 
@@ -60,9 +62,28 @@ inline bool lane_layout_matches(int N, int KPOC, int NSOC, int SDIM, int n, int 
     }
     return kpoc == KPOC && nsoc == NSOC;
 }
-template <class D>
-inline bool lane_matches(int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs, const std::vector<int>& dim) {
-    return lane_layout_matches(D::N, D::KPOC, D::NSOC, D::SDIM, n, p, k, kind, offs, dim);
+// the family of the kernel: orthant rows first, then second-order cones back to back; returns the cones as groups of
+// consecutive equal dimensions (count, dim) and the number of orthant rows
+inline bool lane_family(int p, int k, const std::vector<int>& kind, const std::vector<int>& offs, const std::vector<int>& dim,
+                        int& kpoc, std::vector<std::pair<int, int>>& groups) {
+    kpoc = 0;
+    groups.clear();
+    if (p != 0) return false;
+    int at = 0;
+    bool soc_seen = false;
+    for (size_t i = 0; i < kind.size(); ++i) {
+        if (offs[i] != at) return false;
+        if (kind[i] == KIND_POC) {
+            if (soc_seen) return false;
+            kpoc += dim[i];
+        } else {
+            soc_seen = true;
+            if (!groups.empty() && groups.back().second == dim[i]) ++groups.back().first;
+            else groups.push_back({1, dim[i]});
+        }
+        at += dim[i];
+    }
+    return at == k;
 }
 // problems in flight per SM: what the shared memory holds, in whole warps, at most four warps
 inline int lane_pps(int sm_per_lane, int dev_smem) { return std::min(128, (int)(dev_smem / (sm_per_lane * sizeof(double))) / 32 * 32); }
@@ -76,7 +97,8 @@ constexpr int FL_WS_SETS = 2;               // launches that may overlap use dif
 struct FLPlan {
     bool fits = false;
     int shape = 0;          // 1: LaneC3, 2: LaneC3r2, 3: LaneT1; 100: specialised at run time (lane_jit.cu)
-    int jn = 0, jkpoc = 0, jnsoc = 0, jsdim = 0, jrs = 1;      // the layout of shape 100
+    int jn = 0, jkpoc = 0, jrs = 1;                            // the layout of shape 100: orthant rows, then
+    std::vector<std::pair<int, int>> jgroups;                  // groups of (count, dimension) equal cones
     void* jit_fn = nullptr; // ... and its kernel once compiled (CUfunction)
     bool jit_tried = false;
     int pps = 64;           // problems in flight per SM (a multiple of 32)
@@ -96,30 +118,32 @@ inline void fl_plan(FLPlan& P, int n, int p, int k, const std::vector<int>& kind
     P.shape = 0;
     int spl = 0, wpl = 0;
     const char* rs2 = getenv("SOCP_B200_LANE_RS2");      // experiment switch: the deeper ring, fewer problems per SM
-    if (lane_matches<LaneC3>(n, p, k, kind, offs, dim)) {
+    if (lane_layout_matches(12, 0, 10, 4, n, p, k, kind, offs, dim)) {
         if (rs2 && atoi(rs2)) { P.shape = 2; spl = LaneC3r2::SM_PER_LANE; wpl = LaneC3r2::WS_PER_LANE; P.pps = lane_pps(LaneC3r2::SM_PER_LANE, dev_smem); }
         else { P.shape = 1; spl = LaneC3::SM_PER_LANE; wpl = LaneC3::WS_PER_LANE; P.pps = lane_pps(LaneC3::SM_PER_LANE, dev_smem); }
-    } else if (lane_matches<LaneT1>(n, p, k, kind, offs, dim)) {
+    } else if (lane_layout_matches(6, 5, 3, 3, n, p, k, kind, offs, dim)) {
         P.shape = 3; spl = LaneT1::SM_PER_LANE; wpl = LaneT1::WS_PER_LANE; P.pps = lane_pps(LaneT1::SM_PER_LANE, dev_smem);
     } else {
         // no compile-time instantiation: a layout of the same family (orthant rows first, then equal second-order cones,
         // p = 0, n <= 16; up to n = 12 the packed H fits the registers) is specialised at run time with NVRTC (lane_jit.cu)
         if (getenv("SOCP_B200_NO_LANE_JIT") || p != 0 || n < 1 || n > 16 || k > 96) return;
-        int kpoc = 0, nsoc = 0, sdim = 0;
-        for (size_t i = 0; i < kind.size(); ++i) {
-            if (kind[i] == KIND_POC) { if (nsoc) return; kpoc += dim[i]; }
-            else { if (nsoc && dim[i] != sdim) return; sdim = dim[i]; ++nsoc; }
+        int kpoc = 0, nsoc = 0;
+        std::vector<std::pair<int, int>> groups;
+        if (!lane_family(p, k, kind, offs, dim, kpoc, groups) || groups.empty() || groups.size() > 6) return;
+        for (const auto& g : groups) {
+            if (g.second < 2 || g.second > 8) return;
+            nsoc += g.first;
         }
-        if (nsoc < 1 || sdim < 2 || sdim > 8 || !lane_layout_matches(n, kpoc, nsoc, sdim, n, p, k, kind, offs, dim)) return;
         const int np = (n + 1) / 2 * 2;
-        const int state = 5 * k + kpoc + 4 * nsoc;                       // LaneDims::SM_STATE
+        const int state = 5 * k + kpoc + 4 * nsoc;                       // LaneDimsG::SM_STATE
         P.jrs = (k % 2 == 0 && lane_pps(state + 2 * 5 * np, dev_smem) >= 128) ? 2 : 1;
-        spl = state + P.jrs * 5 * np;                                    // + LaneDims::SM_RING
-        wpl = k * np + k + n + n * (n + 1) / 2 + 2 * n + 4 * k;          // LaneDims::WS_PER_LANE
+        spl = state + P.jrs * 5 * np;                                    // + LaneDimsG::SM_RING
+        wpl = k * np + k + n + n * (n + 1) / 2 + 2 * n + 4 * k;          // LaneDimsG::WS_PER_LANE
         P.pps = lane_pps(spl, dev_smem);
         if (P.pps < 32) return;
+        P.jgroups = groups;
         P.shape = 100;
-        P.jn = n; P.jkpoc = kpoc; P.jnsoc = nsoc; P.jsdim = sdim;
+        P.jn = n; P.jkpoc = kpoc;
     }
     // only what fused_lane.cu instantiates: 96 (or 64) problems per SM for C3, 64 with the deeper ring, 128 for T1
     const char* pe = getenv("SOCP_B200_LANE_PPS");       // experiment switch: 64 problems per SM on the C3 layout

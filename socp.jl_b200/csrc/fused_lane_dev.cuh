@@ -6,10 +6,18 @@
 
 namespace socp {
 
-template <int N_, int KPOC_, int NSOC_, int SDIM_, int RS_>
-struct LaneDims {
-    static constexpr int N = N_, KPOC = KPOC_, NSOC = NSOC_, SDIM = SDIM_;
-    static constexpr int K = KPOC_ + NSOC_ * SDIM_;
+// COUNT consecutive second-order cones of dimension DIM
+template <int COUNT_, int DIM_>
+struct ConeGroup { static constexpr int COUNT = COUNT_, DIM = DIM_; };
+// what the kernel's cone loops see of one group: its first row in a k-vector and the index of its first cone
+template <int COUNT_, int DIM_, int OFF_, int C0_>
+struct ConeGroupAt { static constexpr int COUNT = COUNT_, DIM = DIM_, OFF = OFF_, C0 = C0_; };
+
+template <int N_, int KPOC_, int RS_, class... Gs>
+struct LaneDimsG {
+    static constexpr int N = N_, KPOC = KPOC_;
+    static constexpr int NSOC = (0 + ... + Gs::COUNT);    // second-order cones: groups of equal cones, in order
+    static constexpr int K = KPOC_ + (0 + ... + (Gs::COUNT * Gs::DIM));
     static constexpr int NH = N_ * (N_ + 1) / 2;
     static constexpr int NP = (N_ + 1) / 2 * 2;           // row stride of G in the workspace (rows are runs of double2)
     static constexpr int RS = RS_;                        // rows per stage of the G ring
@@ -20,7 +28,7 @@ struct LaneDims {
     enum { V_LAM = 0, V_WB, V_K0, V_K2, V_U, NVEC };
     static constexpr int O_IWB = NVEC * K;
     static constexpr int O_CS = O_IWB + KPOC_;            // 4 per cone: eta, 1/eta, 1/(1+w0), |lam_1|^2
-    static constexpr int SM_STATE = O_CS + 4 * NSOC_;
+    static constexpr int SM_STATE = O_CS + 4 * NSOC;
     static constexpr int SM_RING = RS * NS * NP;
     static constexpr int SM_PER_LANE = SM_STATE + SM_RING;
     // global workspace (L2 resident), doubles per lane: G (row-major k x NP, as double2 pairs), h, c, the packed factor,
@@ -28,7 +36,21 @@ struct LaneDims {
     static constexpr int W_G = 0, W_H = K * NP, W_C = W_H + K, W_L = W_C + N_, W_X = W_L + NH, W_DX = W_X + N_,
                          W_DZ = W_DX + N_, W_DSC = W_DZ + K, W_S = W_DSC + K, W_Z = W_S + K;
     static constexpr int WS_PER_LANE = W_Z + K;
+    // f(ConeGroupAt<...>{}) for every group, in order
+    template <class F>
+    __device__ __forceinline__ static void for_groups(F&& f) { walk<KPOC_, 0, Gs...>(f); }
+    template <int OFF, int C0, class F>
+    __device__ __forceinline__ static void walk(F&) {}
+    template <int OFF, int C0, class G, class... Rest, class F>
+    __device__ __forceinline__ static void walk(F& f) {
+        f(ConeGroupAt<G::COUNT, G::DIM, OFF, C0>{});
+        walk<OFF + G::COUNT * G::DIM, C0 + G::COUNT, Rest...>(f);
+    }
 };
+// the common case: NSOC equal cones of dimension SDIM
+template <int N_, int KPOC_, int NSOC_, int SDIM_, int RS_>
+using LaneDims = LaneDimsG<N_, KPOC_, RS_, ConeGroup<NSOC_, SDIM_>>;
+
 
 
 struct FLArgs {
@@ -136,7 +158,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
 #ifndef SOCP_SIMT_EMU
     extern __shared__ __align__(16) double fl_sm[];
 #endif
-    constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NSOC = D::NSOC, SDIM = D::SDIM, NH = D::NH, NP = D::NP, RS = D::RS, NS = D::NS;
+    constexpr int N = D::N, K = D::K, KPOC = D::KPOC, NH = D::NH, NP = D::NP, RS = D::RS, NS = D::NS;
     constexpr unsigned MASK = LPW == 32 ? 0xffffffffu : ((1u << LPW) - 1u);
     // measured on C3: interleaving five cones per loop body instead of two, and four partial sums per row instead of
     // two, made the kernel slower (16.5M -> 13.4M problems/s at 16 lanes per warp): code size, not chain length
@@ -183,17 +205,18 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         llacc = fma(lv, lv, llacc);
                     }
                     // s, z and h come from the L2 workspace: the loads of the next two cones are in flight under this one
-                    double sn[SDIM], zn[SDIM], hn[SDIM], sm2[SDIM], zm2[SDIM], hm2[SDIM];
+                    D::for_groups([&](auto gtag) {
+                        constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
+                        double sn[SDIM], zn[SDIM], hn[SDIM], sm2[SDIM], zm2[SDIM], hm2[SDIM];
 #pragma unroll
-                    for (int e = 0; e < SDIM; ++e) {
-                        sn[e] = NSOC ? WO(D::W_S, KPOC + e) : 0.0; zn[e] = NSOC ? WO(D::W_Z, KPOC + e) : 0.0;
-                        hn[e] = NSOC ? WO(D::W_H, KPOC + e) : 0.0;
-                        sm2[e] = NSOC > 1 ? WO(D::W_S, KPOC + SDIM + e) : 0.0; zm2[e] = NSOC > 1 ? WO(D::W_Z, KPOC + SDIM + e) : 0.0;
-                        hm2[e] = NSOC > 1 ? WO(D::W_H, KPOC + SDIM + e) : 0.0;
-                    }
+                        for (int e = 0; e < SDIM; ++e) {
+                            sn[e] = WO(D::W_S, GOFF + e); zn[e] = WO(D::W_Z, GOFF + e); hn[e] = WO(D::W_H, GOFF + e);
+                            sm2[e] = GCNT > 1 ? WO(D::W_S, GOFF + SDIM + e) : 0.0; zm2[e] = GCNT > 1 ? WO(D::W_Z, GOFF + SDIM + e) : 0.0;
+                            hm2[e] = GCNT > 1 ? WO(D::W_H, GOFF + SDIM + e) : 0.0;
+                        }
 #pragma unroll CU
-                    for (int c = 0; c < NSOC; ++c) {                                    // src/scalings.jl:32-99
-                        const int o = KPOC + c * SDIM;
+                        for (int cc = 0; cc < GCNT; ++cc) {                                    // src/scalings.jl:32-99
+                        const int c = GC0 + cc, o = GOFF + cc * SDIM;
                         double sv[SDIM], zv[SDIM];
 #pragma unroll
                         for (int e = 0; e < SDIM; ++e) {
@@ -202,7 +225,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                             SV(D::V_K2, o + e) = hn[e] - sn[e];
                             sn[e] = sm2[e]; zn[e] = zm2[e]; hn[e] = hm2[e];
                         }
-                        if (c + 2 < NSOC) {
+                        if (cc + 2 < GCNT) {
 #pragma unroll
                             for (int e = 0; e < SDIM; ++e) {
                                 sm2[e] = WO(D::W_S, o + 2 * SDIM + e); zm2[e] = WO(D::W_Z, o + 2 * SDIM + e);
@@ -246,6 +269,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         gap += sv[0] * zv[0] + sz;
                         llacc += l0 * l0 + llt;
                     }
+                    });
                     // negated residuals (:110-118, :125) in one pass over G: dx = -G'z - c, dz = -G x - s + h
                     double rx[N], xr[N];
 #pragma unroll
@@ -411,10 +435,14 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                     SV(D::V_WB, r) = 0.0;
                 }
                 for (int i = 0; i < KPOC; ++i) { SV(D::V_WB, i) = 1.0; SO(D::O_IWB, i) = 1.0; }
-                for (int c = 0; c < NSOC; ++c) {
-                    SV(D::V_WB, KPOC + c * SDIM) = 1.0;
+                D::for_groups([&](auto gtag) {
+                    constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
+                    for (int cc = 0; cc < GCNT; ++cc) {
+                        const int c = GC0 + cc;
+                    SV(D::V_WB, GOFF + cc * SDIM) = 1.0;
                     SO(D::O_CS, 4 * c + 0) = 1.0; SO(D::O_CS, 4 * c + 1) = 1.0; SO(D::O_CS, 4 * c + 2) = 0.5; SO(D::O_CS, 4 * c + 3) = 0.0;
                 }
+                });
 #pragma unroll
                 for (int j = 0; j < N; ++j) WO(D::W_DX, j) = -WO(D::W_C, j);
                 sc = 1.0;
@@ -433,9 +461,11 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                     const double kz = sc * dzr[i] - w * kk;
                     SV(D::V_K0, i) = kk; SV(D::V_K2, i) = kz; SV(D::V_U, i) = iw * iw * kz;
                 }
+                D::for_groups([&](auto gtag) {
+                    constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
 #pragma unroll
-                for (int c = 0; c < NSOC; ++c) {
-                    const int o = KPOC + c * SDIM;
+                    for (int cc = 0; cc < GCNT; ++cc) {
+                    const int c = GC0 + cc, o = GOFF + cc * SDIM;
                     const double eta = SO(D::O_CS, 4 * c + 0), ie = SO(D::O_CS, 4 * c + 1), r1w = SO(D::O_CS, 4 * c + 2),
                                  llt = SO(D::O_CS, 4 * c + 3);
                     const double ie2 = ie * ie;
@@ -480,6 +510,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                     SV(D::V_K2, o) = k2v[0];
                     SV(D::V_U, o) = ie2 * (2.0 * w0 * qv - k2v[0]);
                 }
+                });
             }
             // ------------------------------------------------ n0 = G'u + sc dx                src/densesolver.jl:66-67
             double n0[N];
@@ -512,12 +543,21 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                 fl_stream_rows<K, NP, LPW, RS, NS>(G2, ring, [&](int r, const double (&g)[NP]) {
                     double d, wq = 0.0, f = 0.0;
                     int e = -1;
+                    bool last = false;
                     if (r < KPOC) {
                         const double iw = SO(D::O_IWB, r);
                         d = iw * iw;
                     } else {
-                        const int c = (r - KPOC) / SDIM;
-                        e = (r - KPOC) - c * SDIM;
+                        int c = 0;
+                        D::for_groups([&](auto gtag) {
+                            constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
+                            if (r >= GOFF && r < GOFF + GCNT * SDIM) {
+                                const int cc = (r - GOFF) / SDIM;
+                                e = (r - GOFF) - cc * SDIM;
+                                c = GC0 + cc;
+                                last = e == SDIM - 1;
+                            }
+                        });
                         const double ie = SO(D::O_CS, 4 * c + 1);
                         const double ie2 = ie * ie;
                         const double wb = SV(D::V_WB, r);
@@ -534,7 +574,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
 #pragma unroll
                         for (int q = j; q < N; ++q) Lr[TRI(q, j)] = fma(g[q], t, Lr[TRI(q, j)]);
                     }
-                    if (e == SDIM - 1) {
+                    if (last) {
 #pragma unroll
                         for (int j = 0; j < N; ++j) hq[j] *= f;
 #pragma unroll
@@ -602,8 +642,10 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                     for (int j = 0; j < N; ++j) WO(D::W_X, j) = n0[j];
                     double mp = -INFINITY, md = -INFINITY;
                     for (int i = 0; i < KPOC; ++i) { const double v = SV(D::V_U, i); mp = fmax(mp, v); md = fmax(md, -v); }
-                    for (int c = 0; c < NSOC; ++c) {
-                        const int o = KPOC + c * SDIM;
+                    D::for_groups([&](auto gtag) {
+                        constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
+                        for (int cc = 0; cc < GCNT; ++cc) {
+                        const int c = GC0 + cc, o = GOFF + cc * SDIM;
                         double sq = 0.0;
 #pragma unroll
                         for (int e = 1; e < SDIM; ++e) { const double v = SV(D::V_U, o + e); sq = fma(v, v, sq); }
@@ -611,6 +653,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         mp = fmax(mp, nr + z0);
                         md = fmax(md, nr - z0);
                     }
+                    });
                     const bool shp = !(fabs(mp) < prm.init_eps), shd = !(fabs(md) < prm.init_eps);
                     const double shs = shp ? 1.0 + mp : 0.0, shz = shd ? 1.0 + md : 0.0;
                     for (int i = 0; i < KPOC; ++i) {
@@ -618,8 +661,10 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         WO(D::W_S, i) = shp ? -z0 + shs : -z0;
                         WO(D::W_Z, i) = shd ? z0 + shz : z0;
                     }
-                    for (int c = 0; c < NSOC; ++c) {
-                        const int o = KPOC + c * SDIM;
+                    D::for_groups([&](auto gtag) {
+                        constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
+                        for (int cc = 0; cc < GCNT; ++cc) {
+                        const int c = GC0 + cc, o = GOFF + cc * SDIM;
 #pragma unroll
                         for (int e = 0; e < SDIM; ++e) {
                             const double z0 = SV(D::V_U, o + e);
@@ -627,6 +672,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                             WO(D::W_Z, o + e) = (e == 0 && shd) ? z0 + shz : z0;
                         }
                     }
+                    });
                     need_top = true;
                     phase = 1;
                 } else {
@@ -650,9 +696,11 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         WO(D::W_DSC, i) = -(kt2 * kt3);
                         if (chk) fl |= !isfinite(cz) | !isfinite(csx);
                     }
+                    D::for_groups([&](auto gtag) {
+                        constexpr int SDIM = decltype(gtag)::DIM, GCNT = decltype(gtag)::COUNT, GOFF = decltype(gtag)::OFF, GC0 = decltype(gtag)::C0;
 #pragma unroll CU
-                    for (int c = 0; c < NSOC; ++c) {
-                        const int o = KPOC + c * SDIM;
+                        for (int cc = 0; cc < GCNT; ++cc) {
+                        const int c = GC0 + cc, o = GOFF + cc * SDIM;
                         const double eta = SO(D::O_CS, 4 * c + 0), ie = SO(D::O_CS, 4 * c + 1), r1w = SO(D::O_CS, 4 * c + 2),
                                      llt = SO(D::O_CS, 4 * c + 3);
                         const double ie2 = ie * ie;
@@ -723,6 +771,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_lane(const FLArgs a) {
                         WO(D::W_DSC, o) = -dot;                                         // src/vectors.jl:66-69
                         if (chk) fl |= !isfinite(czv[0]) | !isfinite(csv[0]);
                     }
+                    });
                     const double tstep = step_from_t(mx);                               // src/solver.jl:130 / :145
                     if (phase == 1) {
                         // centering parameter (:130-134) and the combined right-hand side (:136-140)

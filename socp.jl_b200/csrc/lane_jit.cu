@@ -11,7 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
-#include <tuple>
+#include <utility>
 #include <vector>
 
 namespace socp {
@@ -81,7 +81,7 @@ std::string csrc_dir() {
     return "csrc";
 }
 
-using Key = std::tuple<int, int, int, int, int, int, int>;      // device, n, kpoc, nsoc, sdim, rs, nwarp
+using Key = std::pair<int, std::string>;      // device, the kernel instance
 std::map<Key, CUfunction_t>& cache() { static std::map<Key, CUfunction_t> c; return c; }
 std::mutex& cache_mutex() { static std::mutex m; return m; }
 
@@ -92,15 +92,16 @@ std::mutex& cache_mutex() { static std::mutex m; return m; }
 void* lane_jit_get(const FLPlan& P, int device) {
     Api& a = api();
     if (!a.ok) return nullptr;
-    const Key key{device, P.jn, P.jkpoc, P.jnsoc, P.jsdim, P.jrs, P.pps / 32};
+    std::string groups;
+    for (const auto& g : P.jgroups) groups += ", socp::ConeGroup<" + std::to_string(g.first) + ", " + std::to_string(g.second) + ">";
+    const std::string inst = "socp::k_fused_lane<socp::LaneDimsG<" + std::to_string(P.jn) + ", " + std::to_string(P.jkpoc) + ", " +
+                             std::to_string(P.jrs) + groups + ">, 32, " + std::to_string(P.pps / 32) + ">";
+    const Key key{device, inst};
     std::lock_guard<std::mutex> lock(cache_mutex());
     auto it = cache().find(key);
     if (it != cache().end()) return it->second;
     CUfunction_t fn = nullptr;
     const bool verbose = getenv("SOCP_B200_JIT_VERBOSE") != nullptr;
-    char inst[256];
-    snprintf(inst, sizeof inst, "socp::k_fused_lane<socp::LaneDims<%d, %d, %d, %d, %d>, 32, %d>", P.jn, P.jkpoc, P.jnsoc, P.jsdim,
-             P.jrs, P.pps / 32);
     const std::string src = "#include \"fused_lane_dev.cuh\"\n";
     nvrtcProgram_t prog = nullptr;
     if (a.CreateProgram(&prog, src.c_str(), "lane_jit_instance.cu", 0, nullptr, nullptr) == 0) {
@@ -108,8 +109,8 @@ void* lane_jit_get(const FLPlan& P, int device) {
         const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-diag-suppress=607", inc.c_str()};
         const char* lowered = nullptr;
         std::vector<char> cubin;
-        if (a.AddNameExpression(prog, inst) == 0 && a.CompileProgram(prog, 5, opts) == 0 &&
-            a.GetLoweredName(prog, inst, &lowered) == 0 && lowered) {
+        if (a.AddNameExpression(prog, inst.c_str()) == 0 && a.CompileProgram(prog, 5, opts) == 0 &&
+            a.GetLoweredName(prog, inst.c_str(), &lowered) == 0 && lowered) {
             size_t sz = 0;
             if (a.GetCUBINSize(prog, &sz) == 0 && sz > 0) {
                 cubin.resize(sz);
@@ -126,11 +127,11 @@ void* lane_jit_get(const FLPlan& P, int device) {
             a.GetProgramLogSize(prog, &n);
             std::vector<char> log(n + 1, 0);
             a.GetProgramLog(prog, log.data());
-            fprintf(stderr, "socp_b200: NVRTC could not build %s:\n%s\n", inst, log.data());
+            fprintf(stderr, "socp_b200: NVRTC could not build %s:\n%s\n", inst.c_str(), log.data());
         }
         a.DestroyProgram(&prog);
     }
-    if (verbose) fprintf(stderr, "socp_b200: lane kernel for %s %s\n", inst, fn ? "compiled at run time" : "NOT available");
+    if (verbose) fprintf(stderr, "socp_b200: lane kernel for %s %s\n", inst.c_str(), fn ? "compiled at run time" : "NOT available");
     cache()[key] = fn;
     return fn;
 }

@@ -30,7 +30,12 @@ extern "C" int emu_fused_lane_solve(int n, int k, int ncones, const int* kind, c
     FLPlan P;
     fl_plan(P, n, 0, k, std::vector<int>(kind, kind + ncones), std::vector<int>(offs, offs + ncones),
             std::vector<int>(dim, dim + ncones), 227 * 1024, 148);
-    if (!P.fits || P.shape == 100) return -1;      // (shape 100: specialised at run time with NVRTC on the device only)
+    // (shape 100: specialised at run time with NVRTC on the device only; one mixed-dimension layout of that kind is
+    // instantiated here so that the grouped cone loops are covered on the CPU)
+    using LaneT2 = LaneDimsG<6, 2, 1, ConeGroup<2, 3>, ConeGroup<1, 5>>;
+    const bool t2 = P.fits && P.shape == 100 && P.jn == 6 && P.jkpoc == 2 && P.jrs == 1 &&
+                    P.jgroups == std::vector<std::pair<int, int>>{{2, 3}, {1, 5}};
+    if (!P.fits || (P.shape == 100 && !t2)) return -1;
     int counter = 0;
     std::vector<int> active(batch, 1), fail(batch, 0);
     FLArgs a;
@@ -45,6 +50,11 @@ extern "C" int emu_fused_lane_solve(int n, int k, int ncones, const int* kind, c
         case 16: run<D, 16, PPS / 16>(P, a, grid_cap, order); break;       \
         case 8: run<D, 8, PPS / 8>(P, a, grid_cap, order); break;          \
         default: run<D, 32, PPS / 32>(P, a, grid_cap, order); break;       \
+    }
+    if (t2) {
+        if (P.pps != 128) return -1;
+        FL_RUN(LaneT2, 128)
+        return 0;
     }
     if (P.shape == 1 && P.pps == 96) { FL_RUN(LaneC3, 96) }
     else if (P.shape == 1) { FL_RUN(LaneC3, 64) }

@@ -92,3 +92,12 @@ def test_c3_deeper_ring_variant(monkeypatch):
     res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=16)
     for key in ("x", "z", "s", "pobj", "dobj", "iters", "status"):
         assert np.array_equal(res[key], ref[key]), key
+
+
+def test_cones_of_different_dimensions():
+    """Two SOC(3) and one SOC(5) after two orthant rows: the cone loops run group by group (LaneDimsG); on the device such
+    a layout is specialised at run time (csrc/lane_jit.cu), here the one instantiation of the emulator harness."""
+    cones = [sb.POC(0, 2), sb.SOC(2, 3), sb.SOC(5, 3), sb.SOC(8, 5)]
+    prob = gen.random_feasible(45, 6, 0, cones, 0.3, 0, 5)
+    res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=16, grid_cap=1)
+    check(prob, res, tol_obj=1e-6, tol_x=1e-4)

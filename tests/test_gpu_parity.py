@@ -830,10 +830,10 @@ def test_fused_panel_steps_small_batch_large_n():
 
 
 def test_lane_kernel_specialised_at_run_time():
-    """A tiny layout without a compile-time instantiation (n = 8, two orthant rows + six SOC(3)): the lane-per-problem
+    """A tiny layout without a compile-time instantiation (n = 8, two orthant rows + four SOC(3) + two SOC(5)): the lane-per-problem
     kernel is specialised for it with NVRTC on first use (csrc/lane_jit.cu) -- against the numpy oracle on a sample and
     against the one-warp teams on the whole batch; a second handle with the same layout reuses the compiled kernel."""
-    cones = [sb.POC(0, 2)] + [sb.SOC(2 + 3 * i, 3) for i in range(6)]
+    cones = [sb.POC(0, 2)] + [sb.SOC(2 + 3 * i, 3) for i in range(4)] + [sb.SOC(14, 5), sb.SOC(19, 5)]
     prob = gen.random_feasible(2500, 8, 0, cones, 0.3, 0, 21)
     run = lambda: sb.solve_socp_batch(prob, sb.SolverState(prob))
     res = _with_env("SOCP_B200_LANE", "1", lambda: _with_env("SOCP_B200_JIT_VERBOSE", "1", run))

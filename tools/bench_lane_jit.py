@@ -11,6 +11,8 @@ from socp_b200 import generators as gen
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 layouts = {"n=8: POC 2 + 6 x SOC(3)": (8, [sb.POC(0, 2)] + [sb.SOC(2 + 3 * i, 3) for i in range(6)]),
            "n=10: 8 x SOC(5)": (10, [sb.SOC(5 * i, 5) for i in range(8)]),
+           "n=9: POC 3 + 4 x SOC(3) + 3 x SOC(5) + SOC(4)": (9, [sb.POC(0, 3)] + [sb.SOC(3 + 3 * i, 3) for i in range(4)] +
+                                                             [sb.SOC(15 + 5 * i, 5) for i in range(3)] + [sb.SOC(30, 4)]),
            "n=14: 12 x SOC(4)": (14, [sb.SOC(4 * i, 4) for i in range(12)]),
            "n=16: POC 8 + 8 x SOC(4)": (16, [sb.POC(0, 8)] + [sb.SOC(8 + 4 * i, 4) for i in range(8)])}
 if len(sys.argv) > 2:
