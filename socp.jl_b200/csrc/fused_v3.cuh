@@ -25,8 +25,10 @@
 // infrastructure) as well.
 #pragma once
 #include "fused_common.cuh"
+#ifndef __CUDACC_RTC__          // (NVRTC compiles the device code of this file alone: run-time specialisation, fused_jit.cu)
 #include <vector>
 #include <algorithm>
+#endif
 
 namespace socp {
 
@@ -106,6 +108,8 @@ struct F3Plan : F3Offs {
     int* d_counter = nullptr;
     unsigned long long* d_clk = nullptr;   // 16 phase-cycle counters (SOCP_PHASE_TIMING builds, tools/phase_timing.py)
     const int* d_tables = nullptr;   // device copy of `tables` (srow_col[k] | scol_ptr[n+1] | scol_rows[nsing])
+    void* jit_fn = nullptr;          // the kernel specialised for this layout at run time (lane_jit.cu), if any,
+    int jit_teams = 0;               // and the number of teams per CTA it was built for
     int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
     int npad = 0, nb = 0, ntl = 0;
     int d0 = 0, kd = 0, kdpad = 0, ldg = 0, kshift = 0, kvl = 0;
@@ -116,6 +120,7 @@ struct F3Plan : F3Offs {
     int soc_offs[F2_MAX_SOC], soc_dim[F2_MAX_SOC];
 };
 
+#ifndef __CUDACC_RTC__
 // rowcol[i]: -1 = row i of G is empty in every problem, j >= 0 = its only nonzeros sit in column j, -2 = dense.
 // `tables` receives the device tables.  No CUDA calls (the simulator tests build plans too).
 inline void f3_plan(F3Plan& P, int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
@@ -178,6 +183,8 @@ inline void f3_plan(F3Plan& P, int n, int p, int k, const std::vector<int>& kind
     P.teams4 = 4 * P.smem + 256 <= (size_t)dev_smem_optin;
     P.fits = true;
 }
+
+#endif  // __CUDACC_RTC__
 
 // global arrays of one shard as the kernel sees them (filled from Ws by the host; the simulator fills it directly)
 struct F3Glob {
@@ -1409,7 +1416,7 @@ __global__ void __launch_bounds__(NW * 32 * TEAMS, MINB) k_fused3(const F3Args a
 // empty, rows 51..100 dense)
 using Dims3C2 = Dims3Static<4, 50, 1, 50, 1, 51, 51, 50, 1>;
 
-#ifndef SOCP_SIMT_EMU
+#if !defined(SOCP_SIMT_EMU) && !defined(__CUDACC_RTC__)
 template <int NW, int TEAMS, int MAXT, int MINB, class D>
 inline void fused3_launch(const F3Plan& plan, const F3Args& args, int grid, cudaStream_t stream) {
     const size_t smem = plan.smem * TEAMS;
@@ -1418,6 +1425,9 @@ inline void fused3_launch(const F3Plan& plan, const F3Args& args, int grid, cuda
 }
 void fused3_launch_c2(const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream);    // fused3.cu
 void fused3_launch_dyn(const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream);   // fused3_dyn.cu
+// run-time specialisation of the kernel for the plan's layout (lane_jit.cu)
+void* fused3_jit_get(const F3Plan& plan, int teams, int device);
+bool fused3_jit_launch(void* fn, const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream);
 
 // Solves problems [first, first + batch) of the shard.  counter_slot: which of the plan's work counters this launch
 // uses (launches that may overlap need different ones).  Batches that give every SM several problems run with four
@@ -1443,6 +1453,7 @@ inline void solve_fused3(const F3Plan& plan, const F3Glob& g, int first, int bat
     const int teams = (plan.teams4 && !(e4 && atoi(e4) == 1)) ? 4 : 1;
     const int grid = teams > 1 ? std::min(batch, plan.num_sms) : std::min(batch, plan.num_sms * plan.ctas_per_sm);
     if (allow_static && Dims3C2::matches(plan)) fused3_launch_c2(plan, args, teams, grid, stream);
+    else if (allow_static && plan.jit_fn && plan.jit_teams == teams && fused3_jit_launch(plan.jit_fn, plan, args, teams, grid, stream)) {}
     else fused3_launch_dyn(plan, args, teams, grid, stream);
 }
 // non-inline entry of solve_fused3, compiled once in fused3.cu (the kernels are instantiated there only)

@@ -6,6 +6,7 @@
 // libnvrtc and libcuda are loaded lazily with dlopen, so the library has no link-time dependency on either; when they
 // are missing, or the compilation fails, the caller falls back to fused_v2's one-warp teams.
 #include "fused_lane.cuh"
+#include "fused_v3.cuh"
 #include <dlfcn.h>
 #include <cstdio>
 #include <map>
@@ -87,24 +88,21 @@ std::mutex& cache_mutex() { static std::mutex m; return m; }
 
 }  // namespace
 
-// Compiles (once per process and device) and returns the kernel for the plan's layout; nullptr when NVRTC / the driver
-// API are not available or the compilation fails (the reason goes to stderr when SOCP_B200_JIT_VERBOSE is set).
-void* lane_jit_get(const FLPlan& P, int device) {
+// Compiles `inst` (an instantiation of a kernel template defined in `header`) once per process and device and returns
+// its CUfunction with `smem` bytes of dynamic shared memory enabled; nullptr when NVRTC / the driver API are not
+// available or the compilation fails (the reason goes to stderr when SOCP_B200_JIT_VERBOSE is set).
+static void* jit_kernel(const char* header, const std::string& inst, int device, size_t smem) {
     Api& a = api();
     if (!a.ok) return nullptr;
-    std::string groups;
-    for (const auto& g : P.jgroups) groups += ", socp::ConeGroup<" + std::to_string(g.first) + ", " + std::to_string(g.second) + ">";
-    const std::string inst = "socp::k_fused_lane<socp::LaneDimsG<" + std::to_string(P.jn) + ", " + std::to_string(P.jkpoc) + ", " +
-                             std::to_string(P.jrs) + groups + ">, 32, " + std::to_string(P.pps / 32) + ">";
     const Key key{device, inst};
     std::lock_guard<std::mutex> lock(cache_mutex());
     auto it = cache().find(key);
     if (it != cache().end()) return it->second;
     CUfunction_t fn = nullptr;
     const bool verbose = getenv("SOCP_B200_JIT_VERBOSE") != nullptr;
-    const std::string src = "#include \"fused_lane_dev.cuh\"\n";
+    const std::string src = std::string("#include \"") + header + "\"\n";
     nvrtcProgram_t prog = nullptr;
-    if (a.CreateProgram(&prog, src.c_str(), "lane_jit_instance.cu", 0, nullptr, nullptr) == 0) {
+    if (a.CreateProgram(&prog, src.c_str(), "socp_b200_jit_instance.cu", 0, nullptr, nullptr) == 0) {
         const std::string inc = "-I" + csrc_dir();
         const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-diag-suppress=607", inc.c_str()};
         const char* lowered = nullptr;
@@ -119,7 +117,7 @@ void* lane_jit_get(const FLPlan& P, int device) {
                 if (a.GetCUBIN(prog, cubin.data()) == 0 && a.ModuleLoadData(&mod, cubin.data()) == 0 &&
                     a.ModuleGetFunction(&fn, mod, lowered) == 0 && fn) {
                     // CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8
-                    if (a.FuncSetAttribute(fn, 8, (int)P.smem) != 0) fn = nullptr;
+                    if (a.FuncSetAttribute(fn, 8, (int)smem) != 0) fn = nullptr;
                 }
             }
         } else if (verbose) {
@@ -131,9 +129,46 @@ void* lane_jit_get(const FLPlan& P, int device) {
         }
         a.DestroyProgram(&prog);
     }
-    if (verbose) fprintf(stderr, "socp_b200: lane kernel for %s %s\n", inst.c_str(), fn ? "compiled at run time" : "NOT available");
+    if (verbose) fprintf(stderr, "socp_b200: %s %s\n", inst.c_str(), fn ? "compiled at run time" : "NOT available");
     cache()[key] = fn;
     return fn;
+}
+
+// the lane-per-problem kernel for the plan's layout (shape 100)
+void* lane_jit_get(const FLPlan& P, int device) {
+    std::string groups;
+    for (const auto& g : P.jgroups) groups += ", socp::ConeGroup<" + std::to_string(g.first) + ", " + std::to_string(g.second) + ">";
+    const std::string inst = "socp::k_fused_lane<socp::LaneDimsG<" + std::to_string(P.jn) + ", " + std::to_string(P.jkpoc) + ", " +
+                             std::to_string(P.jrs) + groups + ">, 32, " + std::to_string(P.pps / 32) + ">";
+    return jit_kernel("fused_lane_dev.cuh", inst, device, P.smem);
+}
+
+// The whole-solve kernel of fused_v3.cuh with the layout as compile-time constants (Dims3Static): what fused3.cu
+// instantiates for BASELINE.json's C2 only, for any layout with one orthant block and equal second-order cones whose
+// singleton rows are the identity block or absent.  2.3x over the runtime-dimension instantiation on C2.
+bool fused3_jit_shape(const F3Plan& P) {
+    if (!P.fits || P.nw != 4 || P.nsoc < 1) return false;
+    if (!(P.nsing == 0 || (P.ident && P.nsing == P.n))) return false;
+    for (int i = 0; i < P.nsoc; ++i)
+        if (P.soc_dim[i] != P.soc_dim[0] || P.soc_offs[i] != P.kpoc + i * P.soc_dim[0]) return false;
+    return P.k == P.kpoc + P.nsoc * P.soc_dim[0];
+}
+void* fused3_jit_get(const F3Plan& P, int teams, int device) {
+    if (!fused3_jit_shape(P)) return nullptr;
+    const int maxt = P.nb <= 4 ? 3 : (P.nb <= 7 ? 7 : 9);
+    const int minb = teams == 4 ? 1 : (P.nb <= 7 ? 4 : 3);
+    char inst[320];
+    snprintf(inst, sizeof inst, "socp::k_fused3<4, %d, %d, %d, socp::Dims3Static<4, %d, %d, %d, %d, %d, %d, %d, %d>>", teams, maxt,
+             minb, P.n, P.p, P.kpoc, P.nsoc, P.soc_dim[0], P.d0, P.kd, P.ident ? 1 : 0);
+    return jit_kernel("fused_v3.cuh", inst, device, P.smem * teams);
+}
+bool fused3_jit_launch(void* fn, const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream) {
+    Api& a = api();
+    if (!a.ok || !fn) return false;
+    F3Args copy = args;
+    void* params[] = {&copy};
+    return a.LaunchKernel(reinterpret_cast<CUfunction_t>(fn), (unsigned)grid, 1, 1, (unsigned)(128 * teams), 1, 1,
+                          (unsigned)(plan.smem * teams), stream, params, nullptr) == 0;
 }
 
 bool lane_jit_launch(void* fn, const FLPlan& plan, FLArgs args, cudaStream_t stream) {

@@ -782,6 +782,15 @@ void plan_fused3(const socp_handle* h, Shard& sh, const std::vector<int>& rowcol
     sh.fused3.d_tables = sh.d_f3_tables;
     sh.f3_planned = true;
     if (!sh.fused3.fits) return;
+    // a layout other than BASELINE.json's C2: the kernel with the layout as compile-time constants, built at run time
+    // (once per process, device and layout; lane_jit.cu) -- the runtime-dimension instantiation otherwise
+    sh.fused3.jit_fn = nullptr;
+    if (!Dims3C2::matches(sh.fused3) && !getenv("SOCP_B200_NO_F3_JIT") && !getenv("SOCP_B200_GENERIC_ONLY")) {
+        const char* e4 = getenv("SOCP_B200_F3_TEAMS");
+        const int teams = (sh.fused3.teams4 && !(e4 && atoi(e4) == 1)) ? 4 : 1;
+        sh.fused3.jit_fn = fused3_jit_get(sh.fused3, teams, sh.device);
+        sh.fused3.jit_teams = teams;
+    }
     // the tables are read by the launch that follows on the same stream; the host vector dies with this call, so
     // the copy must have left pageable memory before returning (cudaMemcpyAsync from pageable memory stages it)
     CK(cudaMemcpyAsync(sh.d_f3_tables, tables.data(), sizeof(int) * tables.size(), cudaMemcpyHostToDevice, stream));

@@ -851,3 +851,21 @@ def test_lane_kernel_specialised_at_run_time():
     d = np.maximum(rel(res.pobj[same], old.pobj[same]), rel(res.dobj[same], old.dobj[same]))
     assert same.mean() > 0.9 and np.quantile(d, 0.99) <= 1e-6, (same.mean(), d.max())
     _check_batch(prob, res, [q for q in range(0, 2500, 250) if conv[q]][:6])
+
+
+def test_fused3_specialised_at_run_time():
+    """A C2-like layout that is not BASELINE.json's (portfolio SOCPs with n = 40): the whole-solve kernel gets the layout
+    as compile-time constants through NVRTC (csrc/lane_jit.cu) -- against the numpy oracle on a sample and against the
+    runtime-dimension instantiation on the whole batch."""
+    prob = gen.portfolio(600, 40)
+    run = lambda: sb.solve_socp_batch(prob, sb.SolverState(prob))
+    res = _with_env("SOCP_B200_JIT_VERBOSE", "1", run)
+    dyn = _with_env("SOCP_B200_NO_F3_JIT", "1", run)
+    assert res.timings["path_used"] == sb.PATH_FUSED
+    assert (res.status == sb.STATUS_CONVERGED).all()
+    assert np.array_equal(res.status, dyn.status)
+    assert np.all(np.abs(res.iters.astype(int) - dyn.iters.astype(int)) <= 1)
+    same = res.iters == dyn.iters
+    assert same.mean() > 0.99
+    assert np.max(np.abs(res.pobj[same] - dyn.pobj[same]) / np.maximum(1.0, np.abs(dyn.pobj[same]))) <= 1e-8
+    _check_batch(prob, res, range(0, 600, 100))
