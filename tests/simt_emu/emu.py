@@ -112,3 +112,15 @@ def solve_lane(c, G_cm, h, cones, lpw=8, order=0, grid_cap=0, max_iter=40, tol=1
     if r != 0:
         raise RuntimeError("no lane-per-problem instantiation takes this layout")
     return dict(x=x, y=np.zeros((B, 0)), z=z, s=s, status=status, iters=iters, pobj=pobj, dobj=dobj)
+
+
+def plan_lane(n, p, cones):
+    """fl_plan (host side of the lane-per-problem kernel) for a layout."""
+    kind = np.array([c[0] for c in cones], dtype=np.int32)
+    offs = np.array([c[1] for c in cones], dtype=np.int32)
+    dim = np.array([c[2] for c in cones], dtype=np.int32)
+    out = np.zeros(24, dtype=np.int32)
+    lib().emu_fused_lane_plan(n, p, int(dim.sum()), len(cones), _i(kind), _i(offs), _i(dim), _i(out))
+    ng = int(out[5])
+    return dict(fits=bool(out[0]), shape=int(out[1]), pps=int(out[2]), smem=int(out[3]), rs=int(out[4]),
+                groups=[(int(out[6 + 2 * i]), int(out[7 + 2 * i])) for i in range(ng)])

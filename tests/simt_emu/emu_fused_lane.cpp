@@ -62,3 +62,13 @@ extern "C" int emu_fused_lane_solve(int n, int k, int ncones, const int* kind, c
     else { FL_RUN(LaneT1, 128) }
     return 0;
 }
+
+// the host-side plan of the lane kernel for a layout: out = fits, shape, pps, smem, rs, #groups, then (count, dim) pairs
+extern "C" int emu_fused_lane_plan(int n, int p, int k, int ncones, const int* kind, const int* offs, const int* dim, int* out) {
+    FLPlan P;
+    fl_plan(P, n, p, k, std::vector<int>(kind, kind + ncones), std::vector<int>(offs, offs + ncones),
+            std::vector<int>(dim, dim + ncones), 227 * 1024, 148);
+    out[0] = P.fits; out[1] = P.shape; out[2] = P.pps; out[3] = (int)P.smem; out[4] = P.jrs; out[5] = (int)P.jgroups.size();
+    for (size_t i = 0; i < P.jgroups.size() && i < 8; ++i) { out[6 + 2 * i] = P.jgroups[i].first; out[7 + 2 * i] = P.jgroups[i].second; }
+    return 0;
+}

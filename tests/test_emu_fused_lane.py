@@ -101,3 +101,20 @@ def test_cones_of_different_dimensions():
     prob = gen.random_feasible(45, 6, 0, cones, 0.3, 0, 5)
     res = emu.solve_lane(prob.c, prob.G_cm, prob.h, oc(prob.cones), lpw=16, grid_cap=1)
     check(prob, res, tol_obj=1e-6, tol_x=1e-4)
+
+
+def test_plan_family_and_specialisation_choice():
+    """fl_plan: C3 has its compile-time instantiation at 96 problems per SM; other layouts of the family are marked for
+    run-time specialisation with their cones grouped by dimension; layouts outside the family are declined."""
+    c3 = [(1, 4 * j, 4) for j in range(10)]
+    pl = emu.plan_lane(12, 0, c3)
+    assert pl["fits"] and pl["shape"] == 1 and pl["pps"] == 96 and pl["smem"] == 96 * 300 * 8
+    mixed = [(0, 0, 3)] + [(1, 3 + 3 * i, 3) for i in range(4)] + [(1, 15 + 5 * i, 5) for i in range(3)] + [(1, 30, 4)]
+    pl = emu.plan_lane(9, 0, mixed)
+    assert pl["fits"] and pl["shape"] == 100 and pl["groups"] == [(4, 3), (3, 5), (1, 4)] and pl["pps"] % 32 == 0
+    assert pl["smem"] <= 227 * 1024
+    assert not emu.plan_lane(9, 1, mixed)["fits"]                                        # equality rows
+    assert not emu.plan_lane(9, 0, [(1, 0, 4), (0, 4, 3)])["fits"]                       # orthant rows after a cone
+    assert not emu.plan_lane(20, 0, [(1, 4 * j, 4) for j in range(10)])["fits"]          # n > 16
+    assert not emu.plan_lane(8, 0, [(1, 0, 12), (1, 12, 12)])["fits"]                    # cone dimension > 8
+    assert not emu.plan_lane(8, 0, [(1, 1, 4), (1, 5, 4)])["fits"]                       # a gap before the first cone
