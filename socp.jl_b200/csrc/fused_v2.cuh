@@ -32,8 +32,11 @@
 // second-order cones of dimension <= 128, at most 64 of them.
 #pragma once
 #include "fused_common.cuh"
+#ifndef __CUDACC_RTC__          // (NVRTC compiles the device code of this file alone: run-time specialisation, lane_jit.cu)
 #include <vector>
 #include <algorithm>
+#include <cstdlib>
+#endif
 
 namespace socp {
 
@@ -46,6 +49,8 @@ struct F2Plan {
     size_t smem = 0;
     int* d_counter = nullptr;
     unsigned long long* d_clk = nullptr;   // 16 phase-cycle counters (SOCP_PHASE_TIMING builds)
+    void* jit_fn = nullptr;                // the kernel specialised for this layout at run time (lane_jit.cu), if any
+    int jit_tried = 0, device = 0;
     // layout
     int n = 0, p = 0, k = 0, kpoc = 0, nsoc = 0, lpc = 1;
     int npad = 0, nb = 0, kpad = 0, ldg = 0, ldh = 0, ppad = 0, pb = 0, ldm = 0;
@@ -59,10 +64,12 @@ struct F2Plan {
     int total = 0;
 };
 
+#ifndef __CUDACC_RTC__
 // kind/offs/dim: the CALLER's cones (POC blocks first).
 inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind, const std::vector<int>& offs,
                     const std::vector<int>& dim, int device) {
     P.fits = false;
+    P.device = device;
     P.n = n; P.p = p; P.k = k;
     P.kpoc = 0; P.nsoc = 0;
     int maxd = 1;
@@ -123,6 +130,8 @@ inline void f2_plan(F2Plan& P, int n, int p, int k, const std::vector<int>& kind
     P.ctas_per_sm = std::max(1, std::min({(int)(per_sm / (P.smem + 1024 + 256)), 2048 / threads, 32, reg_cap}));
     P.fits = true;
 }
+
+#endif  // __CUDACC_RTC__
 
 // ------------------------------------------------------------------------------------------------ SYRK
 // Tile t (row-major over the lower triangle) -> (ti, tj), ti >= tj.
@@ -1054,10 +1063,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_fused2(const F2Args a) {
 using DimsC2 = DimsStatic<8, 50, 1, 50, 1, 51>;
 using DimsC3 = DimsStatic<1, 12, 0, 0, 10, 4>;
 
+#ifndef __CUDACC_RTC__
 template <int NW, int MAXT, int MINB, class D>
 inline void fused2_launch(const F2Plan& plan, const F2Args& args, int grid, cudaStream_t stream) {
     cudaFuncSetAttribute(k_fused2<NW, MAXT, MINB, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
     k_fused2<NW, MAXT, MINB, D><<<grid, NW * 32, plan.smem, stream>>>(args);
+}
+
+// run-time specialisation of the kernel for the plan's layout (lane_jit.cu): DimsStatic per layout instead of DimsDyn
+void* fused2_jit_get(const F2Plan& plan);
+bool fused2_jit_launch(void* fn, const F2Plan& plan, const F2Args& args, int grid, cudaStream_t stream);
+// tries it once per plan (callers outside their timed regions)
+inline void fused2_prepare(F2Plan& plan) {
+    if (plan.jit_tried || !plan.fits) return;
+    plan.jit_tried = 1;
+    if (getenv("SOCP_B200_NO_F2_JIT") || getenv("SOCP_B200_GENERIC_ONLY")) return;
+    plan.jit_fn = fused2_jit_get(plan);
 }
 
 // Solves problems [first, first + batch) of the shard.
@@ -1075,6 +1096,7 @@ inline void solve_fused2(F2Plan& plan, const Ws& g, int first, int batch, int ma
     const int grid = std::min(batch, plan.num_sms * plan.ctas_per_sm);
     if (allow_static && DimsC2::matches(plan)) { fused2_launch<8, 4, 2, DimsC2>(plan, args, grid, stream); return; }
     if (allow_static && DimsC3::matches(plan)) { fused2_launch<1, 3, 16, DimsC3>(plan, args, grid, stream); return; }
+    if (allow_static && plan.jit_fn && fused2_jit_launch(plan.jit_fn, plan, args, grid, stream)) return;
     switch (plan.variant) {
         case 0: fused2_launch<1, 3, 16, DimsDyn>(plan, args, grid, stream); break;     // n <= 16: one warp per problem
         case 1: fused2_launch<4, 3, 4, DimsDyn>(plan, args, grid, stream); break;      // n <= 32: 10 tiles over 4 warps
@@ -1086,5 +1108,7 @@ inline void solve_fused2(F2Plan& plan, const Ws& g, int first, int batch, int ma
 // non-inline entry of solve_fused2, compiled once in fused2.cu (the kernels are instantiated there only)
 void solve_fused2_ext(F2Plan& plan, const Ws& g, int first, int batch, int max_iter, double tol, double step_damp,
                       double init_eps, cudaStream_t stream, bool allow_static, int counter_slot);
+
+#endif  // __CUDACC_RTC__
 
 }  // namespace socp

@@ -7,6 +7,7 @@
 // are missing, or the compilation fails, the caller falls back to fused_v2's one-warp teams.
 #include "fused_lane.cuh"
 #include "fused_v3.cuh"
+#include "fused_v2.cuh"
 #include <dlfcn.h>
 #include <cstdio>
 #include <map>
@@ -162,6 +163,29 @@ void* fused3_jit_get(const F3Plan& P, int teams, int device) {
              minb, P.n, P.p, P.kpoc, P.nsoc, P.soc_dim[0], P.d0, P.kd, P.ident ? 1 : 0);
     return jit_kernel("fused_v3.cuh", inst, device, P.smem * teams);
 }
+// fused_v2's kernel (one-warp teams for n <= 16; what fused_v3 declines) with the layout as compile-time constants
+void* fused2_jit_get(const F2Plan& P) {
+    if (!P.fits || P.nsoc < 1) return nullptr;
+    if (DimsC2::matches(P) || DimsC3::matches(P)) return nullptr;       // instantiated at compile time
+    for (int i = 0; i < P.nsoc; ++i)
+        if (P.soc_dim[i] != P.soc_dim[0] || P.soc_offs[i] != P.kpoc + i * P.soc_dim[0]) return nullptr;
+    if (P.k != P.kpoc + P.nsoc * P.soc_dim[0]) return nullptr;
+    static const int cfg[4][3] = {{1, 3, 16}, {4, 3, 4}, {8, 4, 2}, {8, 5, 2}};      // NW, MAXT, MINB of fused2_launch per variant
+    const int v = P.variant < 0 || P.variant > 3 ? 3 : P.variant;
+    char inst[256];
+    snprintf(inst, sizeof inst, "socp::k_fused2<%d, %d, %d, socp::DimsStatic<%d, %d, %d, %d, %d, %d>>", cfg[v][0], cfg[v][1],
+             cfg[v][2], cfg[v][0], P.n, P.p, P.kpoc, P.nsoc, P.soc_dim[0]);
+    return jit_kernel("fused_v2.cuh", inst, P.device, P.smem);
+}
+bool fused2_jit_launch(void* fn, const F2Plan& plan, const F2Args& args, int grid, cudaStream_t stream) {
+    Api& a = api();
+    if (!a.ok || !fn) return false;
+    F2Args copy = args;
+    void* params[] = {&copy};
+    return a.LaunchKernel(reinterpret_cast<CUfunction_t>(fn), (unsigned)grid, 1, 1, (unsigned)(plan.nw * 32), 1, 1,
+                          (unsigned)plan.smem, stream, params, nullptr) == 0;
+}
+
 bool fused3_jit_launch(void* fn, const F3Plan& plan, const F3Args& args, int teams, int grid, cudaStream_t stream) {
     Api& a = api();
     if (!a.ok || !fn) return false;

@@ -866,7 +866,11 @@ int fused_kind(const socp_handle* h, Shard& sh) {
     if (sh.fused2.fits) {
         if (!sh.sing_known) ensure_prepared(sh);       // fused_v2 cannot take sing problems: the flags must be known
         if (!sh.prepared) ensure_prepared(sh);
-        if (!sh.any_sing) return lane_wanted(sh, sh.batch) ? FUSED_LANE : FUSED_V2;
+        if (!sh.any_sing) {
+            if (lane_wanted(sh, sh.batch)) return FUSED_LANE;
+            fused2_prepare(sh.fused2);          // the kernel specialised for this layout, once per plan (NVRTC)
+            return FUSED_V2;
+        }
     }
     return FUSED_NONE;
 }
@@ -1005,6 +1009,7 @@ bool run_pipelined(socp_handle* h, Shard& sh, const socp_params& prm, const doub
     const bool v3 = f3_candidate(h);
     const bool lane = !v3 && lane_wanted(sh, B);
     if (lane) ensure_lane_ws(sh);
+    else if (!v3) fused2_prepare(sh.fused2);
     sh.sharedA = (flags & SOCP_FLAG_SHARED_A) != 0;
     sh.sharedG = (flags & SOCP_FLAG_SHARED_G) != 0;
     sh.w.sA = sh.sharedA ? 0 : (int64_t)p * n;

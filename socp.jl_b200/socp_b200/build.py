@@ -21,7 +21,7 @@ UNITS = {
     "fused3.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
     "fused3_dyn.cu": ["common.cuh", "fused_common.cuh", "fused_v3.cuh"],
     "fused_lane.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh", "fused_lane_dev.cuh"],
-    "lane_jit.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh", "fused_lane_dev.cuh", "fused_v3.cuh"],
+    "lane_jit.cu": ["common.cuh", "fused_common.cuh", "fused_lane.cuh", "fused_lane_dev.cuh", "fused_v3.cuh", "fused_v2.cuh"],
     "syrk_tma.cu": ["common.cuh", "syrk_tma.cuh"],
 }
 

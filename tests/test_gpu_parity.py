@@ -869,3 +869,32 @@ def test_fused3_specialised_at_run_time():
     assert same.mean() > 0.99
     assert np.max(np.abs(res.pobj[same] - dyn.pobj[same]) / np.maximum(1.0, np.abs(dyn.pobj[same]))) <= 1e-8
     _check_batch(prob, res, range(0, 600, 100))
+
+
+def test_fused2_specialised_at_run_time():
+    """A tiny layout with equality rows (n = 12, p = 3, ten SOC(4): not the lane kernel's family): the one-warp-team
+    kernel of fused_v2.cuh gets the layout as compile-time constants through NVRTC -- against its runtime-dimension
+    instantiation on the whole batch (the two differ in rounding only: a handful of the ~0.02 % of problems that do not
+    converge may change status) and against the numpy oracle on a sample."""
+    cones = [sb.SOC(4 * i, 4) for i in range(10)]
+    prob = gen.random_feasible(2000, 12, 3, cones, 0.3, 0, 31)
+    run = lambda: sb.solve_socp_batch(prob, sb.SolverState(prob))
+    res = _with_env("SOCP_B200_JIT_VERBOSE", "1", run)
+    dyn = _with_env("SOCP_B200_NO_F2_JIT", "1", run)
+    assert res.timings["path_used"] == sb.PATH_FUSED
+    assert (res.status == dyn.status).mean() >= 0.998
+    conv = (res.status == sb.STATUS_CONVERGED) & (dyn.status == sb.STATUS_CONVERGED)
+    assert conv.mean() > 0.99
+    assert np.all(np.abs(res.iters.astype(int) - dyn.iters.astype(int))[conv] <= 1)
+    same = conv & (res.iters == dyn.iters)
+    assert same.mean() > 0.98
+    assert np.quantile(np.abs(res.pobj[same] - dyn.pobj[same]) / np.maximum(1.0, np.abs(dyn.pobj[same])), 0.99) <= 1e-8
+    # the numpy oracle on a sample; objectives to 1e-6 as for the other randomly generated families with equality rows
+    # (the two oracles themselves differ by more than 1e-8 on some of these problems, see test_fused_generic_layouts_*)
+    for q in [q for q in range(0, 2000, 200) if same[q]][:6]:
+        pr = so.Problem.create(prob.c[q], prob.A_dense(q), prob.b[q], prob.G_dense(q), prob.h[q], ocones(prob.cones), sing=False)
+        ref = so.solve_socp(pr, init="reduced", fast_iprod=True)
+        assert res.status[q] == ref.status and abs(int(res.iters[q]) - ref.iters) <= 1
+        if res.iters[q] == ref.iters:
+            assert abs(res.pobj[q] - ref.pobj) <= 1e-6 * max(1.0, abs(ref.pobj))
+            assert abs(res.dobj[q] - ref.dobj) <= 1e-6 * max(1.0, abs(ref.dobj))
